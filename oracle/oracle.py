@@ -115,13 +115,14 @@ class OracleEnv(object):
     def _new_obs(self):
         return np.zeros((self.B,) + self.cfg.obs_shape, dtype=np.uint8)
 
-    def step(self, actions, action_order=None, tape=None, render=True):
-        """tape = dict(move_order u8[B,N], uniforms f64[B,K], waste_order u16[B,nw] or None)."""
+    def step(self, actions, action_order=None, tape=None, render=True, obs_out=None):
+        """tape = dict(move_order u8[B,N], uniforms f64[B,K], waste_order u16[B,nw] or None).
+        obs_out: optional preallocated uint8 buffer (the timed baseline reuses one)."""
         cfg, B, N = self.cfg, self.B, self.cfg.num_agents
         actions = _chk(np.ascontiguousarray(actions, dtype=np.int8), np.int8, (B, N))
         if action_order is not None:
             action_order = _chk(np.ascontiguousarray(action_order, dtype=np.uint8), np.uint8, (B, N))
-        obs = self._new_obs() if render else None
+        obs = (obs_out if obs_out is not None else self._new_obs()) if render else None
         rew = np.zeros((B, N), dtype=np.int32)
         tp, keep = None, []
         if tape is not None:

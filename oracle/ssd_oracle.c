@@ -247,7 +247,7 @@ static void fire_beam(const OrcEnv* e, uint8_t* grid, const Cell* pos, const uin
 /* HarvestEnv.spawn_apples harvest.py:75-104 (3x3 window: j*j + k*k <= 2) */
 static void harvest_spawn(const OrcEnv* e, uint8_t* grid, const Cell* pos, Draws* d, int64_t* st) {
     const int H = e->H, W = e->W;
-    int16_t* newp = (int16_t*)malloc(sizeof(int16_t) * (e->n_apple + 1));
+    int16_t newp[e->n_apple + 1]; /* VLA: no allocator traffic on the threaded baseline */
     int n_new = 0;
     for (int i = 0; i < e->n_apple; ++i) {
         Cell p = {e->apple_pts[2 * i], e->apple_pts[2 * i + 1]};
@@ -260,7 +260,6 @@ static void harvest_spawn(const OrcEnv* e, uint8_t* grid, const Cell* pos, Draws
         if (draw_less(e, d, e->harvest_prob[n < 3 ? n : 3])) newp[n_new++] = (int16_t)(p.r * W + p.c);
     }
     for (int i = 0; i < n_new; ++i) { grid[newp[i]] = 'A'; st[6]++; } /* harvest.py:72-73 */
-    free(newp);
 }
 
 /* CleanupEnv.custom_map_update cleanup.py:113-179 */
@@ -270,7 +269,7 @@ static void cleanup_spawn(const OrcEnv* e, uint8_t* grid, const Cell* pos, Draws
     for (int i = 0; i < e->H * e->W; ++i) h += grid[i] == 'H'; /* compute_permitted_area :173-179 */
     if (h > e->area) h = e->area;
     double apple_p = e->apple_prob[h], waste_p = e->waste_prob[h]; /* compute_probabilities :156-171 */
-    int16_t* newp = (int16_t*)malloc(sizeof(int16_t) * (e->n_apple + 2));
+    int16_t newp[e->n_apple + 2];
     int n_new = 0, waste_cell = -1;
     for (int i = 0; i < e->n_apple; ++i) { /* :135-141 */
         Cell p = {e->apple_pts[2 * i], e->apple_pts[2 * i + 1]};
@@ -287,7 +286,7 @@ static void cleanup_spawn(const OrcEnv* e, uint8_t* grid, const Cell* pos, Draws
         } else {
             /* random.shuffle replacement: canonical points ordered by (32-bit key, index) */
             int n = e->n_waste;
-            uint64_t* keyed = (uint64_t*)malloc(sizeof(uint64_t) * n);
+            uint64_t keyed[n];
             for (int i = 0; i < n; ++i) keyed[i] = ((uint64_t)px_word(d, STREAM_WASTE, (uint32_t)i) << 32) | (uint32_t)i;
             for (int i = 1; i < n; ++i) { uint64_t kx = keyed[i]; int j = i - 1; while (j >= 0 && keyed[j] > kx) { keyed[j + 1] = keyed[j]; --j; } keyed[j + 1] = kx; }
             for (int i = 0; i < n; ++i) {
@@ -295,12 +294,10 @@ static void cleanup_spawn(const OrcEnv* e, uint8_t* grid, const Cell* pos, Draws
                 int idx = e->waste_pts[2 * w] * W + e->waste_pts[2 * w + 1];
                 if (grid[idx] != 'H' && draw_less(e, d, waste_p)) { waste_cell = idx; break; }
             }
-            free(keyed);
         }
     }
     for (int i = 0; i < n_new; ++i) { grid[newp[i]] = 'A'; st[6]++; } /* :116 update_map */
     if (waste_cell >= 0) { grid[waste_cell] = 'H'; st[7]++; }
-    free(newp);
 }
 
 /* ------------------------------------------------------------------ rendering */
@@ -314,7 +311,7 @@ static uint8_t agent_char(int i) { /* str(int(agent_id[-1]) + 1) stored into a <
 static void render(const OrcEnv* e, const uint8_t* grid, const Cell* pos, const uint8_t* ori,
                    const BeamList* beams, int rotate, uint8_t* obs) {
     const int H = e->H, W = e->W, N = e->N, r = e->r, V = e->V;
-    uint8_t* ov = (uint8_t*)malloc((size_t)H * W);
+    uint8_t ov[H * W];
     memcpy(ov, grid, (size_t)H * W);
     for (int a = 0; a < N; ++a)
         if (pos[a].r >= 0 && pos[a].r < H && pos[a].c >= 0 && pos[a].c < W) ov[pos[a].r * W + pos[a].c] = agent_char(a);
@@ -337,7 +334,6 @@ static void render(const OrcEnv* e, const uint8_t* grid, const Cell* pos, const 
                 o[(i * V + j) * 3 + 0] = rgb[0]; o[(i * V + j) * 3 + 1] = rgb[1]; o[(i * V + j) * 3 + 2] = rgb[2];
             }
     }
-    free(ov);
 }
 
 /* ------------------------------------------------------------------ one env step, map_env.py:152-212 */

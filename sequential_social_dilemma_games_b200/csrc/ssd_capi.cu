@@ -1,0 +1,495 @@
+// C-ABI host layer of libssd_b200 (include/ssd_b200.h): handle management, static tables,
+// shared-memory carve-up, launch plumbing.  No torch types, no exceptions across the boundary.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "ssd_internal.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t e_ = (expr);                                                               \
+        if (e_ != cudaSuccess) return fail(SSD_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
+    } while (0)
+
+uint32_t up16(uint32_t x) { return (x + 15u) & ~15u; }
+
+// u < p for u = k / 2^53  <=>  k < ceil(p * 2^53); p * 2^53 is an exact scaling of a double.
+uint64_t threshold53(double p) {
+    if (!(p > 0.0)) return 0;
+    if (p >= 1.0) return 1ull << 53;
+    return static_cast<uint64_t>(std::ceil(std::ldexp(p, 53)));
+}
+
+}  // namespace
+
+struct SsdEnv {
+    SsdConfig cfg{};
+    int B = 0, B_pad = 0, E = 0, threads = 128;
+    int HW = 0, cell_stride = 0, V = 0, obs_env = 0, n_apple = 0, n_waste = 0, n_spawn = 0;
+    uint64_t seed = 0;
+    uint32_t t = 0;
+    int64_t launches = 0;
+    ssd::SmemLayout L{};
+    // device allocations
+    std::vector<void*> allocs;
+    uint32_t* d_wall = nullptr; uint16_t* d_apple = nullptr; uint8_t* d_apple_nb = nullptr;
+    uint16_t* d_waste = nullptr; uint16_t* d_spawn = nullptr; uint32_t* d_color = nullptr;
+    uint64_t* d_hthr = nullptr; double* d_hp = nullptr;
+    uint64_t* d_athr = nullptr; double* d_ap = nullptr; uint64_t* d_wthr = nullptr; double* d_wp = nullptr;
+    uint8_t* d_init_grid = nullptr;
+    uint8_t* d_grid = nullptr; uint32_t* d_agents = nullptr; uint32_t* d_beam_buf = nullptr; int32_t* d_beam_cnt = nullptr;
+    unsigned long long* d_stats = nullptr;
+    // ssd_step_host plumbing
+    cudaStream_t hs[2] = {nullptr, nullptr};
+    int8_t* d_act_stage = nullptr; uint8_t* d_obs_stage = nullptr; int32_t* d_rew_stage = nullptr;
+    // staging for host-pointer set/get state
+    uint8_t* d_io_grid = nullptr; int16_t* d_io_pos = nullptr; uint8_t* d_io_ori = nullptr;
+
+    template <typename T>
+    int alloc(T** p, size_t n) {
+        void* q = nullptr;
+        if (cudaMalloc(&q, n * sizeof(T) > 0 ? n * sizeof(T) : 16) != cudaSuccess) return -1;
+        allocs.push_back(q);
+        *p = static_cast<T*>(q);
+        return 0;
+    }
+    template <typename T>
+    int upload(T** p, const std::vector<T>& v) {
+        if (alloc(p, v.size())) return -1;
+        if (!v.empty() && cudaMemcpy(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) return -1;
+        return 0;
+    }
+};
+
+namespace {
+
+bool is_device_ptr(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+ssd::SmemLayout make_layout(const SsdEnv& h, int E, int threads) {
+    ssd::SmemLayout L{};
+    uint32_t off = 0;
+    L.mbar = off; off += 16;
+    L.img = off; off += up16(static_cast<uint32_t>(E) * h.obs_env) + 16;
+    L.grid = off; off += static_cast<uint32_t>(E) * h.cell_stride;
+    L.wall = off; off += up16(((h.HW + 31) / 32) * 4);
+    L.color = off; off += 512;
+    L.apple = off; off += up16(h.n_apple * 2);
+    L.apple_nb = off; off += up16(h.n_apple);
+    L.env = off; off += static_cast<uint32_t>(E) * sizeof(ssd::EnvScratch);
+    L.max_beams = static_cast<uint32_t>(h.cfg.num_agents) * 3 * h.cfg.beam_len;
+    L.beams = off; off += up16(static_cast<uint32_t>(E) * L.max_beams * 4);
+    L.list_stride = up16(std::max(h.n_apple * 2, h.n_waste * 4));
+    L.list = off; off += (threads / 32) * L.list_stride;
+    L.stats = off; off += 32;
+    L.total = off;
+    return L;
+}
+
+void fill_args(SsdEnv* h, ssd::StepArgs& a) {
+    memset(&a, 0, sizeof a);
+    const SsdConfig& c = h->cfg;
+    a.kind = c.kind; a.H = c.height; a.W = c.width; a.N = c.num_agents; a.r = c.view_radius; a.V = h->V;
+    a.beam_len = c.beam_len; a.HW = h->HW; a.cell_stride = h->cell_stride;
+    a.n_apple = h->n_apple; a.n_waste = h->n_waste; a.area = c.potential_waste_area;
+    a.obs_env = h->obs_env;
+    a.nv_magic = static_cast<uint32_t>((1ull << 32) / static_cast<uint32_t>(a.N * a.V) + 1);
+    a.E = h->E; a.env_begin = 0; a.env_end = h->B;
+    a.phases = SSD_PHASE_ALL; a.rotate = 1; a.spawn_stream = ssd::STREAM_SPAWN;
+    a.key0 = static_cast<uint32_t>(h->seed); a.key1 = static_cast<uint32_t>(h->seed >> 32); a.t = h->t;
+    a.env_id0 = c.env_id_offset;
+    a.L = h->L;
+    a.wall_bits = h->d_wall; a.apple_cell = h->d_apple; a.apple_nb = h->d_apple_nb; a.waste_cell = h->d_waste;
+    a.color = h->d_color; a.harvest_thr = h->d_hthr; a.harvest_p = h->d_hp;
+    a.apple_thr = h->d_athr; a.apple_p = h->d_ap; a.waste_thr = h->d_wthr; a.waste_p = h->d_wp;
+    a.grid = h->d_grid; a.agents = h->d_agents; a.beam_buf = h->d_beam_buf; a.beam_cnt = h->d_beam_cnt;
+    a.stats = h->d_stats;
+}
+
+int check_handle(ssd_handle h) { return h ? 0 : fail(SSD_ERR_INVALID, "null handle"); }
+
+}  // namespace
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+const char* ssd_last_error(void) { return g_err; }
+int ssd_abi_version(void) { return SSD_ABI_VERSION; }
+
+int ssd_create(const SsdConfig* cfg, ssd_handle* out) {
+    if (!cfg || !out) return fail(SSD_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (cfg->abi_version != SSD_ABI_VERSION) return fail(SSD_ERR_INVALID, "ABI version mismatch: caller %d, library %d", cfg->abi_version, SSD_ABI_VERSION);
+    const int H = cfg->height, W = cfg->width, N = cfg->num_agents;
+    if (cfg->kind < 0 || cfg->kind > SSD_KIND_PLAIN) return fail(SSD_ERR_INVALID, "unknown kind %d", cfg->kind);
+    if (H < 3 || W < 3 || H > 255 || W > 255) return fail(SSD_ERR_INVALID, "map shape %dx%d outside 3..255", H, W);
+    if (N < 1 || N > SSD_MAX_AGENTS) return fail(SSD_ERR_INVALID, "num_agents %d outside 1..%d", N, SSD_MAX_AGENTS);
+    if (cfg->view_radius < 0 || cfg->view_radius > 31) return fail(SSD_ERR_INVALID, "view_radius %d outside 0..31", cfg->view_radius);
+    if (cfg->beam_len < 0 || cfg->beam_len > 32) return fail(SSD_ERR_INVALID, "beam_len %d outside 0..32", cfg->beam_len);
+    if (cfg->num_envs < 1) return fail(SSD_ERR_INVALID, "num_envs must be positive");
+    if (!cfg->base_map || !cfg->color_lut) return fail(SSD_ERR_INVALID, "base_map and color_lut are required");
+    if (cfg->kind == SSD_KIND_HARVEST && !cfg->harvest_spawn_prob) return fail(SSD_ERR_INVALID, "harvest_spawn_prob is required");
+    if (cfg->kind == SSD_KIND_CLEANUP && (!cfg->cleanup_apple_prob || !cfg->cleanup_waste_prob || cfg->potential_waste_area < 0))
+        return fail(SSD_ERR_INVALID, "cleanup probability tables are required");
+    for (int r = 0; r < H; ++r)
+        for (int c = 0; c < W; ++c) {
+            const uint8_t ch = cfg->base_map[r * W + c];
+            if (ch >= 128) return fail(SSD_ERR_INVALID, "map characters must be 7-bit ASCII");
+            if ((r == 0 || c == 0 || r == H - 1 || c == W - 1) && ch != '@')
+                return fail(SSD_ERR_INVALID, "the map must be enclosed by '@' walls (cell %d,%d): the reference indexes grid[new_row, new_col] unchecked (agent.py:111)", r, c);
+        }
+    // "There are not enough spawn points!" (map_env.py:661)
+    {
+        std::vector<int> seen;
+        for (int s = 0; s < cfg->num_spawn_points; ++s) {
+            const int r = cfg->spawn_points[2 * s], c = cfg->spawn_points[2 * s + 1];
+            if (r < 0 || r >= H || c < 0 || c >= W) return fail(SSD_ERR_INVALID, "spawn point %d outside the map", s);
+            const int key = r * W + c;
+            bool dup = false;
+            for (int k : seen) dup |= (k == key);
+            if (!dup) seen.push_back(key);
+        }
+        if (cfg->num_spawn_points > 0 && static_cast<int>(seen.size()) < N)
+            return fail(SSD_ERR_INVALID, "There are not enough spawn points! Check your map? (%d distinct, %d agents; map_env.py:661)", static_cast<int>(seen.size()), N);
+    }
+    CUDA_TRY(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major < 10) return fail(SSD_ERR_UNSUPPORTED, "libssd_b200 is built for sm_100a only; device %d is sm_%d%d", cfg->device, prop.major, prop.minor);
+
+    SsdEnv* h = new (std::nothrow) SsdEnv();
+    if (!h) return fail(SSD_ERR_INVALID, "out of host memory");
+    h->cfg = *cfg;
+    h->B = cfg->num_envs; h->HW = H * W; h->cell_stride = static_cast<int>(up16(h->HW));
+    h->V = 2 * cfg->view_radius + 1; h->obs_env = N * h->V * h->V * 3;
+
+    // static tables
+    std::vector<uint32_t> wall((h->HW + 31) / 32, 0), color(128, 0);
+    std::vector<uint16_t> apple, waste, spawn;
+    std::vector<uint8_t> apple_nb, init_grid(h->cell_stride, 0);
+    const uint8_t apple_ch = cfg->kind == SSD_KIND_HARVEST ? 'A' : (cfg->kind == SSD_KIND_CLEANUP ? 'B' : 0);
+    for (int r = 0; r < H; ++r)
+        for (int c = 0; c < W; ++c) {
+            const int i = r * W + c;
+            const uint8_t ch = cfg->base_map[i];
+            uint8_t g = ' ';  // reset_map + build_walls + custom_reset (map_env.py:560-564, harvest.py:57-60, cleanup.py:84-92)
+            if (ch == '@') { wall[i >> 5] |= 1u << (i & 31); g = '@'; }
+            else if (cfg->kind == SSD_KIND_HARVEST && ch == 'A') g = 'A';
+            else if (cfg->kind == SSD_KIND_CLEANUP && (ch == 'H' || ch == 'R' || ch == 'S')) g = ch;
+            init_grid[i] = g;
+            if (apple_ch && ch == apple_ch) {
+                apple.push_back(static_cast<uint16_t>(i));
+                uint8_t m = 0;
+                int bit = 0;
+                for (int dr = -1; dr <= 1; ++dr)
+                    for (int dc = -1; dc <= 1; ++dc) {
+                        if (dr == 0 && dc == 0) continue;
+                        if (r + dr >= 0 && r + dr < H && c + dc >= 0 && c + dc < W) m |= 1u << bit;
+                        ++bit;
+                    }
+                apple_nb.push_back(m);
+            }
+            if (cfg->kind == SSD_KIND_CLEANUP && (ch == 'H' || ch == 'R')) waste.push_back(static_cast<uint16_t>(i));
+        }
+    for (int s = 0; s < cfg->num_spawn_points; ++s)
+        spawn.push_back(static_cast<uint16_t>(cfg->spawn_points[2 * s] << 8 | cfg->spawn_points[2 * s + 1]));
+    for (int i = 0; i < 128; ++i)
+        color[i] = cfg->color_lut[3 * i] | cfg->color_lut[3 * i + 1] << 8 | cfg->color_lut[3 * i + 2] << 16;
+    h->n_apple = static_cast<int>(apple.size()); h->n_waste = static_cast<int>(waste.size()); h->n_spawn = static_cast<int>(spawn.size());
+    if (h->n_apple >= 0x8000) { delete h; return fail(SSD_ERR_UNSUPPORTED, "too many apple points"); }
+    if (cfg->kind == SSD_KIND_CLEANUP && cfg->potential_waste_area < h->n_waste) {
+        delete h;
+        return fail(SSD_ERR_INVALID, "potential_waste_area %d smaller than the number of 'H'/'R' cells %d", cfg->potential_waste_area, h->n_waste);
+    }
+    std::vector<uint64_t> hthr(4, 0), athr, wthr;
+    std::vector<double> hp(4, 0.0), ap, wp;
+    if (cfg->harvest_spawn_prob)
+        for (int i = 0; i < 4; ++i) { hp[i] = cfg->harvest_spawn_prob[i]; hthr[i] = threshold53(hp[i]); }
+    const int area = cfg->kind == SSD_KIND_CLEANUP ? cfg->potential_waste_area : 0;
+    for (int i = 0; i <= area; ++i) {
+        const double pa = cfg->kind == SSD_KIND_CLEANUP ? cfg->cleanup_apple_prob[i] : 0.0;
+        const double pw = cfg->kind == SSD_KIND_CLEANUP ? cfg->cleanup_waste_prob[i] : 0.0;
+        ap.push_back(pa); athr.push_back(threshold53(pa)); wp.push_back(pw); wthr.push_back(threshold53(pw));
+    }
+
+    // envs per CTA: the largest of {16, 8, 4, 2, 1} whose tile fits; prefer >= 2 resident CTAs per SM
+    const int smem_max = static_cast<int>(prop.sharedMemPerBlockOptin);
+    const int smem_sm = static_cast<int>(prop.sharedMemPerMultiprocessor);
+    int E = cfg->envs_per_cta;
+    if (E != 0 && E != 1 && E != 2 && E != 4 && E != 8 && E != 16) { delete h; return fail(SSD_ERR_INVALID, "envs_per_cta must be 0, 1, 2, 4, 8 or 16"); }
+    if (E == 0) {
+        for (E = 16; E > 1; E >>= 1)
+            if (static_cast<int>(make_layout(*h, E, 128).total) <= smem_max) break;
+    }
+    h->E = E;
+    h->L = make_layout(*h, E, 128);
+    h->threads = 128;
+    if (static_cast<int>(h->L.total) + 1024 > smem_sm / 2) {  // a single resident CTA: give it more warps
+        h->threads = 256;
+        h->L = make_layout(*h, E, 256);
+    }
+    if (static_cast<int>(h->L.total) > smem_max) {
+        const unsigned need = h->L.total;
+        delete h;
+        return fail(SSD_ERR_UNSUPPORTED, "one environment needs %u bytes of shared memory (limit %d)", need, smem_max);
+    }
+    h->B_pad = (h->B + E - 1) / E * E;
+
+    int bad = 0;
+    bad |= h->upload(&h->d_wall, wall); bad |= h->upload(&h->d_apple, apple); bad |= h->upload(&h->d_apple_nb, apple_nb);
+    bad |= h->upload(&h->d_waste, waste); bad |= h->upload(&h->d_spawn, spawn); bad |= h->upload(&h->d_color, color);
+    bad |= h->upload(&h->d_hthr, hthr); bad |= h->upload(&h->d_hp, hp); bad |= h->upload(&h->d_athr, athr);
+    bad |= h->upload(&h->d_ap, ap); bad |= h->upload(&h->d_wthr, wthr); bad |= h->upload(&h->d_wp, wp);
+    bad |= h->upload(&h->d_init_grid, init_grid);
+    bad |= h->alloc(&h->d_grid, static_cast<size_t>(h->B_pad) * h->cell_stride);
+    bad |= h->alloc(&h->d_agents, static_cast<size_t>(h->B_pad) * N);
+    bad |= h->alloc(&h->d_beam_buf, static_cast<size_t>(h->B_pad) * h->L.max_beams);
+    bad |= h->alloc(&h->d_beam_cnt, static_cast<size_t>(h->B_pad));
+    bad |= h->alloc(&h->d_stats, static_cast<size_t>(SSD_NUM_STATS));
+    if (bad) { const char* m = cudaGetErrorString(cudaGetLastError()); ssd_destroy(h); return fail(SSD_ERR_CUDA, "device allocation failed: %s", m); }
+    // initial state: post-reset_map grid, agents parked on the first spawn point (or cell 1,1)
+    {
+        std::vector<uint8_t> g(static_cast<size_t>(h->B_pad) * h->cell_stride);
+        for (int b = 0; b < h->B_pad; ++b) memcpy(g.data() + static_cast<size_t>(b) * h->cell_stride, init_grid.data(), h->cell_stride);
+        const uint32_t park = spawn.empty() ? (1u | 1u << 8) : ((spawn[0] >> 8) | (spawn[0] & 255u) << 8);
+        std::vector<uint32_t> ag(static_cast<size_t>(h->B_pad) * N, park);
+        cudaError_t e1 = cudaMemcpy(h->d_grid, g.data(), g.size(), cudaMemcpyHostToDevice);
+        cudaError_t e2 = cudaMemcpy(h->d_agents, ag.data(), ag.size() * 4, cudaMemcpyHostToDevice);
+        cudaError_t e3 = cudaMemset(h->d_stats, 0, SSD_NUM_STATS * sizeof(unsigned long long));
+        cudaError_t e4 = cudaMemset(h->d_beam_cnt, 0, static_cast<size_t>(h->B_pad) * 4);
+        if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess) {
+            ssd_destroy(h);
+            return fail(SSD_ERR_CUDA, "state initialisation failed");
+        }
+    }
+    *out = h;
+    return SSD_OK;
+}
+
+int ssd_destroy(ssd_handle h) {
+    if (!h) return SSD_OK;
+    cudaSetDevice(h->cfg.device);
+    for (int i = 0; i < 2; ++i) if (h->hs[i]) cudaStreamDestroy(h->hs[i]);
+    for (void* p : h->allocs) cudaFree(p);
+    delete h;
+    return SSD_OK;
+}
+
+int ssd_num_apple_points(ssd_handle h) { return h ? h->n_apple : -1; }
+int ssd_num_waste_points(ssd_handle h) { return h ? h->n_waste : -1; }
+int64_t ssd_obs_bytes_per_env(ssd_handle h) { return h ? h->obs_env : -1; }
+int ssd_envs_per_cta(ssd_handle h) { return h ? h->E : -1; }
+int64_t ssd_launch_count(ssd_handle h) { return h ? h->launches : -1; }
+
+int64_t ssd_algorithmic_bytes_per_env_step(ssd_handle h) {
+    if (!h) return -1;
+    // grid read+write, agent state 8 B read+write, actions, rewards, observations.
+    // (The reference's persistent waste order carries no information under either replay mode and
+    // is not device state, so its 4*n_waste term is not counted.)
+    const int64_t N = h->cfg.num_agents;
+    return 2ll * h->HW + 16 * N + N + 4 * N + h->obs_env;
+}
+
+int ssd_seed(ssd_handle h, uint64_t seed, uint32_t t) {
+    if (check_handle(h)) return SSD_ERR_INVALID;
+    h->seed = seed; h->t = t;
+    return SSD_OK;
+}
+int ssd_get_counter(ssd_handle h, uint32_t* t) {
+    if (check_handle(h) || !t) return SSD_ERR_INVALID;
+    *t = h->t;
+    return SSD_OK;
+}
+
+int ssd_set_state(ssd_handle h, const uint8_t* grid, const int16_t* pos, const uint8_t* ori, void* stream) {
+    if (check_handle(h)) return SSD_ERR_INVALID;
+    if (!grid || !pos || !ori) return fail(SSD_ERR_INVALID, "grid, pos and ori are required");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int N = h->cfg.num_agents;
+    const size_t ng = static_cast<size_t>(h->B) * h->HW, np = static_cast<size_t>(h->B) * N;
+    if (!is_device_ptr(grid) || !is_device_ptr(pos) || !is_device_ptr(ori)) {
+        if (!h->d_io_grid) {
+            if (h->alloc(&h->d_io_grid, ng) || h->alloc(&h->d_io_pos, np * 2) || h->alloc(&h->d_io_ori, np))
+                return fail(SSD_ERR_CUDA, "staging allocation failed");
+        }
+        CUDA_TRY(cudaMemcpyAsync(h->d_io_grid, grid, ng, cudaMemcpyDefault, st));
+        CUDA_TRY(cudaMemcpyAsync(h->d_io_pos, pos, np * 2 * sizeof(int16_t), cudaMemcpyDefault, st));
+        CUDA_TRY(cudaMemcpyAsync(h->d_io_ori, ori, np, cudaMemcpyDefault, st));
+        grid = h->d_io_grid; pos = h->d_io_pos; ori = h->d_io_ori;
+    }
+    CUDA_TRY(ssd::launch_pack_state(h->B, N, h->HW, h->cell_stride, grid, pos, ori, h->d_grid, h->d_agents, st));
+    h->launches++;
+    return SSD_OK;
+}
+
+int ssd_get_state(ssd_handle h, uint8_t* grid, int16_t* pos, uint8_t* ori, void* stream) {
+    if (check_handle(h)) return SSD_ERR_INVALID;
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int N = h->cfg.num_agents;
+    const size_t ng = static_cast<size_t>(h->B) * h->HW, np = static_cast<size_t>(h->B) * N;
+    const bool dev = (!grid || is_device_ptr(grid)) && (!pos || is_device_ptr(pos)) && (!ori || is_device_ptr(ori));
+    if (dev) {
+        CUDA_TRY(ssd::launch_unpack_state(h->B, N, h->HW, h->cell_stride, h->d_grid, h->d_agents, grid, pos, ori, st));
+        h->launches++;
+        return SSD_OK;
+    }
+    if (!h->d_io_grid) {
+        if (h->alloc(&h->d_io_grid, ng) || h->alloc(&h->d_io_pos, np * 2) || h->alloc(&h->d_io_ori, np))
+            return fail(SSD_ERR_CUDA, "staging allocation failed");
+    }
+    CUDA_TRY(ssd::launch_unpack_state(h->B, N, h->HW, h->cell_stride, h->d_grid, h->d_agents, h->d_io_grid, h->d_io_pos, h->d_io_ori, st));
+    h->launches++;
+    if (grid) CUDA_TRY(cudaMemcpyAsync(grid, h->d_io_grid, ng, cudaMemcpyDefault, st));
+    if (pos) CUDA_TRY(cudaMemcpyAsync(pos, h->d_io_pos, np * 2 * sizeof(int16_t), cudaMemcpyDefault, st));
+    if (ori) CUDA_TRY(cudaMemcpyAsync(ori, h->d_io_ori, np, cudaMemcpyDefault, st));
+    CUDA_TRY(cudaStreamSynchronize(st));  // host destinations are complete on return
+    return SSD_OK;
+}
+
+int ssd_reset(ssd_handle h, const uint8_t* mask, uint8_t* obs_out, void* stream) {
+    if (check_handle(h)) return SSD_ERR_INVALID;
+    if (h->n_spawn == 0) return fail(SSD_ERR_INVALID, "the map has no 'P' spawn points");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ssd::ResetArgs r{};
+    r.N = h->cfg.num_agents; r.n_spawn = h->n_spawn; r.cell_stride = h->cell_stride; r.env_end = h->B;
+    r.key0 = static_cast<uint32_t>(h->seed); r.key1 = static_cast<uint32_t>(h->seed >> 32); r.t = h->t;
+    r.env_id0 = h->cfg.env_id_offset;
+    r.spawn_key = h->d_spawn; r.init_grid = h->d_init_grid; r.mask = mask; r.grid = h->d_grid; r.agents = h->d_agents;
+    CUDA_TRY(ssd::launch_reset(r, st));
+    ssd::StepArgs a;
+    fill_args(h, a);
+    a.phases = SSD_PHASE_SPAWN | (obs_out ? SSD_PHASE_RENDER : 0);  // custom_map_update + un-rotated render (map_env.py:230-248)
+    a.rotate = 0; a.spawn_stream = ssd::STREAM_RSPAWN; a.mask = mask; a.obs = obs_out;
+    CUDA_TRY(ssd::launch_step(a, h->threads, st));
+    h->launches += 2;
+    return SSD_OK;
+}
+
+int ssd_step_phases(ssd_handle h, int phases, const int8_t* actions, const uint8_t* action_order, const SsdTape* tape,
+                    uint8_t* obs_out, int32_t* reward_out, void* stream) {
+    if (check_handle(h)) return SSD_ERR_INVALID;
+    if ((phases & ~SSD_PHASE_ALL) || phases == 0) return fail(SSD_ERR_INVALID, "bad phase mask %d", phases);
+    if ((phases & (SSD_PHASE_MOVES | SSD_PHASE_BEAMS)) && !actions) return fail(SSD_ERR_INVALID, "actions are required");
+    if (tape && h->cfg.kind == SSD_KIND_CLEANUP && !tape->waste_order && (phases & SSD_PHASE_SPAWN))
+        return fail(SSD_ERR_INVALID, "tape.waste_order is required for Cleanup");
+    if (tape && (!tape->move_order || !tape->uniforms)) return fail(SSD_ERR_INVALID, "tape.move_order and tape.uniforms are required");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    ssd::StepArgs a;
+    fill_args(h, a);
+    a.phases = phases;
+    a.use_beam_buf = phases != SSD_PHASE_ALL;
+    a.rew_accumulate = phases != SSD_PHASE_ALL;
+    a.actions = actions; a.order = action_order; a.obs = obs_out; a.rew = reward_out;
+    if (tape) { a.tape_move = tape->move_order; a.tape_u = tape->uniforms; a.u_stride = tape->u_stride; a.tape_waste = tape->waste_order; }
+    CUDA_TRY(ssd::launch_step(a, h->threads, static_cast<cudaStream_t>(stream)));
+    h->launches++;
+    if (phases & SSD_PHASE_SPAWN) h->t++;
+    return SSD_OK;
+}
+
+int ssd_step(ssd_handle h, const int8_t* actions, const uint8_t* action_order, const SsdTape* tape, uint8_t* obs_out,
+             int32_t* reward_out, void* stream) {
+    return ssd_step_phases(h, SSD_PHASE_ALL, actions, action_order, tape, obs_out, reward_out, stream);
+}
+
+int ssd_render(ssd_handle h, int rotate, uint8_t* obs_out, void* stream) {
+    if (check_handle(h)) return SSD_ERR_INVALID;
+    if (!obs_out) return fail(SSD_ERR_INVALID, "obs_out is required");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    ssd::StepArgs a;
+    fill_args(h, a);
+    a.phases = SSD_PHASE_RENDER; a.rotate = rotate ? 1 : 0; a.obs = obs_out;
+    CUDA_TRY(ssd::launch_step(a, h->threads, static_cast<cudaStream_t>(stream)));
+    h->launches++;
+    return SSD_OK;
+}
+
+int ssd_step_host(ssd_handle h, const int8_t* actions_host, uint8_t* obs_host, int32_t* reward_host) {
+    if (check_handle(h)) return SSD_ERR_INVALID;
+    if (!actions_host || !reward_host) return fail(SSD_ERR_INVALID, "actions_host and reward_host are required");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    const int N = h->cfg.num_agents, B = h->B, E = h->E;
+    if (!h->hs[0]) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&h->hs[0], cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&h->hs[1], cudaStreamNonBlocking));
+        if (h->alloc(&h->d_act_stage, static_cast<size_t>(h->B_pad) * N) || h->alloc(&h->d_rew_stage, static_cast<size_t>(h->B_pad) * N) ||
+            h->alloc(&h->d_obs_stage, static_cast<size_t>(h->B_pad) * h->obs_env))
+            return fail(SSD_ERR_CUDA, "staging allocation failed");
+    }
+    // chunks of whole CTAs, ~8 per step, alternating between two streams so that the D2H copy of
+    // chunk i overlaps the kernel of chunk i+1
+    int chunk = ((B + 7) / 8 + E - 1) / E * E;
+    if (chunk < E) chunk = E;
+    int k = 0;
+    for (int b0 = 0; b0 < B; b0 += chunk, ++k) {
+        const int b1 = b0 + chunk < B ? b0 + chunk : B;
+        cudaStream_t st = h->hs[k & 1];
+        const size_t na = static_cast<size_t>(b1 - b0) * N;
+        CUDA_TRY(cudaMemcpyAsync(h->d_act_stage + static_cast<size_t>(b0) * N, actions_host + static_cast<size_t>(b0) * N, na, cudaMemcpyHostToDevice, st));
+        ssd::StepArgs a;
+        fill_args(h, a);
+        a.env_begin = b0; a.env_end = b1;
+        a.actions = h->d_act_stage; a.obs = obs_host ? h->d_obs_stage : nullptr; a.rew = h->d_rew_stage;
+        CUDA_TRY(ssd::launch_step(a, h->threads, st));
+        h->launches++;
+        CUDA_TRY(cudaMemcpyAsync(reward_host + static_cast<size_t>(b0) * N, h->d_rew_stage + static_cast<size_t>(b0) * N, na * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        if (obs_host)
+            CUDA_TRY(cudaMemcpyAsync(obs_host + static_cast<size_t>(b0) * h->obs_env, h->d_obs_stage + static_cast<size_t>(b0) * h->obs_env,
+                                     static_cast<size_t>(b1 - b0) * h->obs_env, cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_TRY(cudaStreamSynchronize(h->hs[0]));
+    CUDA_TRY(cudaStreamSynchronize(h->hs[1]));
+    h->t++;
+    return SSD_OK;
+}
+
+int ssd_stats(ssd_handle h, int64_t* out_host, void* stream) {
+    if (check_handle(h) || !out_host) return SSD_ERR_INVALID;
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    unsigned long long tmp[SSD_NUM_STATS];
+    CUDA_TRY(cudaMemcpyAsync(tmp, h->d_stats, sizeof tmp, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (int i = 0; i < SSD_NUM_STATS; ++i) out_host[i] = static_cast<int64_t>(tmp[i]);
+    out_host[1] = out_host[2] - out_host[3] - 50 * out_host[4];  // reward_sum = apples - fires - 50 * hits
+    return SSD_OK;
+}
+
+int ssd_philox_selftest(int device, const uint32_t ctr[4], const uint32_t key[2], uint32_t* out_host) {
+    if (!ctr || !key || !out_host) return fail(SSD_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(device));
+    uint32_t host[6] = {ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1]};
+    uint32_t* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, 10 * sizeof(uint32_t)));
+    cudaError_t e = cudaMemcpy(d, host, sizeof host, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = ssd::launch_philox_selftest(d, d + 6, nullptr);
+    if (e == cudaSuccess) e = cudaMemcpy(out_host, d + 6, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(SSD_ERR_CUDA, "philox selftest: %s", cudaGetErrorString(e));
+    return SSD_OK;
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

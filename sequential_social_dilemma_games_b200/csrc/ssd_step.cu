@@ -1,0 +1,768 @@
+// Fused MapEnv.step kernel for sm_100a: one CTA steps E independent environments.
+//
+//   load   grid tile (E x cell_stride bytes) by one TMA bulk copy; agent table, actions by plain loads
+//   A      moves (map_env.py:357-543), consume (:178-181), beams (:545-649): ONE THREAD PER ENV --
+//          the conflict resolution is sequential and order dependent, so it is emulated literally;
+//          E envs advance in parallel on E threads spread over the CTA's warps
+//   B      custom_map_update (harvest.py:69-104, cleanup.py:113-179): ONE WARP PER ENV, ballot/popc
+//          prefix ranks give every eligible cell its sequential draw index
+//   store  grid, agent table, rewards back to HBM
+//   C      get_map_with_agents + return_view + map_to_colors + rotate_view (map_env.py:189-199):
+//          one thread per VIEW ROW, pixels packed to the exact byte image of obs[e0:e0+E] in shared
+//          memory, then one TMA bulk store of the whole slab
+//
+// Reference citations are relative to the reference root (social_dilemmas/envs/...).
+#include <cstdio>
+
+#include "ssd_device.cuh"
+#include "ssd_internal.h"
+
+namespace ssd {
+
+// ====================================================================== phase A: moves
+__device__ __forceinline__ bool occupied(const uint16_t* p, int N, uint32_t key) {
+    bool f = false;
+    for (int a = 0; a < N; ++a) f |= (p[a] == key);
+    return f;
+}
+__device__ __forceinline__ int by_pos(const uint16_t* p, int N, uint32_t key) {
+    int o = -1;  // dict built in agent order: the LAST agent on a cell wins (map_env.py:397)
+    for (int a = 0; a < N; ++a) o = (p[a] == key) ? a : o;
+    return o;
+}
+
+template <bool TAPE>
+__device__ __noinline__ void moves_slow(const StepArgs& a, EnvScratch& S, uint32_t movers, int local_env,
+                                         const PhiloxKey& pk) {
+    const int N = a.N;
+    // mover list in action order (agent_moves is an insertion-ordered dict, map_env.py:400-412)
+    uint8_t* shuf = S.shuf;
+    int n_mov = 0;
+    for (int k = 0; k < N; ++k) {
+        const int ag = S.order[k];
+        if (movers >> ag & 1) shuf[n_mov++] = static_cast<uint8_t>(ag);
+    }
+    // np.random.shuffle(shuffle_list), map_env.py:421-423
+    if (TAPE) {
+        const uint8_t* mo = a.tape_move + static_cast<size_t>(local_env) * N;
+        for (int i = 0; i < n_mov; ++i) shuf[i] = mo[i] < N ? mo[i] : static_cast<uint8_t>(N - 1);  // malformed tapes must not fault
+    } else {
+        uint4 blk = make_uint4(0, 0, 0, 0);
+        uint32_t w = 0;
+        for (int i = n_mov - 1; i >= 1; --i, ++w) {
+            if ((w & 3) == 0) blk = philox4x32_10(pk.env, pk.t, STREAM_MOVE, w >> 2, pk.k0, pk.k1);
+            const uint32_t j = __umulhi(pick_word(blk, w), static_cast<uint32_t>(i + 1));
+            const uint8_t tmp = shuf[i]; shuf[i] = shuf[j]; shuf[j] = tmp;
+        }
+    }
+    for (int ag = 0; ag < N; ++ag) S.orig[ag] = (movers >> ag & 1) ? S.tgt[ag] : 0xFFFFu;
+
+    // contested cells in lexicographic (row, col) order == ascending key (np.unique axis=0, :424)
+    int prev = -1;
+    while (true) {
+        int cell = 0x10000, cnt = 0;
+        for (int ag = 0; ag < N; ++ag) {
+            const int o = S.orig[ag];
+            if (o != 0xFFFF && o > prev) {
+                if (o < cell) { cell = o; cnt = 1; } else if (o == cell) ++cnt;
+            }
+        }
+        if (cell == 0x10000) break;
+        prev = cell;
+        if (cnt < 2) continue;
+        bool cell_free = true;
+        int winner = -1;
+        for (int i = 0; i < n_mov; ++i) {  // conflicting agents in shuffled order (:441-442)
+            const int ag = shuf[i];
+            if (S.orig[ag] != cell) continue;
+            if (winner < 0) winner = ag;  // agent_to_slot[index]: first occurrence (:481)
+            if (occupied(S.pos, N, cell)) {                       // :449
+                const int o = by_pos(S.pos, N, cell);             // :452 (rebuilt after every update)
+                const uint32_t cpos = S.pos[o];
+                const bool o_moves = movers >> o & 1;
+                const uint32_t cmove = o_moves ? S.tgt[o] : cpos; // :456
+                if (ag == o) cell_free = false;                                   // (1) :460
+                else if (!o_moves || cpos == cmove) cell_free = false;            // (2) :466
+                else if (S.tgt[o] == S.pos[ag] && cell == (int)S.pos[o]) cell_free = false;  // (3) :472
+            }
+        }
+        if (cell_free) S.pos[winner] = static_cast<uint16_t>(cell);  // :480-483
+        for (int i = 0; i < n_mov; ++i) {                            // :486-491
+            const int ag = shuf[i];
+            if (S.orig[ag] == cell) S.tgt[ag] = S.pos[ag];
+        }
+    }
+
+    // remaining moves: fix-point loop, map_env.py:494-543
+    uint32_t alive = movers;
+    while (alive) {
+        for (int ag = 0; ag < N; ++ag) S.snap[ag] = S.pos[ag];  // agent_by_pos snapshot (:495)
+        const uint32_t in_copy = alive;                         // moves_copy (:498)
+        uint32_t deleted = 0;
+        for (int k = 0; k < N; ++k) {
+            const int ag = S.order[k];
+            if (!(in_copy >> ag & 1) || (deleted >> ag & 1)) continue;
+            const uint32_t mv = S.tgt[ag];
+            if (occupied(S.pos, N, mv)) {                   // :503 live positions
+                const int o = by_pos(S.snap, N, mv);        // :506 snapshot
+                if (o < 0) continue;                        // reference would KeyError; unreachable
+                const uint32_t cpos = S.pos[o];
+                const uint32_t cmove = (alive >> o & 1) ? S.tgt[o] : cpos;  // :509 live agent_moves
+                if (ag == o) { alive &= ~(1u << ag); deleted |= 1u << ag; }                                  // (1)
+                else if (!(in_copy >> o & 1) || cpos == cmove) { alive &= ~(1u << ag); deleted |= 1u << ag; }  // (2)
+                else if (S.tgt[o] == S.pos[ag] && mv == S.pos[o]) {                                           // (3)
+                    alive &= ~((1u << ag) | (1u << o)); deleted |= (1u << ag) | (1u << o);
+                }
+            } else {
+                S.pos[ag] = static_cast<uint16_t>(mv);      // :532-535
+                alive &= ~(1u << ag); deleted |= 1u << ag;
+            }
+        }
+        if (alive == in_copy) {  // nobody could move freely: move them all (:540-543)
+            for (int ag = 0; ag < N; ++ag) if (alive >> ag & 1) S.pos[ag] = S.tgt[ag];
+            break;
+        }
+    }
+}
+
+template <bool TAPE>
+__device__ __forceinline__ void moves_env(const StepArgs& a, EnvScratch& S, const uint32_t* s_wall, int local_env,
+                                          const PhiloxKey& pk) {
+    const int N = a.N, W = a.W;
+    uint32_t movers = 0;
+    for (int k = 0; k < N; ++k) {  // map_env.py:379-392, action-dict order
+        const int ag = S.order[k];
+        const int act = S.act[ag];
+        if (act < 0) continue;
+        if (act <= 4) {
+            const int v0 = (act == 0) ? -1 : (act == 1) ? 1 : 0;  // ACTIONS map_env.py:11-15
+            const int v1 = (act == 2) ? -1 : (act == 3) ? 1 : 0;
+            const int o = S.ori[ag];
+            int r0, r1;  // rotate_action map_env.py:701-716
+            if (o == 0) { r0 = v0; r1 = v1; } else if (o == 3) { r0 = v1; r1 = -v0; }
+            else if (o == 1) { r0 = -v1; r1 = v0; } else { r0 = -v0; r1 = -v1; }
+            const int key = S.pos[ag];
+            const int nr = (key >> 8) + r0, nc = (key & 255) + r1;
+            const int idx = nr * W + nc;
+            const bool wall = (s_wall[idx >> 5] >> (idx & 31)) & 1;  // agent.py:105-113
+            S.tgt[ag] = static_cast<uint16_t>(wall ? key : (nr << 8 | nc));
+            movers |= 1u << ag;
+        } else if (act == 5) {
+            S.ori[ag] = (S.ori[ag] + 1) & 3;  // TURN_CLOCKWISE map_env.py:729-737
+        } else if (act == 6) {
+            S.ori[ag] = (S.ori[ag] + 3) & 3;  // TURN_COUNTERCLOCKWISE map_env.py:720-728
+        }
+    }
+    if (!movers) return;  // map_env.py:415
+    // Fast path: all targets distinct and no target currently occupied by ANOTHER agent => the
+    // contested pass is empty and the first fix-point pass moves everybody (a STAY hits rule (1)
+    // and keeps its place).  Anything else runs the literal emulation.
+    bool conflict = false;
+    for (int x = 0; x < N; ++x) {
+        if (!(movers >> x & 1)) continue;
+        const uint32_t tx = S.tgt[x];
+        for (int y = 0; y < N; ++y) {
+            if (y == x) continue;
+            conflict |= (S.pos[y] == tx);
+            conflict |= (y > x) && (movers >> y & 1) && (S.tgt[y] == tx);
+        }
+    }
+    if (!conflict) {
+        for (int x = 0; x < N; ++x) if (movers >> x & 1) S.pos[x] = S.tgt[x];
+        return;
+    }
+    moves_slow<TAPE>(a, S, movers, local_env, pk);
+}
+
+// ====================================================================== phase A: beams, map_env.py:566-649
+__device__ __noinline__ void fire_beam(const StepArgs& a, EnvScratch& S, uint8_t* g, const uint32_t* s_wall,
+                                        uint32_t* beams, int ag, bool clean, int* s_stats) {
+    const int N = a.N, H = a.H, W = a.W;
+    const uint32_t ch = clean ? 'C' : 'F';
+    const int o = S.ori[ag];
+    const int d0 = (o == 1) - (o == 3), d1 = (o == 2) - (o == 0);  // ORIENTATIONS map_env.py:19-22
+    const int rs0 = -d1, rs1 = d0;                                  // rotate_right :607,715
+    const int pr = S.pos[ag] >> 8, pc = S.pos[ag] & 255;
+    int upd[3] = {-1, -1, -1};
+    int nb = S.nbeams;
+    for (int s = 0; s < 3; ++s) {  // :608-612
+        int r = pr + d0, c = pc + d1;
+        if (s == 1) { r += rs0 - d0; c += rs1 - d1; }
+        if (s == 2) { r -= rs0 + d0; c -= rs1 + d1; }
+        for (int i = 0; i < a.beam_len; ++i) {
+            if (r < 0 || r >= H || c < 0 || c >= W) break;          // :615, :645
+            const int idx = r * W + c;
+            if ((s_wall[idx >> 5] >> (idx & 31)) & 1) break;       // :616
+            const uint32_t key = r << 8 | c;
+            const bool isH = clean && g[idx] == 'H';
+            if (occupied(S.pos, N, key)) {                          // :621-629 agents absorb beams
+                const int hit = by_pos(S.pos, N, key);
+                if (!clean) { S.rew[hit] -= 50; atomicAdd(&s_stats[4], 1); }  // agent.py:166-168, 212-214
+                beams[nb++] = idx | ch << 16;
+                if (isH) upd[s] = idx;
+                break;
+            }
+            if (isH) upd[s] = idx;                                  // :632-634
+            beams[nb++] = idx | ch << 16;                           // :636
+            if (isH) break;                                         // blocking_cells :639
+            r += d0; c += d1;
+        }
+    }
+    S.nbeams = nb;
+    for (int s = 0; s < 3; ++s)                                     // update_map :551-558
+        if (upd[s] >= 0) { g[upd[s]] = 'R'; atomicAdd(&s_stats[5], 1); }
+}
+
+// ====================================================================== phase B: spawning (one warp per env)
+// Agent cells are flagged with bit 7 while the spawn pass runs ("[row, col] not in self.agent_pos",
+// harvest.py:90, cleanup.py:138); consume already turned every apple under an agent into ' '.
+template <bool TAPE>
+__device__ __forceinline__ void harvest_spawn(const StepArgs& a, uint8_t* g, const uint16_t* s_apple,
+                                              const uint8_t* s_apple_nb, uint16_t* list, int local_env,
+                                              const PhiloxKey& pk, int lane, int* s_stats) {
+    const int W = a.W, n_apple = a.n_apple;
+    int base = 0;
+    for (int i0 = 0; i0 < n_apple; i0 += 32) {  // eligibility scan in row-major apple-point order (harvest.py:87-90)
+        const int i = i0 + lane;
+        bool el = false;
+        if (i < n_apple) { const uint8_t c = g[s_apple[i]]; el = (c != 'A') && !(c & 0x80); }
+        const uint32_t m = __ballot_sync(0xffffffffu, el);
+        if (el) list[base + __popc(m & lanemask_lt())] = static_cast<uint16_t>(i);
+        base += __popc(m);
+    }
+    const int n_draw = base;  // k-th eligible point consumes the k-th np.random.rand (harvest.py:101)
+    __syncwarp();
+    for (int j0 = 0; j0 < n_draw; j0 += 32) {
+        const int j = j0 + lane;
+        if (j < n_draw) {
+            const int i = list[j];
+            const int idx = s_apple[i];
+            const uint32_t nbm = s_apple_nb[i];
+            int n = 0;  // 3x3 window, j*j + k*k <= APPLE_RADIUS(2)  (harvest.py:92-99)
+            n += (nbm & 1) && g[idx - W - 1] == 'A';
+            n += (nbm & 2) && g[idx - W] == 'A';
+            n += (nbm & 4) && g[idx - W + 1] == 'A';
+            n += (nbm & 8) && g[idx - 1] == 'A';
+            n += (nbm & 16) && g[idx + 1] == 'A';
+            n += (nbm & 32) && g[idx + W - 1] == 'A';
+            n += (nbm & 64) && g[idx + W] == 'A';
+            n += (nbm & 128) && g[idx + W + 1] == 'A';
+            n = n < 3 ? n : 3;
+            bool spawn = false;
+            if (TAPE) spawn = a.tape_u[static_cast<size_t>(local_env) * a.u_stride + j] < a.harvest_p[n];
+            else if (n > 0) spawn = philox_u53(pk, a.spawn_stream, j) < a.harvest_thr[n];  // u < p  <=>  u53 < ceil(p * 2^53)
+            if (spawn) list[j] = static_cast<uint16_t>(i | 0x8000);
+        }
+    }
+    __syncwarp();  // every read saw the pre-spawn grid; writes happen after the scan (harvest.py:72-73)
+    int n_new = 0;
+    for (int j = lane; j < n_draw; j += 32)
+        if (list[j] & 0x8000) { g[s_apple[list[j] & 0x7fff]] = 'A'; ++n_new; }
+    if (n_new) atomicAdd(&s_stats[6], n_new);
+}
+
+template <bool TAPE>
+__device__ __forceinline__ void cleanup_spawn(const StepArgs& a, uint8_t* g, const uint16_t* s_apple, uint32_t* keys,
+                                              int local_env, const PhiloxKey& pk, int lane, int* s_stats) {
+    const int n_apple = a.n_apple, n_waste = a.n_waste;
+    // compute_permitted_area / compute_probabilities, cleanup.py:156-179: count 'H' over the whole grid
+    int cnt = 0;
+    for (int i = lane * 16; i < a.cell_stride; i += 512) {
+        const uint4 v = *reinterpret_cast<const uint4*>(g + i);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t x = (w[q] & 0x7F7F7F7Fu) ^ 0x48484848u;          // byte == 0  <=>  cell is 'H'
+            const uint32_t nz = ((x + 0x7F7F7F7Fu) | x) & 0x80808080u;      // bit 7 set  <=>  byte != 0
+            cnt += 4 - __popc(nz);
+        }
+    }
+    int h = __reduce_add_sync(0xffffffffu, cnt);
+    h = h < a.area ? h : a.area;
+    const double apple_p = a.apple_p[h], waste_p = a.waste_p[h];
+    const uint64_t apple_thr = a.apple_thr[h], waste_thr = a.waste_thr[h];
+
+    int base = 0, n_new = 0;
+    for (int i0 = 0; i0 < n_apple; i0 += 32) {  // apple pass, cleanup.py:135-141 (a draw per eligible point)
+        const int i = i0 + lane;
+        bool el = false;
+        int idx = 0;
+        if (i < n_apple) { idx = s_apple[i]; const uint8_t c = g[idx]; el = (c != 'A') && !(c & 0x80); }
+        const uint32_t m = __ballot_sync(0xffffffffu, el);
+        if (el) {
+            const int rank = base + __popc(m & lanemask_lt());
+            bool spawn;
+            if (TAPE) spawn = a.tape_u[static_cast<size_t>(local_env) * a.u_stride + rank] < apple_p;
+            else spawn = apple_thr != 0 && philox_u53(pk, a.spawn_stream, rank) < apple_thr;
+            if (spawn) { g[idx] = 'A'; ++n_new; }  // apple cells are never read again in this pass
+        }
+        base += __popc(m);
+    }
+    if (n_new) atomicAdd(&s_stats[6], n_new);
+
+    if (waste_p != 0.0 && n_waste > 0) {  // `not np.isclose(p, 0)`: p is 0 or wasteSpawnProbability (cleanup.py:144)
+        if (TAPE) {
+            const uint16_t* wo = a.tape_waste + static_cast<size_t>(local_env) * n_waste;  // order after random.shuffle (:145)
+            for (int i0 = 0; i0 < n_waste; i0 += 32) {
+                const int i = i0 + lane;
+                bool el = false;
+                int idx = 0;
+                if (i < n_waste) { idx = wo[i]; el = (g[idx] & 0x7F) != 'H'; }       // :149
+                const uint32_t m = __ballot_sync(0xffffffffu, el);
+                bool ok = false;
+                if (el) ok = a.tape_u[static_cast<size_t>(local_env) * a.u_stride + base + __popc(m & lanemask_lt())] < waste_p;
+                const uint32_t s = __ballot_sync(0xffffffffu, ok);
+                if (s) {  // first success spawns and breaks (:151-153); waste may appear under an agent
+                    if (lane == __ffs(s) - 1) { g[idx] = 'H' | (g[idx] & 0x80); atomicAdd(&s_stats[7], 1); }
+                    break;
+                }
+                base += __popc(m);
+            }
+        } else {
+            // random.shuffle replacement: canonical waste points ordered by (32-bit key, index).
+            int n_el = 0;
+            for (int i0 = 0; i0 < n_waste; i0 += 128) {  // one Philox block = keys of 4 consecutive points
+                const int i = i0 + lane * 4;
+                if (i < n_waste) {
+                    const uint4 k4 = philox4x32_10(pk.env, pk.t, STREAM_WASTE, i >> 2, pk.k0, pk.k1);
+                    keys[i] = k4.x;
+                    if (i + 1 < n_waste) keys[i + 1] = k4.y;
+                    if (i + 2 < n_waste) keys[i + 2] = k4.z;
+                    if (i + 3 < n_waste) keys[i + 3] = k4.w;
+                }
+            }
+            for (int i = lane; i < n_waste; i += 32) n_el += (g[a.waste_cell[i]] & 0x7F) != 'H';
+            n_el = __reduce_add_sync(0xffffffffu, n_el);
+            __syncwarp();
+            // the k-th scanned non-'H' cell draws uniform #(base + k); the first success wins
+            int kstar = 0;
+            while (kstar < n_el && !(philox_u53(pk, a.spawn_stream, base + kstar) < waste_thr)) ++kstar;
+            if (kstar < n_el) {
+                uint64_t prev = 0;  // select the (kstar+1)-th smallest (key, index) among the eligible cells
+                bool first = true;
+                for (int it = 0; it <= kstar; ++it) {
+                    uint64_t best = ~0ull;
+                    for (int i = lane; i < n_waste; i += 32) {
+                        if ((g[a.waste_cell[i]] & 0x7F) == 'H') continue;
+                        const uint64_t kx = static_cast<uint64_t>(keys[i]) << 32 | static_cast<uint32_t>(i);
+                        if ((first || kx > prev) && kx < best) best = kx;
+                    }
+                    prev = warp_min_u64(best);
+                    first = false;
+                }
+                if (lane == 0) {
+                    const int idx = a.waste_cell[static_cast<uint32_t>(prev)];
+                    g[idx] = 'H' | (g[idx] & 0x80);
+                    atomicAdd(&s_stats[7], 1);
+                }
+            }
+        }
+    }
+}
+
+// ====================================================================== phase C: rendering
+// One thread renders one row of one agent's view (V pixels = 3V bytes) and writes it at its exact
+// byte offset of the obs slab image.  3V is odd, so consecutive rows start at byte phases
+// 0,1,2,3,...: each thread owns the 32-bit words whose FIRST byte lies in its row and fetches the
+// first pixel of the next row from the neighbouring lane to complete its last word.
+template <int VT>
+__device__ __forceinline__ void render_rows(const StepArgs& a, const EnvScratch* s_env, const uint8_t* s_grid,
+                                            const uint32_t* s_color, uint32_t* img_words, int total_rows) {
+    constexpr int RB = 3 * VT;           // bytes per view row
+    constexpr int NP = (RB + 3 + 3) / 4; // words covering the row plus the next row's first pixel
+    const int lane = threadIdx.x & 31;
+    const int NV = a.N * VT;
+    for (int base = threadIdx.x & ~31; base < total_rows; base += blockDim.x) {
+        const int R = base + lane;
+        uint32_t X[VT + 2];
+#pragma unroll
+        for (int j = 0; j < VT + 2; ++j) X[j] = 0;
+        if (R < total_rows) {
+            const int e = __umulhi(static_cast<uint32_t>(R), a.nv_magic);
+            const int rem = R - e * NV;
+            const int ag = rem / VT, i = rem - ag * VT;
+            const EnvScratch& S = s_env[e];
+            const int pr = S.pos[ag] >> 8, pc = S.pos[ag] & 255, r = a.r;
+            const int k = a.rotate ? ((4 - S.ori[ag]) & 3) : 0;  // rotate_view map_env.py:669-689: UP 0, LEFT 1, DOWN 2, RIGHT 3
+            // view row i, pixel j reads map cell (fixed f, varying x0 + sg*j): np.rot90 index algebra
+            const bool roww = !(k & 1);
+            const int sg = (k & 2) ? -1 : 1;
+            int f, x0;
+            if (k == 0) { f = pr - r + i; x0 = pc - r; }
+            else if (k == 2) { f = pr + r - i; x0 = pc + r; }
+            else if (k == 1) { f = pc + r - i; x0 = pr - r; }
+            else { f = pc - r + i; x0 = pr + r; }
+            const int F = roww ? a.H : a.W, XB = roww ? a.W : a.H;
+            const int astep = roww ? sg : sg * a.W;
+            const int addr0 = roww ? f * a.W + x0 : x0 * a.W + f;
+            int jlo = sg > 0 ? -x0 : x0 - XB + 1;
+            int jhi = sg > 0 ? XB - 1 - x0 : x0;
+            jlo = jlo > 0 ? jlo : 0;
+            jhi = jhi < VT - 1 ? jhi : VT - 1;
+            const uint32_t len = (static_cast<uint32_t>(f) < static_cast<uint32_t>(F) && jhi >= jlo) ? jhi - jlo + 1 : 0;
+            const uint8_t* g = s_grid + e * a.cell_stride + addr0;
+#pragma unroll
+            for (int j = 0; j < VT; ++j)  // cells outside the map are '0' = black (utility_funcs.py:94-114)
+                X[j] = (static_cast<uint32_t>(j - jlo) < len) ? s_color[g[j * astep]] : 0u;
+        }
+        X[VT] = __shfl_down_sync(0xffffffffu, X[0], 1);
+        uint32_t P[NP + 1];
+#pragma unroll
+        for (int w = 0; w < NP; ++w) {
+            const int p = (4 * w) / 3, ph = (4 * w) % 3;
+            P[w] = __byte_perm(X[p], X[p + 1], ph == 0 ? 0x4210u : (ph == 1 ? 0x5421u : 0x6542u));
+        }
+        P[NP] = 0;
+        if (R < total_rows) {
+            const uint32_t o = static_cast<uint32_t>(R) * RB;
+            const uint32_t d = (4 - (o & 3)) & 3;
+            const uint32_t w0 = (o + 3) >> 2, w1 = (o + RB - 1) >> 2;
+            const int M = w1 - w0 + 1;
+#pragma unroll
+            for (int m = 0; m < NP; ++m)
+                if (m < M) img_words[w0 + m] = __funnelshift_r(P[m], P[m + 1], 8 * d);
+        }
+    }
+}
+
+// Any view size: one thread per pixel, byte stores.
+__device__ __forceinline__ void render_generic(const StepArgs& a, const EnvScratch* s_env, const uint8_t* s_grid,
+                                               const uint32_t* s_color, uint8_t* img, int n_envs) {
+    const int V = a.V, N = a.N, r = a.r;
+    const int total = n_envs * N * V * V;
+    for (int p = threadIdx.x; p < total; p += blockDim.x) {
+        const int j = p % V, i = (p / V) % V, ag = (p / (V * V)) % N, e = p / (V * V * N);
+        const EnvScratch& S = s_env[e];
+        const int k = a.rotate ? ((4 - S.ori[ag]) & 3) : 0;
+        int vi, vj;
+        if (k == 0) { vi = i; vj = j; } else if (k == 1) { vi = j; vj = V - 1 - i; }
+        else if (k == 2) { vi = V - 1 - i; vj = V - 1 - j; } else { vi = V - 1 - j; vj = i; }
+        const int mr = (S.pos[ag] >> 8) - r + vi, mc = (S.pos[ag] & 255) - r + vj;
+        uint32_t c = 0;
+        if (mr >= 0 && mr < a.H && mc >= 0 && mc < a.W) c = s_color[s_grid[e * a.cell_stride + mr * a.W + mc]];
+        img[3 * p] = c & 255; img[3 * p + 1] = (c >> 8) & 255; img[3 * p + 2] = (c >> 16) & 255;
+    }
+}
+
+__device__ __forceinline__ uint8_t agent_char(int i) {  // str(int(agent_id[-1]) + 1) in a <U1 array (map_env.py:290,297)
+    const int v = i % 10 + 1;
+    return static_cast<uint8_t>(v == 10 ? '1' : '0' + v);
+}
+
+// ====================================================================== the fused kernel
+template <int KIND, bool TAPE, int VT>
+__global__ void __launch_bounds__(kMaxThreads) ssd_step_kernel(const __grid_constant__ StepArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
+    const int E = a.E, N = a.N;
+    const int e0 = a.env_begin + blockIdx.x * E;
+    const int nvalid = min(E, a.env_end - e0);
+
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + a.L.mbar);
+    uint8_t* s_grid = smem + a.L.grid;
+    uint32_t* s_wall = reinterpret_cast<uint32_t*>(smem + a.L.wall);
+    uint32_t* s_color = reinterpret_cast<uint32_t*>(smem + a.L.color);
+    uint16_t* s_apple = reinterpret_cast<uint16_t*>(smem + a.L.apple);
+    uint8_t* s_apple_nb = smem + a.L.apple_nb;
+    EnvScratch* s_env = reinterpret_cast<EnvScratch*>(smem + a.L.env);
+    uint32_t* s_beams = reinterpret_cast<uint32_t*>(smem + a.L.beams);
+    int* s_stats = reinterpret_cast<int*>(smem + a.L.stats);
+
+    const int phases = a.phases;
+    const uint32_t tile_bytes = static_cast<uint32_t>(E) * a.cell_stride;
+
+    // ---- load: grid tile by TMA, everything else by plain loads while it is in flight
+    if (tid == 0) mbar_init(mbar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(mbar, tile_bytes);
+        bulk_g2s(s_grid, a.grid + static_cast<size_t>(e0) * a.cell_stride, tile_bytes, mbar);
+    }
+    for (int i = tid; i < (a.HW + 31) / 32; i += nthr) s_wall[i] = a.wall_bits[i];
+    for (int i = tid; i < 128; i += nthr) s_color[i] = a.color[i];
+    for (int i = tid; i < a.n_apple; i += nthr) { s_apple[i] = a.apple_cell[i]; s_apple_nb[i] = a.apple_nb[i]; }
+    for (int i = tid; i < E * kMaxAgents; i += nthr) {
+        const int e = i / kMaxAgents, ag = i % kMaxAgents;
+        EnvScratch& S = s_env[e];
+        const bool valid = e < nvalid && (a.mask == nullptr || a.mask[e0 + e] != 0);
+        if (ag < N) {
+            const size_t gi = static_cast<size_t>(e0 + e) * N + ag;
+            const uint32_t w = a.agents[gi];
+            S.pos[ag] = static_cast<uint16_t>((w & 255) << 8 | ((w >> 8) & 255));
+            S.ori[ag] = (w >> 16) & 3;
+            S.act[ag] = (valid && a.actions) ? a.actions[gi] : static_cast<int8_t>(-1);
+            S.order[ag] = (valid && a.order) ? a.order[gi] : static_cast<uint8_t>(ag);
+            S.rew[ag] = (valid && a.rew_accumulate && a.rew) ? a.rew[gi] : 0;
+        }
+        if (ag == 0) { S.nbeams = 0; S.active = valid; }
+    }
+    if (tid < SSD_NUM_STATS) s_stats[tid] = 0;
+    __syncthreads();
+
+    // ---- phase A: one thread per env
+    const int tpe = nthr / E;
+    const bool env_thread = (tid % tpe == 0) && (tid / tpe < E);
+    const int my_e = tid / tpe;
+    PhiloxKey pk;
+    pk.k0 = a.key0; pk.k1 = a.key1; pk.t = a.t;
+    if (env_thread && s_env[my_e].active) {
+        pk.env = static_cast<uint32_t>(a.env_id0 + static_cast<uint64_t>(e0 + my_e));
+        if (phases & SSD_PHASE_MOVES) {
+            moves_env<TAPE>(a, s_env[my_e], s_wall, e0 + my_e, pk);
+            atomicAdd(&s_stats[0], 1);
+        }
+    }
+    mbar_wait(mbar, 0);  // grid tile landed
+    if (a.use_beam_buf && (phases & SSD_PHASE_RENDER) && !(phases & SSD_PHASE_BEAMS)) {
+        for (int e = warp; e < E; e += nwarps) {  // beams recorded by an earlier phase call of this step
+            const int n = s_env[e].active ? a.beam_cnt[e0 + e] : 0;
+            for (int i = lane; i < n; i += 32) s_beams[e * a.L.max_beams + i] = a.beam_buf[static_cast<size_t>(e0 + e) * a.L.max_beams + i];
+            if (lane == 0) s_env[e].nbeams = n;
+        }
+    }
+    if (env_thread && s_env[my_e].active) {
+        EnvScratch& S = s_env[my_e];
+        uint8_t* g = s_grid + my_e * a.cell_stride;
+        if (phases & SSD_PHASE_CONSUME) {  // map_env.py:178-181, agent.py:177-183 / 216-222
+            int eaten = 0;
+            for (int ag = 0; ag < N; ++ag) {
+                const int idx = (S.pos[ag] >> 8) * a.W + (S.pos[ag] & 255);
+                if (g[idx] == 'A') { S.rew[ag] += 1; g[idx] = ' '; ++eaten; }
+            }
+            if (eaten) atomicAdd(&s_stats[2], eaten);
+        }
+        if ((phases & SSD_PHASE_BEAMS) && KIND != SSD_KIND_PLAIN) {  // update_custom_moves map_env.py:545-552
+            for (int k = 0; k < N; ++k) {
+                const int ag = S.order[k];
+                const int act = S.act[ag];
+                if (act == 7) {  // FIRE: harvest.py:62-67, cleanup.py:97-101; agent.py:170-172
+                    S.rew[ag] -= 1;
+                    atomicAdd(&s_stats[3], 1);
+                    fire_beam(a, S, g, s_wall, s_beams + my_e * a.L.max_beams, ag, false, s_stats);
+                } else if (act == 8 && KIND == SSD_KIND_CLEANUP) {  // CLEAN: cleanup.py:102-110
+                    fire_beam(a, S, g, s_wall, s_beams + my_e * a.L.max_beams, ag, true, s_stats);
+                }
+            }
+        }
+        if (phases & SSD_PHASE_SPAWN)  // flag agent cells for the spawn pass
+            for (int ag = 0; ag < N; ++ag) g[(S.pos[ag] >> 8) * a.W + (S.pos[ag] & 255)] |= 0x80;
+    }
+    __syncthreads();
+
+    // ---- phase B: one warp per env
+    if ((phases & SSD_PHASE_SPAWN) && KIND != SSD_KIND_PLAIN) {
+        for (int e = warp; e < E; e += nwarps) {
+            if (!s_env[e].active) continue;
+            uint8_t* g = s_grid + e * a.cell_stride;
+            pk.env = static_cast<uint32_t>(a.env_id0 + static_cast<uint64_t>(e0 + e));
+            void* scratch = smem + a.L.list + warp * a.L.list_stride;
+            if (KIND == SSD_KIND_HARVEST)
+                harvest_spawn<TAPE>(a, g, s_apple, s_apple_nb, static_cast<uint16_t*>(scratch), e0 + e, pk, lane, s_stats);
+            else
+                cleanup_spawn<TAPE>(a, g, s_apple, static_cast<uint32_t*>(scratch), e0 + e, pk, lane, s_stats);
+        }
+        __syncthreads();
+    }
+    if ((phases & SSD_PHASE_SPAWN) && env_thread && s_env[my_e].active) {
+        EnvScratch& S = s_env[my_e];
+        uint8_t* g = s_grid + my_e * a.cell_stride;
+        for (int ag = 0; ag < N; ++ag) g[(S.pos[ag] >> 8) * a.W + (S.pos[ag] & 255)] &= 0x7F;
+    }
+    if (phases & SSD_PHASE_SPAWN) __syncthreads();
+
+    // ---- store: state back to HBM
+    if (phases & (SSD_PHASE_MOVES | SSD_PHASE_CONSUME | SSD_PHASE_BEAMS | SSD_PHASE_SPAWN)) {
+        const int vec_per_env = a.cell_stride / 16;
+        uint4* gdst = reinterpret_cast<uint4*>(a.grid + static_cast<size_t>(e0) * a.cell_stride);
+        const uint4* gsrc = reinterpret_cast<const uint4*>(s_grid);
+        for (int i = tid; i < E * vec_per_env; i += nthr)
+            if (s_env[i / vec_per_env].active) gdst[i] = gsrc[i];
+        for (int i = tid; i < E * N; i += nthr) {
+            const int e = i / N, ag = i - e * N;
+            const EnvScratch& S = s_env[e];
+            if (!S.active) continue;
+            const size_t gi = static_cast<size_t>(e0 + e) * N + ag;
+            a.agents[gi] = (S.pos[ag] >> 8) | (S.pos[ag] & 255) << 8 | static_cast<uint32_t>(S.ori[ag]) << 16;
+            if (a.rew) a.rew[gi] = S.rew[ag];
+        }
+        if (a.use_beam_buf && (phases & SSD_PHASE_BEAMS) && !(phases & SSD_PHASE_RENDER)) {
+            for (int e = warp; e < E; e += nwarps) {
+                if (!s_env[e].active) continue;
+                const int n = s_env[e].nbeams;
+                for (int i = lane; i < n; i += 32) a.beam_buf[static_cast<size_t>(e0 + e) * a.L.max_beams + i] = s_beams[e * a.L.max_beams + i];
+                if (lane == 0) a.beam_cnt[e0 + e] = n;
+            }
+        }
+    }
+
+    // ---- phase C: overlay + render + slab store
+    if ((phases & SSD_PHASE_RENDER) && a.obs != nullptr) {
+        __syncthreads();  // the grid write-back above has read the tile
+        if (env_thread) {  // get_map_with_agents map_env.py:280-302: agents in order, then beams in order
+            EnvScratch& S = s_env[my_e];
+            uint8_t* g = s_grid + my_e * a.cell_stride;
+            for (int ag = 0; ag < N; ++ag) g[(S.pos[ag] >> 8) * a.W + (S.pos[ag] & 255)] = agent_char(ag);
+            const uint32_t* bl = s_beams + my_e * a.L.max_beams;
+            for (int i = 0; i < S.nbeams; ++i) g[bl[i] & 0xffff] = static_cast<uint8_t>(bl[i] >> 16);
+        }
+        __syncthreads();
+        uint8_t* dst = a.obs + static_cast<size_t>(e0) * a.obs_env;
+        const uint32_t shift = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(dst) & 15);
+        uint8_t* img = smem + a.L.img + shift;  // same 16-byte phase as the destination
+        if constexpr (VT > 0) render_rows<VT>(a, s_env, s_grid, s_color, reinterpret_cast<uint32_t*>(img), E * N * a.V);
+        else render_generic(a, s_env, s_grid, s_color, img, E);
+        fence_async_smem();
+        __syncthreads();
+        if (a.mask == nullptr) {
+            const uint32_t n = static_cast<uint32_t>(nvalid) * a.obs_env;
+            uint32_t head = (16 - shift) & 15;
+            head = head < n ? head : n;
+            const uint32_t mid = (n - head) & ~15u, tail = n - head - mid;
+            if (tid == 0 && mid) { bulk_s2g(dst + head, img + head, mid); bulk_commit(); }
+            for (uint32_t i = tid; i < head; i += nthr) dst[i] = img[i];
+            for (uint32_t i = tid; i < tail; i += nthr) dst[head + mid + i] = img[head + mid + i];
+            if (tid == 0 && mid) bulk_wait_read();
+        } else {
+            for (int e = 0; e < nvalid; ++e) {
+                if (!s_env[e].active) continue;
+                for (int i = tid; i < a.obs_env; i += nthr) dst[static_cast<size_t>(e) * a.obs_env + i] = img[e * a.obs_env + i];
+            }
+        }
+    }
+    if (tid < SSD_NUM_STATS && s_stats[tid] != 0 && a.stats != nullptr)
+        atomicAdd(&a.stats[tid], static_cast<unsigned long long>(s_stats[tid]));
+}
+
+// ====================================================================== reset: setup_agents + reset_map
+// map_env.py:214-229: spawn_point (:651-662) with the shuffle replaced by a (key, index) order --
+// the reference takes the LAST free entry of the shuffled list = the free entry with the largest
+// (key, index); spawn_rotation (:664-667) indexes ['LEFT','RIGHT','UP','DOWN'] with randint(4).
+__global__ void __launch_bounds__(128) ssd_reset_kernel(const ResetArgs a) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= a.env_end) return;
+    if (a.mask != nullptr && a.mask[e] == 0) return;
+    const uint32_t env = static_cast<uint32_t>(a.env_id0 + static_cast<uint64_t>(e));
+    uint16_t taken[kMaxAgents];
+    for (int ag = 0; ag < a.N; ++ag) {
+        uint64_t best = 0;
+        int best_s = -1;
+        uint4 blk = make_uint4(0, 0, 0, 0);
+        int blk_id = -1;
+        for (int s = 0; s < a.n_spawn; ++s) {
+            const uint32_t wi = ag * a.n_spawn + s;
+            if (static_cast<int>(wi >> 2) != blk_id) { blk_id = wi >> 2; blk = philox4x32_10(env, a.t, STREAM_RPOINT, blk_id, a.key0, a.key1); }
+            const uint16_t key = a.spawn_key[s];
+            bool free_cell = true;
+            for (int q = 0; q < ag; ++q) free_cell &= (taken[q] != key);
+            const uint64_t kx = static_cast<uint64_t>(pick_word(blk, wi)) << 32 | static_cast<uint32_t>(s);
+            if (free_cell && (best_s < 0 || kx > best)) { best = kx; best_s = s; }
+        }
+        const uint16_t key = a.spawn_key[best_s < 0 ? 0 : best_s];
+        taken[ag] = key;
+        const uint32_t rot = philox_word(PhiloxKey{a.key0, a.key1, env, a.t}, STREAM_RROT, ag) & 3;
+        const uint32_t ori = (rot == 0) ? 3u : (rot == 1) ? 1u : (rot == 2) ? 0u : 2u;  // LEFT, RIGHT, UP, DOWN
+        a.agents[static_cast<size_t>(e) * a.N + ag] = (key >> 8) | (key & 255) << 8 | ori << 16;
+    }
+    // reset_map + build_walls + custom_reset (map_env.py:560-564, harvest.py:57-60, cleanup.py:84-92)
+    const uint4* src = reinterpret_cast<const uint4*>(a.init_grid);
+    uint4* dst = reinterpret_cast<uint4*>(a.grid + static_cast<size_t>(e) * a.cell_stride);
+    for (int i = 0; i < a.cell_stride / 16; ++i) dst[i] = src[i];
+}
+
+// ====================================================================== state pack / unpack, selftest
+__global__ void pack_state_kernel(int B, int N, int HW, int cell_stride, const uint8_t* grid_in, const int16_t* pos_in,
+                                  const uint8_t* ori_in, uint8_t* grid, uint32_t* agents) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < static_cast<size_t>(B) * cell_stride) {
+        const size_t b = i / cell_stride, c = i % cell_stride;
+        grid[i] = c < static_cast<size_t>(HW) ? grid_in[b * HW + c] : 0;
+    }
+    if (i < static_cast<size_t>(B) * N)
+        agents[i] = (pos_in[2 * i] & 255) | (pos_in[2 * i + 1] & 255) << 8 | static_cast<uint32_t>(ori_in[i] & 3) << 16;
+}
+__global__ void unpack_state_kernel(int B, int N, int HW, int cell_stride, const uint8_t* grid, const uint32_t* agents,
+                                    uint8_t* grid_out, int16_t* pos_out, uint8_t* ori_out) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (grid_out != nullptr && i < static_cast<size_t>(B) * HW) {
+        const size_t b = i / HW, c = i % HW;
+        grid_out[i] = grid[b * cell_stride + c];
+    }
+    if (i < static_cast<size_t>(B) * N) {
+        const uint32_t w = agents[i];
+        if (pos_out != nullptr) { pos_out[2 * i] = w & 255; pos_out[2 * i + 1] = (w >> 8) & 255; }
+        if (ori_out != nullptr) ori_out[i] = (w >> 16) & 3;
+    }
+}
+__global__ void philox_selftest_kernel(const uint32_t* ck, uint32_t* out) {
+    const uint4 v = philox4x32_10(ck[0], ck[1], ck[2], ck[3], ck[4], ck[5]);
+    out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+}
+
+// ====================================================================== launchers
+template <int KIND, bool TAPE>
+static cudaError_t launch_v(const StepArgs& a, int threads, cudaStream_t stream, bool fast_rows) {
+    const int ctas = (a.env_end - a.env_begin + a.E - 1) / a.E;
+    if (ctas <= 0) return cudaSuccess;
+    const int vt = fast_rows ? a.V : 0;
+#define SSD_LAUNCH(VT_)                                                                                       \
+    do {                                                                                                      \
+        auto kern = ssd_step_kernel<KIND, TAPE, VT_>;                                                         \
+        static uint32_t smem_set = 0;                                                                         \
+        if (a.L.total > smem_set) {                                                                           \
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, a.L.total); \
+            if (e != cudaSuccess) return e;                                                                   \
+            smem_set = a.L.total;                                                                             \
+        }                                                                                                     \
+        kern<<<ctas, threads, a.L.total, stream>>>(a);                                                        \
+        return cudaGetLastError();                                                                            \
+    } while (0)
+    switch (vt) {
+        case 11: SSD_LAUNCH(11);
+        case 15: SSD_LAUNCH(15);
+        case 21: SSD_LAUNCH(21);
+        default: SSD_LAUNCH(0);
+    }
+#undef SSD_LAUNCH
+}
+
+cudaError_t launch_step(const StepArgs& a, int threads, cudaStream_t stream) {
+    // the packed row renderer needs word-aligned slabs: E % 4 == 0 and a 4-byte aligned obs base
+    const bool fast_rows = (a.E % 4 == 0) && (reinterpret_cast<uintptr_t>(a.obs) % 4 == 0);
+    const bool tape = a.tape_u != nullptr || a.tape_move != nullptr;
+    switch (a.kind) {
+        case SSD_KIND_HARVEST:
+            return tape ? launch_v<SSD_KIND_HARVEST, true>(a, threads, stream, fast_rows)
+                        : launch_v<SSD_KIND_HARVEST, false>(a, threads, stream, fast_rows);
+        case SSD_KIND_CLEANUP:
+            return tape ? launch_v<SSD_KIND_CLEANUP, true>(a, threads, stream, fast_rows)
+                        : launch_v<SSD_KIND_CLEANUP, false>(a, threads, stream, fast_rows);
+        default:
+            return tape ? launch_v<SSD_KIND_PLAIN, true>(a, threads, stream, fast_rows)
+                        : launch_v<SSD_KIND_PLAIN, false>(a, threads, stream, fast_rows);
+    }
+}
+
+cudaError_t launch_reset(const ResetArgs& a, cudaStream_t stream) {
+    if (a.env_end <= 0) return cudaSuccess;
+    ssd_reset_kernel<<<(a.env_end + 127) / 128, 128, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pack_state(int B, int N, int HW, int cell_stride, const uint8_t* grid_in, const int16_t* pos_in,
+                              const uint8_t* ori_in, uint8_t* grid, uint32_t* agents, cudaStream_t stream) {
+    const size_t n = static_cast<size_t>(B) * cell_stride;
+    pack_state_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(B, N, HW, cell_stride, grid_in, pos_in, ori_in, grid, agents);
+    return cudaGetLastError();
+}
+cudaError_t launch_unpack_state(int B, int N, int HW, int cell_stride, const uint8_t* grid, const uint32_t* agents,
+                                uint8_t* grid_out, int16_t* pos_out, uint8_t* ori_out, cudaStream_t stream) {
+    const size_t n = static_cast<size_t>(B) * (HW > N ? HW : N);
+    unpack_state_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(B, N, HW, cell_stride, grid, agents, grid_out, pos_out, ori_out);
+    return cudaGetLastError();
+}
+cudaError_t launch_philox_selftest(const uint32_t* ctr_key, uint32_t* out, cudaStream_t stream) {
+    philox_selftest_kernel<<<1, 1, 0, stream>>>(ctr_key, out);
+    return cudaGetLastError();
+}
+
+}  // namespace ssd

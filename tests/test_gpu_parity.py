@@ -1,0 +1,227 @@
+"""GPU parity: the CUDA path (through the C-ABI, libssd_b200.so) against
+  (1) the golden outputs of the unmodified Python reference (tests/golden/*.npz), and
+  (2) the CPU oracle (oracle/ssd_oracle.c) on larger seeded batches.
+Everything is bit-exact: grids, positions, orientations, rewards, uint8 observations."""
+import numpy as np
+import pytest
+import torch
+
+from golden_util import Fixture, PHILOX_FIXTURES, TAPE_FIXTURES
+
+pytestmark = pytest.mark.gpu
+
+
+def _env(cfg, B, **kw):
+    from sequential_social_dilemma_games_b200.batched import BatchedSSDEnv
+    return BatchedSSDEnv(cfg, B, device="cuda:0", **kw)
+
+
+def _state(env):
+    g, p, o = env.get_state()
+    return g.cpu().numpy(), p.cpu().numpy(), o.cpu().numpy()
+
+
+def _assert_state(env, grid, pos, ori, tag):
+    g, p, o = _state(env)
+    assert np.array_equal(p, pos), (tag, "pos")
+    assert np.array_equal(o, ori), (tag, "ori")
+    assert np.array_equal(g, grid), (tag, "grid")
+
+
+def test_philox_on_device():
+    from sequential_social_dilemma_games_b200.batched import philox_selftest
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        assert tuple(int(x) for x in philox_selftest(ctr, key)) == want
+
+
+@pytest.mark.parametrize("name", TAPE_FIXTURES)
+def test_tape_golden(name):
+    """Reference trajectories replayed on the device from the recorded RNG tape."""
+    fx = Fixture(name)
+    env = _env(fx.cfg, fx.B)
+    env.set_state(fx["init_grid"], fx["init_pos"], fx["init_ori"])
+    assert np.array_equal(env.render(rotate=False).cpu().numpy(), fx["init_obs"])  # reset() view, map_env.py:239
+    for t in range(fx.T):
+        obs, rew = env.step(fx["actions"][t], action_order=fx["order"][t], tape=fx.tape(t))
+        _assert_state(env, fx["grid"][t], fx["pos"][t], fx["ori"][t], (name, t))
+        assert np.array_equal(rew.cpu().numpy(), fx["reward"][t]), (name, t, "reward")
+        assert np.array_equal(obs.cpu().numpy(), fx["obs"][t]), (name, t, "obs")
+    st = env.stats()
+    assert st["env_steps"] == fx.T * fx.B and st["reward_sum"] == int(fx["reward"].sum())
+
+
+@pytest.mark.parametrize("name", PHILOX_FIXTURES)
+def test_philox_golden(name):
+    """Reference driven by the production Philox streams: on-device reset + step, no tape."""
+    fx = Fixture(name)
+    reset_at = list(fx["reset_at"])
+    for b in range(fx.B):
+        env = _env(fx.cfg, 1, seed=int(fx["seeds"][b]), env_id_offset=int(fx["env_ids"][b]))
+        obs = env.reset()
+        _assert_state(env, fx["init_grid"][b:b + 1], fx["init_pos"][b:b + 1], fx["init_ori"][b:b + 1], (name, b, "reset"))
+        assert np.array_equal(obs.cpu().numpy()[0], fx["init_obs"][b])
+        for t in range(fx.T):
+            if t in reset_at:
+                ri = reset_at.index(t)
+                obs = env.reset()
+                _assert_state(env, fx["reset_grid"][ri, b:b + 1], fx["reset_pos"][ri, b:b + 1], fx["reset_ori"][ri, b:b + 1], (name, b, t, "reset"))
+                assert np.array_equal(obs.cpu().numpy()[0], fx["reset_obs"][ri, b])
+            assert env.t == t
+            obs, rew = env.step(fx["actions"][t, b:b + 1], action_order=fx["order"][t, b:b + 1])
+            _assert_state(env, fx["grid"][t, b:b + 1], fx["pos"][t, b:b + 1], fx["ori"][t, b:b + 1], (name, b, t))
+            assert np.array_equal(rew.cpu().numpy()[0], fx["reward"][t, b]), (name, b, t)
+            assert np.array_equal(obs.cpu().numpy()[0], fx["obs"][t, b]), (name, b, t)
+
+
+def test_config2_cleanup_4096_tape():
+    """BASELINE.json configs[1]: CleanupEnv, 5 agents, 4096 batched envs, bit-exact vs the reference
+    under replayed RNG: the 8 reference trajectories of cleanup_tape are tiled over 4096 slots."""
+    fx = Fixture("cleanup_tape")
+    B = 4096
+    sel = np.arange(B) % fx.B
+    env = _env(fx.cfg, B)
+    env.set_state(fx["init_grid"][sel], fx["init_pos"][sel], fx["init_ori"][sel])
+    for t in range(fx.T):
+        obs, rew = env.step(fx["actions"][t][sel], action_order=fx["order"][t][sel], tape=fx.tape(t, sel))
+        if t % 10 == 0 or t == fx.T - 1:
+            _assert_state(env, fx["grid"][t][sel], fx["pos"][t][sel], fx["ori"][t][sel], ("cfg2", t))
+            assert np.array_equal(obs.cpu().numpy(), fx["obs"][t][sel]), ("cfg2", t)
+        assert np.array_equal(rew.cpu().numpy(), fx["reward"][t][sel]), ("cfg2", t)
+
+
+def _random_actions(rng, cfg, B, p_clean=0.0):
+    a = rng.randint(cfg.num_actions, size=(B, cfg.num_agents)).astype(np.int8)
+    if p_clean:
+        a[rng.rand(B, cfg.num_agents) < p_clean] = 8
+    return a
+
+
+@pytest.mark.parametrize("game,B,steps,N,amap", [("harvest", 2048, 60, 5, None), ("cleanup", 2048, 90, 5, None),
+                                                 ("cleanup", 512, 40, 10, "tiled"), ("harvest", 333, 30, 5, None)])
+def test_philox_vs_oracle(game, B, steps, N, amap):
+    """Production mode (Philox, device reset) against the CPU oracle on the same seeds."""
+    from oracle.oracle import OracleEnv
+    from sequential_social_dilemma_games_b200.batched import make_config
+    from sequential_social_dilemma_games_b200.maps import CLEANUP_MAP, tile_map
+    cfg = make_config(game, num_agents=N, ascii_map=tile_map(CLEANUP_MAP) if amap == "tiled" else None)
+    seed, off = 0xC0FFEE1234567, 77777
+    env = _env(cfg, B, seed=seed, env_id_offset=off)
+    orc = OracleEnv(cfg, B, seed=seed, env_id_offset=off, n_threads=8)
+    obs = env.reset()
+    oobs = orc.reset()
+    _assert_state(env, orc.grid, orc.pos, orc.ori, (game, "reset"))
+    assert np.array_equal(obs.cpu().numpy(), oobs)
+    rng = np.random.RandomState(5)
+    for t in range(steps):
+        a = _random_actions(rng, cfg, B, p_clean=0.4 if game == "cleanup" and t < steps * 2 // 3 else 0.0)
+        obs, rew = env.step(a)
+        oobs, orew = orc.step(a)
+        assert np.array_equal(rew.cpu().numpy(), orew), (game, t, "reward")
+        _assert_state(env, orc.grid, orc.pos, orc.ori, (game, t))
+        assert np.array_equal(obs.cpu().numpy(), oobs), (game, t, "obs")
+    st = env.stats()
+    for i, k in enumerate(("env_steps", "reward_sum", "apples_eaten", "fires", "hits", "cleaned", "apples_spawned", "waste_spawned")):
+        assert st[k] == int(orc.stats[i]), (k, st, orc.stats)
+    if game == "cleanup":
+        assert st["waste_spawned"] > 0 and st["cleaned"] > 0
+
+
+def test_full_size_properties():
+    """BASELINE.json configs[2] size (65536 Harvest envs): properties that need no oracle.
+    (a) shard invariance: two handles of 32768 envs with env_id_offset reproduce the single
+    65536-env handle; (b) determinism; (c) the stats counters equal the summed rewards;
+    (d) re-rendering the final state reproduces the observations wherever no beam was drawn."""
+    from sequential_social_dilemma_games_b200.batched import make_config
+    cfg = make_config("harvest")
+    B, steps = 65536, 12
+    full = _env(cfg, B, seed=9)
+    lo = _env(cfg, B // 2, seed=9)
+    hi = _env(cfg, B // 2, seed=9, env_id_offset=B // 2)
+    o_full = full.reset().clone()
+    o_lo, o_hi = lo.reset().clone(), hi.reset().clone()
+    assert torch.equal(o_full[:B // 2], o_lo) and torch.equal(o_full[B // 2:], o_hi)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    rsum = 0
+    for t in range(steps):
+        a = torch.randint(0, 8, (B, cfg.num_agents), generator=g, device="cuda", dtype=torch.int8)
+        of, rf = full.step(a)
+        ol, rl = lo.step(a[:B // 2])
+        oh, rh = hi.step(a[B // 2:])
+        assert torch.equal(of[:B // 2], ol) and torch.equal(of[B // 2:], oh)
+        assert torch.equal(rf[:B // 2], rl) and torch.equal(rf[B // 2:], rh)
+        rsum += int(rf.sum().item())
+    gf, pf, orf = full.get_state()
+    gl, pl, orl = lo.get_state()
+    assert torch.equal(gf[:B // 2], gl) and torch.equal(pf[:B // 2], pl) and torch.equal(orf[:B // 2], orl)
+    st = full.stats()
+    assert st["env_steps"] == B * steps and st["reward_sum"] == rsum
+    nofire = (a != 7).all(dim=1)
+    last = of.clone()
+    again = full.render(rotate=True)
+    assert torch.equal(last[nofire], again[nofire]) and int(nofire.sum()) > 1000
+
+
+def test_edge_cases():
+    """Tail CTAs (B not a multiple of the CTA tile), B = 1, empty action dicts, masked reset,
+    the host-buffer entry point and the phase-split entry point."""
+    from oracle.oracle import OracleEnv
+    from sequential_social_dilemma_games_b200 import _lib
+    from sequential_social_dilemma_games_b200.batched import make_config
+    cfg = make_config("cleanup")
+    rng = np.random.RandomState(11)
+    for B in (1, 17, 50):
+        env = _env(cfg, B, seed=4, env_id_offset=B)
+        orc = OracleEnv(cfg, B, seed=4, env_id_offset=B)
+        assert np.array_equal(env.reset().cpu().numpy(), orc.reset())
+        for t in range(25):
+            a = _random_actions(rng, cfg, B, p_clean=0.3)
+            if t % 5 == 0:
+                a[:] = -1  # step({}) : absent agents do nothing (tests/test_envs.py:437-438)
+            if t % 2:
+                obs, rew = env.step(a)
+                obs, rew = obs.cpu().numpy(), rew.cpu().numpy()
+            else:  # ssd_step_host: host buffers in, host buffers out
+                obs = np.empty(env.obs_shape, np.uint8)
+                _, rew = env.step_host(a, obs_host=obs)
+            oobs, orew = orc.step(a)
+            assert np.array_equal(obs, oobs) and np.array_equal(rew, orew), (B, t)
+            _assert_state(env, orc.grid, orc.pos, orc.ori, (B, t))
+    # masked reset: only the selected envs change; the others keep their state
+    B = 40
+    env = _env(cfg, B, seed=6)
+    orc = OracleEnv(cfg, B, seed=6)
+    env.reset()
+    orc.reset()
+    for t in range(10):
+        a = _random_actions(rng, cfg, B, p_clean=0.3)
+        env.step(a)
+        orc.step(a)
+    mask = (np.arange(B) % 3 == 0).astype(np.uint8)
+    before = _state(env)
+    sentinel = torch.full(env.obs_shape, 7, dtype=torch.uint8, device="cuda")
+    obs = env.reset(mask=mask, out=sentinel).cpu().numpy()
+    fresh = OracleEnv(cfg, B, seed=6)
+    fresh.t = orc.t
+    fobs = fresh.reset()
+    g, p, o = _state(env)
+    m = mask.astype(bool)
+    assert np.array_equal(g[m], fresh.grid[m]) and np.array_equal(p[m], fresh.pos[m]) and np.array_equal(o[m], fresh.ori[m])
+    assert np.array_equal(g[~m], before[0][~m]) and np.array_equal(p[~m], before[1][~m])
+    assert np.array_equal(obs[m], fobs[m]) and (obs[~m] == 7).all()
+    # phase-split step == fused step
+    e1 = _env(cfg, 64, seed=8)
+    e2 = _env(cfg, 64, seed=8)
+    e1.reset()
+    e2.reset()
+    for t in range(15):
+        a = _random_actions(rng, cfg, 64, p_clean=0.3)
+        o1, r1 = e1.step(a)
+        r2 = torch.zeros((64, cfg.num_agents), dtype=torch.int32, device="cuda")
+        e2.step(a, reward_out=r2, render=False, phases=_lib.PHASE_MOVES | _lib.PHASE_CONSUME)
+        e2.step(a, reward_out=r2, render=False, phases=_lib.PHASE_BEAMS)
+        o2, _ = e2.step(a, reward_out=r2, phases=_lib.PHASE_SPAWN | _lib.PHASE_RENDER)
+        assert torch.equal(o1, o2) and torch.equal(r1, r2), t
