@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -40,7 +41,7 @@ uint64_t threshold53(double p) {
 
 struct SsdEnv {
     SsdConfig cfg{};
-    int B = 0, B_pad = 0, E = 0, threads = 128;
+    int B = 0, B_pad = 0, E = 0, epw = 16, threads = 128;
     int HW = 0, cell_stride = 0, V = 0, obs_env = 0, n_apple = 0, n_waste = 0, n_spawn = 0;
     uint64_t seed = 0;
     uint32_t t = 0;
@@ -89,7 +90,6 @@ ssd::SmemLayout make_layout(const SsdEnv& h, int E, int threads) {
     ssd::SmemLayout L{};
     uint32_t off = 0;
     L.mbar = off; off += 16;
-    L.img = off; off += up16(static_cast<uint32_t>(E) * h.obs_env) + 16;
     L.grid = off; off += static_cast<uint32_t>(E) * h.cell_stride;
     L.wall = off; off += up16(((h.HW + 31) / 32) * 4);
     L.color = off; off += 512;
@@ -100,6 +100,9 @@ ssd::SmemLayout make_layout(const SsdEnv& h, int E, int threads) {
     L.beams = off; off += up16(static_cast<uint32_t>(E) * L.max_beams * 4);
     L.list_stride = up16(std::max(h.n_apple * 2, h.n_waste * 4));
     L.list = off; off += (threads / 32) * L.list_stride;
+    L.view = off; off += static_cast<uint32_t>(E) * h.cfg.num_agents * 16;
+    L.stage_stride = up16(32u * 3u * h.V);
+    L.stage = off; off += (threads / 32) * L.stage_stride;
     L.stats = off; off += 32;
     L.total = off;
     return L;
@@ -113,7 +116,7 @@ void fill_args(SsdEnv* h, ssd::StepArgs& a) {
     a.n_apple = h->n_apple; a.n_waste = h->n_waste; a.area = c.potential_waste_area;
     a.obs_env = h->obs_env;
     a.nv_magic = static_cast<uint32_t>((1ull << 32) / static_cast<uint32_t>(a.N * a.V) + 1);
-    a.E = h->E; a.env_begin = 0; a.env_end = h->B;
+    a.E = h->E; a.epw = h->epw; a.env_begin = 0; a.env_end = h->B;
     a.phases = SSD_PHASE_ALL; a.rotate = 1; a.spawn_stream = ssd::STREAM_SPAWN;
     a.key0 = static_cast<uint32_t>(h->seed); a.key1 = static_cast<uint32_t>(h->seed >> 32); a.t = h->t;
     a.env_id0 = c.env_id_offset;
@@ -231,27 +234,32 @@ int ssd_create(const SsdConfig* cfg, ssd_handle* out) {
         ap.push_back(pa); athr.push_back(threshold53(pa)); wp.push_back(pw); wthr.push_back(threshold53(pw));
     }
 
-    // envs per CTA: the largest of {16, 8, 4, 2, 1} whose tile fits; prefer >= 2 resident CTAs per SM
+    // CTA shape: E envs per CTA (largest of {32,16,8,4,2,1} that leaves >= 2 CTAs per SM), 256 threads,
+    // env threads packed `epw` per warp.  SSD_E / SSD_THREADS / SSD_EPW override for tuning.
     const int smem_max = static_cast<int>(prop.sharedMemPerBlockOptin);
     const int smem_sm = static_cast<int>(prop.sharedMemPerMultiprocessor);
-    int E = cfg->envs_per_cta;
-    if (E != 0 && E != 1 && E != 2 && E != 4 && E != 8 && E != 16) { delete h; return fail(SSD_ERR_INVALID, "envs_per_cta must be 0, 1, 2, 4, 8 or 16"); }
+    auto env_int = [](const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; };
+    int E = env_int("SSD_E", cfg->envs_per_cta);
+    int threads = env_int("SSD_THREADS", 128);
+    if (threads != 128 && threads != 256) { delete h; return fail(SSD_ERR_INVALID, "SSD_THREADS must be 128 or 256"); }
+    if (E != 0 && E != 1 && E != 2 && E != 4 && E != 8 && E != 16 && E != 32) { delete h; return fail(SSD_ERR_INVALID, "envs_per_cta must be 0, 1, 2, 4, 8, 16 or 32"); }
     if (E == 0) {
-        for (E = 16; E > 1; E >>= 1)
-            if (static_cast<int>(make_layout(*h, E, 128).total) <= smem_max) break;
+        for (E = 32; E > 1; E >>= 1)
+            if (static_cast<int>(make_layout(*h, E, threads).total) + 1024 <= smem_sm / 2) break;
+        while (E > 1 && E / 2 >= h->B) E >>= 1;  // tiny batches: do not pad 1 env to 32
     }
     h->E = E;
-    h->L = make_layout(*h, E, 128);
-    h->threads = 128;
-    if (static_cast<int>(h->L.total) + 1024 > smem_sm / 2) {  // a single resident CTA: give it more warps
-        h->threads = 256;
-        h->L = make_layout(*h, E, 256);
-    }
+    h->threads = threads;
+    h->L = make_layout(*h, E, threads);
     if (static_cast<int>(h->L.total) > smem_max) {
         const unsigned need = h->L.total;
         delete h;
-        return fail(SSD_ERR_UNSUPPORTED, "one environment needs %u bytes of shared memory (limit %d)", need, smem_max);
+        return fail(SSD_ERR_UNSUPPORTED, "a CTA tile of %d envs needs %u bytes of shared memory (limit %d)", E, need, smem_max);
     }
+    int epw = env_int("SSD_EPW", 8);
+    if (epw != 4 && epw != 8 && epw != 16 && epw != 32) { delete h; return fail(SSD_ERR_INVALID, "SSD_EPW must be 4, 8, 16 or 32"); }
+    while (epw < 32 && epw * (threads / 32) < E) epw <<= 1;
+    h->epw = epw;
     h->B_pad = (h->B + E - 1) / E * E;
 
     int bad = 0;

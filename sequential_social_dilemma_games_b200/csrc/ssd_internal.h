@@ -39,8 +39,9 @@ static_assert(sizeof(EnvScratch) % 16 == 0, "EnvScratch must stay 16-byte sized"
 
 // Byte offsets of the dynamic shared-memory carve-up of one CTA (all 16-byte aligned).
 struct SmemLayout {
-    uint32_t mbar, img, grid, wall, color, apple, apple_nb, env, beams, list, stats, total;
+    uint32_t mbar, grid, wall, color, apple, apple_nb, env, beams, list, view, stage, stats, total;
     uint32_t list_stride;  // bytes of spawn scratch per warp
+    uint32_t stage_stride; // bytes of render staging per warp (32 view rows)
     uint32_t max_beams;    // beam cells per env
 };
 
@@ -52,6 +53,7 @@ struct StepArgs {
     uint32_t nv_magic;    // ceil(2^32 / (N*V)) for the row -> env division in the renderer
     // ---- launch description
     int E;                // envs per CTA
+    int epw;              // env threads per warp in the sequential phases
     int env_begin;        // first local env of this launch (multiple of E)
     int env_end;          // one past the last valid local env
     int phases, rotate;

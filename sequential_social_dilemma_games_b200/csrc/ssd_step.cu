@@ -8,8 +8,8 @@
 //          prefix ranks give every eligible cell its sequential draw index
 //   store  grid, agent table, rewards back to HBM
 //   C      get_map_with_agents + return_view + map_to_colors + rotate_view (map_env.py:189-199):
-//          one thread per VIEW ROW, pixels packed to the exact byte image of obs[e0:e0+E] in shared
-//          memory, then one TMA bulk store of the whole slab
+//          one thread per VIEW ROW; a warp packs 32 rows to their exact byte offsets in a private
+//          staging buffer and writes them with coalesced 16-byte stores
 //
 // Reference citations are relative to the reference root (social_dilemmas/envs/...).
 #include <cstdio>
@@ -361,49 +361,54 @@ __device__ __forceinline__ void cleanup_spawn(const StepArgs& a, uint8_t* g, con
 }
 
 // ====================================================================== phase C: rendering
-// One thread renders one row of one agent's view (V pixels = 3V bytes) and writes it at its exact
-// byte offset of the obs slab image.  3V is odd, so consecutive rows start at byte phases
-// 0,1,2,3,...: each thread owns the 32-bit words whose FIRST byte lies in its row and fetches the
-// first pixel of the next row from the neighbouring lane to complete its last word.
+// Per-agent window geometry (np.rot90 index algebra of rotate_view map_env.py:669-689 folded with
+// return_view utility_funcs.py:59-114): view pixel (i, j) reads tile byte a0 + i*si + j*sj and is
+// inside the map iff ilo <= i < ilo+ilen and jlo <= j < jlo+jlen; everything else is '0' = black.
+__device__ __forceinline__ uint4 view_param(const StepArgs& a, const EnvScratch& S, int e, int ag) {
+    const int pr = S.pos[ag] >> 8, pc = S.pos[ag] & 255, r = a.r, V = a.V, H = a.H, W = a.W;
+    const int k = a.rotate ? ((4 - S.ori[ag]) & 3) : 0;  // UP 0, LEFT 1, DOWN 2, RIGHT 3
+    int a0, si, sj, ilo, ihi, jlo, jhi;
+    if (k == 0)      { a0 = (pr - r) * W + pc - r; si = W;  sj = 1;  ilo = r - pr;         ihi = H - 1 - pr + r; jlo = r - pc;         jhi = W - 1 - pc + r; }
+    else if (k == 2) { a0 = (pr + r) * W + pc + r; si = -W; sj = -1; ilo = pr + r - H + 1; ihi = pr + r;         jlo = pc + r - W + 1; jhi = pc + r; }
+    else if (k == 1) { a0 = (pr - r) * W + pc + r; si = -1; sj = W;  ilo = pc + r - W + 1; ihi = pc + r;         jlo = r - pr;         jhi = H - 1 - pr + r; }
+    else             { a0 = (pr + r) * W + pc - r; si = 1;  sj = -W; ilo = r - pc;         ihi = W - 1 - pc + r; jlo = pr + r - H + 1; jhi = pr + r; }
+    ilo = max(ilo, 0); jlo = max(jlo, 0); ihi = min(ihi, V - 1); jhi = min(jhi, V - 1);
+    const int ilen = max(ihi - ilo + 1, 0), jlen = max(jhi - jlo + 1, 0);
+    uint4 p;
+    p.x = static_cast<uint32_t>(a0 + e * a.cell_stride);
+    p.y = (static_cast<uint32_t>(si) & 0xffffu) | static_cast<uint32_t>(sj) << 16;
+    p.z = static_cast<uint32_t>(jlo) | static_cast<uint32_t>(jlen) << 8 | static_cast<uint32_t>(ilo) << 16 | static_cast<uint32_t>(ilen) << 24;
+    p.w = 0;
+    return p;
+}
+
+// One thread renders one row of one agent's view (V pixels = 3V bytes).  A warp owns 32 consecutive
+// rows = 96V contiguous, 16-byte-multiple bytes of the obs tensor: rows are packed to their exact
+// byte offsets in a warp-private staging buffer (3V is odd, so consecutive rows start at byte
+// phases 0,1,2,3: each thread owns the 32-bit words whose FIRST byte lies in its row and takes the
+// first pixel of the next row from the neighbouring lane), then stored with coalesced 16-byte writes.
 template <int VT>
-__device__ __forceinline__ void render_rows(const StepArgs& a, const EnvScratch* s_env, const uint8_t* s_grid,
-                                            const uint32_t* s_color, uint32_t* img_words, int total_rows) {
+__device__ __forceinline__ void render_rows(const StepArgs& a, const uint4* s_view, const uint8_t* s_grid,
+                                            const uint32_t* s_color, uint32_t* stage, uint8_t* dst, int total_rows,
+                                            bool aligned16) {
     constexpr int RB = 3 * VT;           // bytes per view row
     constexpr int NP = (RB + 3 + 3) / 4; // words covering the row plus the next row's first pixel
-    const int lane = threadIdx.x & 31;
-    const int NV = a.N * VT;
-    for (int base = threadIdx.x & ~31; base < total_rows; base += blockDim.x) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int base = warp * 32; base < total_rows; base += nwarps * 32) {
         const int R = base + lane;
         uint32_t X[VT + 2];
 #pragma unroll
         for (int j = 0; j < VT + 2; ++j) X[j] = 0;
         if (R < total_rows) {
-            const int e = __umulhi(static_cast<uint32_t>(R), a.nv_magic);
-            const int rem = R - e * NV;
-            const int ag = rem / VT, i = rem - ag * VT;
-            const EnvScratch& S = s_env[e];
-            const int pr = S.pos[ag] >> 8, pc = S.pos[ag] & 255, r = a.r;
-            const int k = a.rotate ? ((4 - S.ori[ag]) & 3) : 0;  // rotate_view map_env.py:669-689: UP 0, LEFT 1, DOWN 2, RIGHT 3
-            // view row i, pixel j reads map cell (fixed f, varying x0 + sg*j): np.rot90 index algebra
-            const bool roww = !(k & 1);
-            const int sg = (k & 2) ? -1 : 1;
-            int f, x0;
-            if (k == 0) { f = pr - r + i; x0 = pc - r; }
-            else if (k == 2) { f = pr + r - i; x0 = pc + r; }
-            else if (k == 1) { f = pc + r - i; x0 = pr - r; }
-            else { f = pc - r + i; x0 = pr + r; }
-            const int F = roww ? a.H : a.W, XB = roww ? a.W : a.H;
-            const int astep = roww ? sg : sg * a.W;
-            const int addr0 = roww ? f * a.W + x0 : x0 * a.W + f;
-            int jlo = sg > 0 ? -x0 : x0 - XB + 1;
-            int jhi = sg > 0 ? XB - 1 - x0 : x0;
-            jlo = jlo > 0 ? jlo : 0;
-            jhi = jhi < VT - 1 ? jhi : VT - 1;
-            const uint32_t len = (static_cast<uint32_t>(f) < static_cast<uint32_t>(F) && jhi >= jlo) ? jhi - jlo + 1 : 0;
-            const uint8_t* g = s_grid + e * a.cell_stride + addr0;
+            const int ga = R / VT, i = R - ga * VT;  // rows are ordered (env, agent, i)
+            const uint4 vp = s_view[ga];
+            const int si = static_cast<int16_t>(vp.y & 0xffffu), sj = static_cast<int32_t>(vp.y) >> 16;
+            const uint32_t jlo = vp.z & 255u, jlen = (vp.z >> 8) & 255u, ilo = (vp.z >> 16) & 255u, ilen = vp.z >> 24;
+            const uint32_t len = (static_cast<uint32_t>(i) - ilo < ilen) ? jlen : 0u;
+            const uint32_t mask = ((1u << len) - 1u) << jlo;
+            const uint8_t* g = s_grid + static_cast<int32_t>(vp.x) + i * si;
 #pragma unroll
-            for (int j = 0; j < VT; ++j)  // cells outside the map are '0' = black (utility_funcs.py:94-114)
-                X[j] = (static_cast<uint32_t>(j - jlo) < len) ? s_color[g[j * astep]] : 0u;
+            for (int j = 0; j < VT; ++j) X[j] = (mask & (1u << j)) ? s_color[g[j * sj]] : 0u;
         }
         X[VT] = __shfl_down_sync(0xffffffffu, X[0], 1);
         uint32_t P[NP + 1];
@@ -414,25 +419,38 @@ __device__ __forceinline__ void render_rows(const StepArgs& a, const EnvScratch*
         }
         P[NP] = 0;
         if (R < total_rows) {
-            const uint32_t o = static_cast<uint32_t>(R) * RB;
+            const uint32_t o = static_cast<uint32_t>(lane) * RB;  // the chunk starts word aligned
             const uint32_t d = (4 - (o & 3)) & 3;
             const uint32_t w0 = (o + 3) >> 2, w1 = (o + RB - 1) >> 2;
             const int M = w1 - w0 + 1;
 #pragma unroll
             for (int m = 0; m < NP; ++m)
-                if (m < M) img_words[w0 + m] = __funnelshift_r(P[m], P[m + 1], 8 * d);
+                if (m < M) stage[w0 + m] = __funnelshift_r(P[m], P[m + 1], 8 * d);
         }
+        __syncwarp();
+        const int rows_here = min(32, total_rows - base);
+        const int nbytes = rows_here * RB;
+        uint8_t* out = dst + static_cast<size_t>(base) * RB;
+        if (aligned16) {
+            for (int off = lane * 16; off < nbytes; off += 512)
+                *reinterpret_cast<uint4*>(out + off) = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(stage) + off);
+        } else {
+            for (int off = lane * 4; off < nbytes; off += 128)
+                *reinterpret_cast<uint32_t*>(out + off) = stage[off >> 2];
+        }
+        __syncwarp();
     }
 }
 
-// Any view size: one thread per pixel, byte stores.
+// Any view size / partially valid tiles: one thread per pixel, byte stores straight to HBM.
 __device__ __forceinline__ void render_generic(const StepArgs& a, const EnvScratch* s_env, const uint8_t* s_grid,
-                                               const uint32_t* s_color, uint8_t* img, int n_envs) {
+                                               const uint32_t* s_color, uint8_t* dst, int n_envs) {
     const int V = a.V, N = a.N, r = a.r;
     const int total = n_envs * N * V * V;
     for (int p = threadIdx.x; p < total; p += blockDim.x) {
         const int j = p % V, i = (p / V) % V, ag = (p / (V * V)) % N, e = p / (V * V * N);
         const EnvScratch& S = s_env[e];
+        if (!S.active) continue;
         const int k = a.rotate ? ((4 - S.ori[ag]) & 3) : 0;
         int vi, vj;
         if (k == 0) { vi = i; vj = j; } else if (k == 1) { vi = j; vj = V - 1 - i; }
@@ -440,7 +458,7 @@ __device__ __forceinline__ void render_generic(const StepArgs& a, const EnvScrat
         const int mr = (S.pos[ag] >> 8) - r + vi, mc = (S.pos[ag] & 255) - r + vj;
         uint32_t c = 0;
         if (mr >= 0 && mr < a.H && mc >= 0 && mc < a.W) c = s_color[s_grid[e * a.cell_stride + mr * a.W + mc]];
-        img[3 * p] = c & 255; img[3 * p + 1] = (c >> 8) & 255; img[3 * p + 2] = (c >> 16) & 255;
+        dst[3 * static_cast<size_t>(p)] = c & 255; dst[3 * static_cast<size_t>(p) + 1] = (c >> 8) & 255; dst[3 * static_cast<size_t>(p) + 2] = (c >> 16) & 255;
     }
 }
 
@@ -500,9 +518,10 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_kernel(const __grid_cons
     __syncthreads();
 
     // ---- phase A: one thread per env
-    const int tpe = nthr / E;
-    const bool env_thread = (tid % tpe == 0) && (tid / tpe < E);
-    const int my_e = tid / tpe;
+    // env threads are packed `epw` to a warp: the sequential phases cost issue slots per WARP
+    // instruction, so idle lanes are pure waste
+    const int my_e = warp * a.epw + lane;
+    const bool env_thread = lane < a.epw && my_e < E;
     PhiloxKey pk;
     pk.k0 = a.key0; pk.k1 = a.key1; pk.t = a.t;
     if (env_thread && s_env[my_e].active) {
@@ -595,7 +614,7 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_kernel(const __grid_cons
         }
     }
 
-    // ---- phase C: overlay + render + slab store
+    // ---- phase C: overlay + render + coalesced stores
     if ((phases & SSD_PHASE_RENDER) && a.obs != nullptr) {
         __syncthreads();  // the grid write-back above has read the tile
         if (env_thread) {  // get_map_with_agents map_env.py:280-302: agents in order, then beams in order
@@ -605,28 +624,20 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_kernel(const __grid_cons
             const uint32_t* bl = s_beams + my_e * a.L.max_beams;
             for (int i = 0; i < S.nbeams; ++i) g[bl[i] & 0xffff] = static_cast<uint8_t>(bl[i] >> 16);
         }
+        uint4* s_view = reinterpret_cast<uint4*>(smem + a.L.view);
+        for (int i = tid; i < E * N; i += nthr) s_view[i] = view_param(a, s_env[i / N], i / N, i % N);
         __syncthreads();
         uint8_t* dst = a.obs + static_cast<size_t>(e0) * a.obs_env;
-        const uint32_t shift = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(dst) & 15);
-        uint8_t* img = smem + a.L.img + shift;  // same 16-byte phase as the destination
-        if constexpr (VT > 0) render_rows<VT>(a, s_env, s_grid, s_color, reinterpret_cast<uint32_t*>(img), E * N * a.V);
-        else render_generic(a, s_env, s_grid, s_color, img, E);
-        fence_async_smem();
-        __syncthreads();
-        if (a.mask == nullptr) {
-            const uint32_t n = static_cast<uint32_t>(nvalid) * a.obs_env;
-            uint32_t head = (16 - shift) & 15;
-            head = head < n ? head : n;
-            const uint32_t mid = (n - head) & ~15u, tail = n - head - mid;
-            if (tid == 0 && mid) { bulk_s2g(dst + head, img + head, mid); bulk_commit(); }
-            for (uint32_t i = tid; i < head; i += nthr) dst[i] = img[i];
-            for (uint32_t i = tid; i < tail; i += nthr) dst[head + mid + i] = img[head + mid + i];
-            if (tid == 0 && mid) bulk_wait_read();
-        } else {
-            for (int e = 0; e < nvalid; ++e) {
-                if (!s_env[e].active) continue;
-                for (int i = tid; i < a.obs_env; i += nthr) dst[static_cast<size_t>(e) * a.obs_env + i] = img[e * a.obs_env + i];
+        bool all_active = (nvalid == E) && (a.mask == nullptr);
+        if constexpr (VT > 0) {
+            if (all_active) {
+                uint32_t* stage = reinterpret_cast<uint32_t*>(smem + a.L.stage + warp * a.L.stage_stride);
+                render_rows<VT>(a, s_view, s_grid, s_color, stage, dst, E * N * VT, (reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+            } else {
+                render_generic(a, s_env, s_grid, s_color, dst, nvalid);
             }
+        } else {
+            render_generic(a, s_env, s_grid, s_color, dst, nvalid);
         }
     }
     if (tid < SSD_NUM_STATS && s_stats[tid] != 0 && a.stats != nullptr)
