@@ -41,7 +41,7 @@ uint64_t threshold53(double p) {
 
 struct SsdEnv {
     SsdConfig cfg{};
-    int B = 0, B_pad = 0, E = 0, epw = 16, threads = 128;
+    int B = 0, B_pad = 0, E = 0, threads = 128;
     int HW = 0, cell_stride = 0, V = 0, obs_env = 0, n_apple = 0, n_waste = 0, n_spawn = 0;
     uint64_t seed = 0;
     uint32_t t = 0;
@@ -54,7 +54,7 @@ struct SsdEnv {
     uint64_t* d_hthr = nullptr; double* d_hp = nullptr;
     uint64_t* d_athr = nullptr; double* d_ap = nullptr; uint64_t* d_wthr = nullptr; double* d_wp = nullptr;
     uint8_t* d_init_grid = nullptr;
-    uint8_t* d_grid = nullptr; uint32_t* d_agents = nullptr; uint32_t* d_beam_buf = nullptr; int32_t* d_beam_cnt = nullptr;
+    uint8_t* d_grid = nullptr; uint32_t* d_agents = nullptr; uint8_t* d_beam_buf = nullptr;
     unsigned long long* d_stats = nullptr;
     // ssd_step_host plumbing
     cudaStream_t hs[2] = {nullptr, nullptr};
@@ -96,8 +96,6 @@ ssd::SmemLayout make_layout(const SsdEnv& h, int E, int threads) {
     L.apple = off; off += up16(h.n_apple * 2);
     L.apple_nb = off; off += up16(h.n_apple);
     L.env = off; off += static_cast<uint32_t>(E) * sizeof(ssd::EnvScratch);
-    L.max_beams = static_cast<uint32_t>(h.cfg.num_agents) * 3 * h.cfg.beam_len;
-    L.beams = off; off += up16(static_cast<uint32_t>(E) * L.max_beams * 4);
     L.list_stride = up16(std::max(h.n_apple * 2, h.n_waste * 4));
     L.list = off; off += (threads / 32) * L.list_stride;
     L.view = off; off += static_cast<uint32_t>(E) * h.cfg.num_agents * 16;
@@ -116,7 +114,7 @@ void fill_args(SsdEnv* h, ssd::StepArgs& a) {
     a.n_apple = h->n_apple; a.n_waste = h->n_waste; a.area = c.potential_waste_area;
     a.obs_env = h->obs_env;
     a.nv_magic = static_cast<uint32_t>((1ull << 32) / static_cast<uint32_t>(a.N * a.V) + 1);
-    a.E = h->E; a.epw = h->epw; a.env_begin = 0; a.env_end = h->B;
+    a.E = h->E; a.G = h->cfg.num_agents <= 8 ? 8 : 16; a.env_begin = 0; a.env_end = h->B;
     a.phases = SSD_PHASE_ALL; a.rotate = 1; a.spawn_stream = ssd::STREAM_SPAWN;
     a.key0 = static_cast<uint32_t>(h->seed); a.key1 = static_cast<uint32_t>(h->seed >> 32); a.t = h->t;
     a.env_id0 = c.env_id_offset;
@@ -124,7 +122,7 @@ void fill_args(SsdEnv* h, ssd::StepArgs& a) {
     a.wall_bits = h->d_wall; a.apple_cell = h->d_apple; a.apple_nb = h->d_apple_nb; a.waste_cell = h->d_waste;
     a.color = h->d_color; a.harvest_thr = h->d_hthr; a.harvest_p = h->d_hp;
     a.apple_thr = h->d_athr; a.apple_p = h->d_ap; a.waste_thr = h->d_wthr; a.waste_p = h->d_wp;
-    a.grid = h->d_grid; a.agents = h->d_agents; a.beam_buf = h->d_beam_buf; a.beam_cnt = h->d_beam_cnt;
+    a.grid = h->d_grid; a.agents = h->d_agents; a.beam_buf = h->d_beam_buf;
     a.stats = h->d_stats;
 }
 
@@ -234,13 +232,13 @@ int ssd_create(const SsdConfig* cfg, ssd_handle* out) {
         ap.push_back(pa); athr.push_back(threshold53(pa)); wp.push_back(pw); wthr.push_back(threshold53(pw));
     }
 
-    // CTA shape: E envs per CTA (largest of {32,16,8,4,2,1} that leaves >= 2 CTAs per SM), 256 threads,
-    // env threads packed `epw` per warp.  SSD_E / SSD_THREADS / SSD_EPW override for tuning.
+    // CTA shape: E envs per CTA (largest of {32,16,8,4,2,1} that leaves >= 2 CTAs per SM), 128 threads.
+    // SSD_E / SSD_THREADS override for tuning.
     const int smem_max = static_cast<int>(prop.sharedMemPerBlockOptin);
     const int smem_sm = static_cast<int>(prop.sharedMemPerMultiprocessor);
     auto env_int = [](const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; };
     int E = env_int("SSD_E", cfg->envs_per_cta);
-    int threads = env_int("SSD_THREADS", 128);
+    int threads = env_int("SSD_THREADS", 256);
     if (threads != 128 && threads != 256) { delete h; return fail(SSD_ERR_INVALID, "SSD_THREADS must be 128 or 256"); }
     if (E != 0 && E != 1 && E != 2 && E != 4 && E != 8 && E != 16 && E != 32) { delete h; return fail(SSD_ERR_INVALID, "envs_per_cta must be 0, 1, 2, 4, 8, 16 or 32"); }
     if (E == 0) {
@@ -256,10 +254,6 @@ int ssd_create(const SsdConfig* cfg, ssd_handle* out) {
         delete h;
         return fail(SSD_ERR_UNSUPPORTED, "a CTA tile of %d envs needs %u bytes of shared memory (limit %d)", E, need, smem_max);
     }
-    int epw = env_int("SSD_EPW", 8);
-    if (epw != 4 && epw != 8 && epw != 16 && epw != 32) { delete h; return fail(SSD_ERR_INVALID, "SSD_EPW must be 4, 8, 16 or 32"); }
-    while (epw < 32 && epw * (threads / 32) < E) epw <<= 1;
-    h->epw = epw;
     h->B_pad = (h->B + E - 1) / E * E;
 
     int bad = 0;
@@ -270,8 +264,7 @@ int ssd_create(const SsdConfig* cfg, ssd_handle* out) {
     bad |= h->upload(&h->d_init_grid, init_grid);
     bad |= h->alloc(&h->d_grid, static_cast<size_t>(h->B_pad) * h->cell_stride);
     bad |= h->alloc(&h->d_agents, static_cast<size_t>(h->B_pad) * N);
-    bad |= h->alloc(&h->d_beam_buf, static_cast<size_t>(h->B_pad) * h->L.max_beams);
-    bad |= h->alloc(&h->d_beam_cnt, static_cast<size_t>(h->B_pad));
+    bad |= h->alloc(&h->d_beam_buf, static_cast<size_t>(h->B_pad) * 64);
     bad |= h->alloc(&h->d_stats, static_cast<size_t>(SSD_NUM_STATS));
     if (bad) { const char* m = cudaGetErrorString(cudaGetLastError()); ssd_destroy(h); return fail(SSD_ERR_CUDA, "device allocation failed: %s", m); }
     // initial state: post-reset_map grid, agents parked on the first spawn point (or cell 1,1)
@@ -283,7 +276,7 @@ int ssd_create(const SsdConfig* cfg, ssd_handle* out) {
         cudaError_t e1 = cudaMemcpy(h->d_grid, g.data(), g.size(), cudaMemcpyHostToDevice);
         cudaError_t e2 = cudaMemcpy(h->d_agents, ag.data(), ag.size() * 4, cudaMemcpyHostToDevice);
         cudaError_t e3 = cudaMemset(h->d_stats, 0, SSD_NUM_STATS * sizeof(unsigned long long));
-        cudaError_t e4 = cudaMemset(h->d_beam_cnt, 0, static_cast<size_t>(h->B_pad) * 4);
+        cudaError_t e4 = cudaMemset(h->d_beam_buf, 0, static_cast<size_t>(h->B_pad) * 64);
         if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess) {
             ssd_destroy(h);
             return fail(SSD_ERR_CUDA, "state initialisation failed");

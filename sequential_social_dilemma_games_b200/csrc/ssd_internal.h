@@ -26,23 +26,22 @@ struct EnvScratch {
     uint16_t tgt[kMaxAgents];   // agent_moves values (map_env.py:400)
     uint16_t orig[kMaxAgents];  // search_list: targets frozen before the contested pass (:426)
     uint16_t snap[kMaxAgents];  // agent_by_pos snapshot of one fix-point pass (:495)
-    int32_t rew[kMaxAgents];    // reward_this_turn (agent.py:43)
+    int32_t rew[kMaxAgents];    // -50 per 'F' hit taken in this step (agent.py:166-168)
     uint8_t ori[kMaxAgents];
     uint8_t shuf[kMaxAgents];   // movers after np.random.shuffle (:422)
     uint8_t order[kMaxAgents];  // action-dict iteration order
-    int8_t act[kMaxAgents];
-    int32_t nbeams;
+    uint8_t firech[kMaxAgents]; // [k] beam char of the k-th entry of the action order (0 = did not fire)
+    uint8_t raylen[3 * kMaxAgents];  // [k*3+s] painted cells of ray s (beam_pos, map_env.py:648)
     int32_t active;             // 0: env masked out of this launch
-    int32_t pad[2];
+    int32_t pad[3];
 };
 static_assert(sizeof(EnvScratch) % 16 == 0, "EnvScratch must stay 16-byte sized");
 
 // Byte offsets of the dynamic shared-memory carve-up of one CTA (all 16-byte aligned).
 struct SmemLayout {
-    uint32_t mbar, grid, wall, color, apple, apple_nb, env, beams, list, view, stage, stats, total;
+    uint32_t mbar, grid, wall, color, apple, apple_nb, env, list, view, stage, stats, total;
     uint32_t list_stride;  // bytes of spawn scratch per warp
     uint32_t stage_stride; // bytes of render staging per warp (32 view rows)
-    uint32_t max_beams;    // beam cells per env
 };
 
 struct StepArgs {
@@ -53,7 +52,7 @@ struct StepArgs {
     uint32_t nv_magic;    // ceil(2^32 / (N*V)) for the row -> env division in the renderer
     // ---- launch description
     int E;                // envs per CTA
-    int epw;              // env threads per warp in the sequential phases
+    int G;                // lanes per env in phase A: 8 (N <= 8) or 16
     int env_begin;        // first local env of this launch (multiple of E)
     int env_end;          // one past the last valid local env
     int phases, rotate;
@@ -75,8 +74,7 @@ struct StepArgs {
     // ---- state (device)
     uint8_t* grid;        // [B_pad][cell_stride]
     uint32_t* agents;     // [B_pad][N] row | col<<8 | ori<<16
-    uint32_t* beam_buf;   // [B_pad][max_beams]
-    int32_t* beam_cnt;    // [B_pad]
+    uint8_t* beam_buf;    // [B_pad][64] raylen + firech between phase-split calls
     // ---- I/O (device)
     const int8_t* actions; const uint8_t* order; const uint8_t* mask;
     const uint8_t* tape_move; const double* tape_u; int u_stride; const uint16_t* tape_waste;

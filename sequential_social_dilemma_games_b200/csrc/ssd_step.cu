@@ -1,9 +1,10 @@
 // Fused MapEnv.step kernel for sm_100a: one CTA steps E independent environments.
 //
 //   load   grid tile (E x cell_stride bytes) by one TMA bulk copy; agent table, actions by plain loads
-//   A      moves (map_env.py:357-543), consume (:178-181), beams (:545-649): ONE THREAD PER ENV --
-//          the conflict resolution is sequential and order dependent, so it is emulated literally;
-//          E envs advance in parallel on E threads spread over the CTA's warps
+//   A      moves (map_env.py:357-543), consume (:178-181), beams (:545-649): ONE LANE PER AGENT, a
+//          group of 8 (or 16) lanes per env.  Conflict-free moves are resolved with shuffles; an env
+//          with any contested / occupied target falls back to the literal sequential emulation of
+//          update_moves on the group's first lane.  Each firing agent's three rays walk on 3 lanes.
 //   B      custom_map_update (harvest.py:69-104, cleanup.py:113-179): ONE WARP PER ENV, ballot/popc
 //          prefix ranks give every eligible cell its sequential draw index
 //   store  grid, agent table, rewards back to HBM
@@ -125,92 +126,95 @@ __device__ __noinline__ void moves_slow(const StepArgs& a, EnvScratch& S, uint32
     }
 }
 
+// ====================================================================== phase A: one lane per agent
+struct AgentLane {
+    uint32_t key;   // row << 8 | col
+    int ori, act, rew;
+};
+
+// update_moves for one group of G lanes (= one env).  All 32 lanes of the warp call this.
 template <bool TAPE>
-__device__ __forceinline__ void moves_env(const StepArgs& a, EnvScratch& S, const uint32_t* s_wall, int local_env,
-                                          const PhiloxKey& pk) {
-    const int N = a.N, W = a.W;
-    uint32_t movers = 0;
-    for (int k = 0; k < N; ++k) {  // map_env.py:379-392, action-dict order
-        const int ag = S.order[k];
-        const int act = S.act[ag];
-        if (act < 0) continue;
+__device__ __forceinline__ void moves_group(const StepArgs& a, EnvScratch& S, const uint32_t* s_wall, AgentLane& me,
+                                            bool valid, int al, int G, int local_env, const PhiloxKey& pk) {
+    const int W = a.W;
+    const int act = me.act;
+    bool mover = false;
+    uint32_t tgt = me.key;
+    if (valid && act >= 0) {  // map_env.py:379-392
         if (act <= 4) {
             const int v0 = (act == 0) ? -1 : (act == 1) ? 1 : 0;  // ACTIONS map_env.py:11-15
             const int v1 = (act == 2) ? -1 : (act == 3) ? 1 : 0;
-            const int o = S.ori[ag];
+            const int o = me.ori;
             int r0, r1;  // rotate_action map_env.py:701-716
             if (o == 0) { r0 = v0; r1 = v1; } else if (o == 3) { r0 = v1; r1 = -v0; }
             else if (o == 1) { r0 = -v1; r1 = v0; } else { r0 = -v0; r1 = -v1; }
-            const int key = S.pos[ag];
-            const int nr = (key >> 8) + r0, nc = (key & 255) + r1;
+            const int nr = static_cast<int>(me.key >> 8) + r0, nc = static_cast<int>(me.key & 255) + r1;
             const int idx = nr * W + nc;
             const bool wall = (s_wall[idx >> 5] >> (idx & 31)) & 1;  // agent.py:105-113
-            S.tgt[ag] = static_cast<uint16_t>(wall ? key : (nr << 8 | nc));
-            movers |= 1u << ag;
+            tgt = wall ? me.key : static_cast<uint32_t>(nr << 8 | nc);
+            mover = true;
         } else if (act == 5) {
-            S.ori[ag] = (S.ori[ag] + 1) & 3;  // TURN_CLOCKWISE map_env.py:729-737
+            me.ori = (me.ori + 1) & 3;  // TURN_CLOCKWISE map_env.py:729-737
         } else if (act == 6) {
-            S.ori[ag] = (S.ori[ag] + 3) & 3;  // TURN_COUNTERCLOCKWISE map_env.py:720-728
+            me.ori = (me.ori + 3) & 3;  // TURN_COUNTERCLOCKWISE map_env.py:720-728
         }
     }
-    if (!movers) return;  // map_env.py:415
     // Fast path: all targets distinct and no target currently occupied by ANOTHER agent => the
     // contested pass is empty and the first fix-point pass moves everybody (a STAY hits rule (1)
-    // and keeps its place).  Anything else runs the literal emulation.
+    // and keeps its place).  Anything else runs the literal emulation below.
+    const uint32_t pos_x = valid ? me.key : 0xFFFF0000u | al;       // never equal to a real cell
+    const uint32_t tgt_x = mover ? tgt : 0xFFFE0000u | al;
     bool conflict = false;
-    for (int x = 0; x < N; ++x) {
-        if (!(movers >> x & 1)) continue;
-        const uint32_t tx = S.tgt[x];
-        for (int y = 0; y < N; ++y) {
-            if (y == x) continue;
-            conflict |= (S.pos[y] == tx);
-            conflict |= (y > x) && (movers >> y & 1) && (S.tgt[y] == tx);
-        }
+    for (int d = 1; d < G; ++d) {
+        const int src = (al + d) & (G - 1);
+        const uint32_t pos_y = __shfl_sync(0xffffffffu, pos_x, src, G);
+        const uint32_t tgt_y = __shfl_sync(0xffffffffu, tgt_x, src, G);
+        conflict |= mover && (pos_y == tgt || tgt_y == tgt);
     }
-    if (!conflict) {
-        for (int x = 0; x < N; ++x) if (movers >> x & 1) S.pos[x] = S.tgt[x];
-        return;
+    const uint32_t gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << ((threadIdx.x & 31) & ~(G - 1));
+    const uint32_t conf_all = __ballot_sync(0xffffffffu, conflict);
+    const uint32_t conf = conf_all & gmask;
+    const uint32_t movers = (__ballot_sync(0xffffffffu, mover) & gmask) >> ((threadIdx.x & 31) & ~(G - 1));
+    if (conf == 0 && mover) me.key = tgt;
+    if (conf_all != 0) {  // warp-uniform branch: the groups without a conflict just keep the barriers company
+        if (conf != 0 && valid) { S.pos[al] = static_cast<uint16_t>(me.key); S.tgt[al] = static_cast<uint16_t>(tgt); }
+        __syncwarp();
+        if (conf != 0 && al == 0) moves_slow<TAPE>(a, S, movers, local_env, pk);
+        __syncwarp();
+        if (conf != 0 && valid) me.key = S.pos[al];
     }
-    moves_slow<TAPE>(a, S, movers, local_env, pk);
 }
 
-// ====================================================================== phase A: beams, map_env.py:566-649
-__device__ __noinline__ void fire_beam(const StepArgs& a, EnvScratch& S, uint8_t* g, const uint32_t* s_wall,
-                                        uint32_t* beams, int ag, bool clean, int* s_stats) {
+// One firing agent of one env: its three rays walk on the group's lanes 0..2 (map_env.py:566-649).
+// Returns the number of painted cells of this lane's ray.
+__device__ __forceinline__ int ray_walk(const StepArgs& a, EnvScratch& S, uint8_t* g, const uint32_t* s_wall, uint32_t key,
+                                        int ori, int s, bool clean, int& upd, int& hits) {
     const int N = a.N, H = a.H, W = a.W;
-    const uint32_t ch = clean ? 'C' : 'F';
-    const int o = S.ori[ag];
-    const int d0 = (o == 1) - (o == 3), d1 = (o == 2) - (o == 0);  // ORIENTATIONS map_env.py:19-22
-    const int rs0 = -d1, rs1 = d0;                                  // rotate_right :607,715
-    const int pr = S.pos[ag] >> 8, pc = S.pos[ag] & 255;
-    int upd[3] = {-1, -1, -1};
-    int nb = S.nbeams;
-    for (int s = 0; s < 3; ++s) {  // :608-612
-        int r = pr + d0, c = pc + d1;
-        if (s == 1) { r += rs0 - d0; c += rs1 - d1; }
-        if (s == 2) { r -= rs0 + d0; c -= rs1 + d1; }
-        for (int i = 0; i < a.beam_len; ++i) {
-            if (r < 0 || r >= H || c < 0 || c >= W) break;          // :615, :645
-            const int idx = r * W + c;
-            if ((s_wall[idx >> 5] >> (idx & 31)) & 1) break;       // :616
-            const uint32_t key = r << 8 | c;
-            const bool isH = clean && g[idx] == 'H';
-            if (occupied(S.pos, N, key)) {                          // :621-629 agents absorb beams
-                const int hit = by_pos(S.pos, N, key);
-                if (!clean) { S.rew[hit] -= 50; atomicAdd(&s_stats[4], 1); }  // agent.py:166-168, 212-214
-                beams[nb++] = idx | ch << 16;
-                if (isH) upd[s] = idx;
-                break;
-            }
-            if (isH) upd[s] = idx;                                  // :632-634
-            beams[nb++] = idx | ch << 16;                           // :636
-            if (isH) break;                                         // blocking_cells :639
-            r += d0; c += d1;
+    const int d0 = (ori == 1) - (ori == 3), d1 = (ori == 2) - (ori == 0);  // ORIENTATIONS map_env.py:19-22
+    const int rs0 = -d1, rs1 = d0;                                          // rotate_right :607,715
+    int r = static_cast<int>(key >> 8) + d0, c = static_cast<int>(key & 255) + d1;  // :608-613
+    if (s == 1) { r += rs0 - d0; c += rs1 - d1; }
+    if (s == 2) { r -= rs0 + d0; c -= rs1 + d1; }
+    int n = 0;
+    for (int i = 0; i < a.beam_len; ++i) {
+        if (r < 0 || r >= H || c < 0 || c >= W) break;          // :615, :645
+        const int idx = r * W + c;
+        if ((s_wall[idx >> 5] >> (idx & 31)) & 1) break;       // :616
+        const uint32_t cell = r << 8 | c;
+        const bool isH = clean && g[idx] == 'H';
+        const int hit = by_pos(S.pos, N, cell);                 // :621-622 agents absorb beams
+        if (hit >= 0) {
+            if (!clean) { S.rew[hit] -= 50; ++hits; }           // agent.py:166-168, 212-214
+            ++n;                                                // :624
+            if (isH) upd = idx;                                 // :625-628
+            break;
         }
+        if (isH) upd = idx;                                     // :632-634
+        ++n;                                                    // :636
+        if (isH) break;                                         // blocking_cells :639
+        r += d0; c += d1;
     }
-    S.nbeams = nb;
-    for (int s = 0; s < 3; ++s)                                     // update_map :551-558
-        if (upd[s] >= 0) { g[upd[s]] = 'R'; atomicAdd(&s_stats[5], 1); }
+    return n;
 }
 
 // ====================================================================== phase B: spawning (one warp per env)
@@ -483,13 +487,12 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_kernel(const __grid_cons
     uint16_t* s_apple = reinterpret_cast<uint16_t*>(smem + a.L.apple);
     uint8_t* s_apple_nb = smem + a.L.apple_nb;
     EnvScratch* s_env = reinterpret_cast<EnvScratch*>(smem + a.L.env);
-    uint32_t* s_beams = reinterpret_cast<uint32_t*>(smem + a.L.beams);
     int* s_stats = reinterpret_cast<int*>(smem + a.L.stats);
 
     const int phases = a.phases;
     const uint32_t tile_bytes = static_cast<uint32_t>(E) * a.cell_stride;
 
-    // ---- load: grid tile by TMA, everything else by plain loads while it is in flight
+    // ---- load: grid tile by TMA, static tables by plain loads while it is in flight
     if (tid == 0) mbar_init(mbar, 1);
     __syncthreads();
     if (tid == 0) {
@@ -497,74 +500,103 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_kernel(const __grid_cons
         bulk_g2s(s_grid, a.grid + static_cast<size_t>(e0) * a.cell_stride, tile_bytes, mbar);
     }
     for (int i = tid; i < (a.HW + 31) / 32; i += nthr) s_wall[i] = a.wall_bits[i];
-    for (int i = tid; i < 128; i += nthr) s_color[i] = a.color[i];
-    for (int i = tid; i < a.n_apple; i += nthr) { s_apple[i] = a.apple_cell[i]; s_apple_nb[i] = a.apple_nb[i]; }
-    for (int i = tid; i < E * kMaxAgents; i += nthr) {
-        const int e = i / kMaxAgents, ag = i % kMaxAgents;
-        EnvScratch& S = s_env[e];
-        const bool valid = e < nvalid && (a.mask == nullptr || a.mask[e0 + e] != 0);
-        if (ag < N) {
-            const size_t gi = static_cast<size_t>(e0 + e) * N + ag;
-            const uint32_t w = a.agents[gi];
-            S.pos[ag] = static_cast<uint16_t>((w & 255) << 8 | ((w >> 8) & 255));
-            S.ori[ag] = (w >> 16) & 3;
-            S.act[ag] = (valid && a.actions) ? a.actions[gi] : static_cast<int8_t>(-1);
-            S.order[ag] = (valid && a.order) ? a.order[gi] : static_cast<uint8_t>(ag);
-            S.rew[ag] = (valid && a.rew_accumulate && a.rew) ? a.rew[gi] : 0;
-        }
-        if (ag == 0) { S.nbeams = 0; S.active = valid; }
-    }
+    if (phases & SSD_PHASE_RENDER)
+        for (int i = tid; i < 128; i += nthr) s_color[i] = a.color[i];
+    if (phases & SSD_PHASE_SPAWN)
+        for (int i = tid; i < a.n_apple; i += nthr) { s_apple[i] = a.apple_cell[i]; s_apple_nb[i] = a.apple_nb[i]; }
     if (tid < SSD_NUM_STATS) s_stats[tid] = 0;
     __syncthreads();
 
-    // ---- phase A: one thread per env
-    // env threads are packed `epw` to a warp: the sequential phases cost issue slots per WARP
-    // instruction, so idle lanes are pure waste
-    const int my_e = warp * a.epw + lane;
-    const bool env_thread = lane < a.epw && my_e < E;
+    // ---- phase A: one lane per agent, G lanes per env, 32/G envs per warp and pass
+    const int G = a.G, al = lane & (G - 1), gbase = lane & ~(G - 1);
+    const int slots = nwarps * (32 / G);
     PhiloxKey pk;
     pk.k0 = a.key0; pk.k1 = a.key1; pk.t = a.t;
-    if (env_thread && s_env[my_e].active) {
-        pk.env = static_cast<uint32_t>(a.env_id0 + static_cast<uint64_t>(e0 + my_e));
+    bool grid_ready = false;
+    for (int ebase = warp * (32 / G); ebase < E; ebase += slots) {  // warp-uniform trip count
+        const int e = ebase + lane / G;
+        const bool env_ok = e < E;
+        EnvScratch& S = s_env[env_ok ? e : 0];
+        const bool active = env_ok && e < nvalid && (a.mask == nullptr || a.mask[e0 + e] != 0);
+        const bool valid = env_ok && al < N;
+        const size_t gi = static_cast<size_t>(e0 + (env_ok ? e : 0)) * N + (valid ? al : 0);
+        AgentLane me;
+        me.key = 0; me.ori = 0; me.act = -1; me.rew = 0;
+        if (valid) {
+            const uint32_t w = a.agents[gi];
+            me.key = (w & 255) << 8 | ((w >> 8) & 255);
+            me.ori = (w >> 16) & 3;
+            if (active && a.actions) me.act = a.actions[gi];
+            if (active && a.rew_accumulate && a.rew) me.rew = a.rew[gi];
+            S.order[al] = (active && a.order) ? a.order[gi] : static_cast<uint8_t>(al);
+            S.rew[al] = 0;
+            S.firech[al] = 0;
+        }
+        if (env_ok && al == 0) S.active = active;
+        pk.env = static_cast<uint32_t>(a.env_id0 + static_cast<uint64_t>(e0 + e));
+        __syncwarp();
         if (phases & SSD_PHASE_MOVES) {
-            moves_env<TAPE>(a, s_env[my_e], s_wall, e0 + my_e, pk);
-            atomicAdd(&s_stats[0], 1);
+            moves_group<TAPE>(a, S, s_wall, me, valid && active, al, G, e0 + e, pk);
+            if (active && al == 0) atomicAdd(&s_stats[0], 1);
         }
-    }
-    mbar_wait(mbar, 0);  // grid tile landed
-    if (a.use_beam_buf && (phases & SSD_PHASE_RENDER) && !(phases & SSD_PHASE_BEAMS)) {
-        for (int e = warp; e < E; e += nwarps) {  // beams recorded by an earlier phase call of this step
-            const int n = s_env[e].active ? a.beam_cnt[e0 + e] : 0;
-            for (int i = lane; i < n; i += 32) s_beams[e * a.L.max_beams + i] = a.beam_buf[static_cast<size_t>(e0 + e) * a.L.max_beams + i];
-            if (lane == 0) s_env[e].nbeams = n;
-        }
-    }
-    if (env_thread && s_env[my_e].active) {
-        EnvScratch& S = s_env[my_e];
-        uint8_t* g = s_grid + my_e * a.cell_stride;
+        if (valid) { S.pos[al] = static_cast<uint16_t>(me.key); S.ori[al] = static_cast<uint8_t>(me.ori); }
+        if (!grid_ready) { mbar_wait(mbar, 0); grid_ready = true; }  // grid tile landed
+        __syncwarp();
+        uint8_t* g = s_grid + (env_ok ? e : 0) * a.cell_stride;
+        const int my_idx = static_cast<int>(me.key >> 8) * a.W + static_cast<int>(me.key & 255);
         if (phases & SSD_PHASE_CONSUME) {  // map_env.py:178-181, agent.py:177-183 / 216-222
-            int eaten = 0;
-            for (int ag = 0; ag < N; ++ag) {
-                const int idx = (S.pos[ag] >> 8) * a.W + (S.pos[ag] & 255);
-                if (g[idx] == 'A') { S.rew[ag] += 1; g[idx] = ' '; ++eaten; }
-            }
-            if (eaten) atomicAdd(&s_stats[2], eaten);
+            const bool on_apple = valid && active && g[my_idx] == 'A';
+            // agents sharing a cell (appendix A.2 quirk): the first one in agent order eats
+            const uint32_t same = __match_any_sync(0xffffffffu, on_apple ? (me.key | static_cast<uint32_t>(gbase) << 16) : (0x80000000u | lane));
+            __syncwarp();
+            if (on_apple && (__ffs(same) - 1) == lane) { g[my_idx] = ' '; me.rew += 1; atomicAdd(&s_stats[2], 1); }
+            __syncwarp();
         }
         if ((phases & SSD_PHASE_BEAMS) && KIND != SSD_KIND_PLAIN) {  // update_custom_moves map_env.py:545-552
-            for (int k = 0; k < N; ++k) {
-                const int ag = S.order[k];
-                const int act = S.act[ag];
-                if (act == 7) {  // FIRE: harvest.py:62-67, cleanup.py:97-101; agent.py:170-172
-                    S.rew[ag] -= 1;
-                    atomicAdd(&s_stats[3], 1);
-                    fire_beam(a, S, g, s_wall, s_beams + my_e * a.L.max_beams, ag, false, s_stats);
-                } else if (act == 8 && KIND == SSD_KIND_CLEANUP) {  // CLEAN: cleanup.py:102-110
-                    fire_beam(a, S, g, s_wall, s_beams + my_e * a.L.max_beams, ag, true, s_stats);
+            for (int k = 0; k < N; ++k) {  // action-dict order
+                const int ag = env_ok ? S.order[k] : 0;
+                const int act_k = __shfl_sync(0xffffffffu, me.act, ag, G);
+                const uint32_t key_k = __shfl_sync(0xffffffffu, me.key, ag, G);
+                const int ori_k = __shfl_sync(0xffffffffu, me.ori, ag, G);
+                const bool fire = active && (act_k == 7 || (KIND == SSD_KIND_CLEANUP && act_k == 8));
+                if (!__any_sync(0xffffffffu, fire)) continue;
+                const bool clean = act_k == 8;
+                int upd = -1, hits = 0, n = 0;
+                if (fire && al < 3) n = ray_walk(a, S, g, s_wall, key_k, ori_k, al, clean, upd, hits);
+                if (fire && al == ag && !clean) { me.rew -= 1; atomicAdd(&s_stats[3], 1); }  // fire_beam agent.py:170-172
+                __syncwarp();
+                if (fire && al < 3) {
+                    S.raylen[k * 3 + al] = static_cast<uint8_t>(n);
+                    if (al == 0) S.firech[k] = clean ? 'C' : 'F';
+                    if (upd >= 0) { g[upd] = 'R'; atomicAdd(&s_stats[5], 1); }  // update_map :551-558, before the next agent fires
+                    if (hits) atomicAdd(&s_stats[4], hits);
                 }
+                __syncwarp();
             }
         }
-        if (phases & SSD_PHASE_SPAWN)  // flag agent cells for the spawn pass
-            for (int ag = 0; ag < N; ++ag) g[(S.pos[ag] >> 8) * a.W + (S.pos[ag] & 255)] |= 0x80;
+        if (valid && active) {
+            me.rew += S.rew[al];  // -50 per hit taken
+            if (phases & (SSD_PHASE_MOVES | SSD_PHASE_CONSUME | SSD_PHASE_BEAMS)) {
+                a.agents[gi] = (me.key >> 8) | (me.key & 255) << 8 | static_cast<uint32_t>(me.ori) << 16;
+                if (a.rew) a.rew[gi] = me.rew;
+            }
+            if (phases & SSD_PHASE_SPAWN) g[my_idx] |= 0x80;  // flag agent cells for the spawn pass
+        }
+    }
+    if (!grid_ready) mbar_wait(mbar, 0);
+    // beams recorded by an earlier phase call of this step (phase-split mode only)
+    if (a.use_beam_buf) {
+        __syncthreads();
+        const bool load = (phases & SSD_PHASE_RENDER) && !(phases & SSD_PHASE_BEAMS);
+        const bool store = (phases & SSD_PHASE_BEAMS) && !(phases & SSD_PHASE_RENDER);
+        for (int i = tid; i < E * 64; i += nthr) {
+            const int e = i >> 6, q = i & 63;
+            if (!s_env[e].active) continue;
+            uint8_t* p = q < 48 ? &s_env[e].raylen[q] : &s_env[e].firech[q - 48];
+            uint8_t* gp = a.beam_buf + static_cast<size_t>(e0 + e) * 64 + q;
+            if (load) *p = *gp;
+            if (store) *gp = *p;
+        }
     }
     __syncthreads();
 
@@ -582,53 +614,58 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_kernel(const __grid_cons
         }
         __syncthreads();
     }
-    if ((phases & SSD_PHASE_SPAWN) && env_thread && s_env[my_e].active) {
-        EnvScratch& S = s_env[my_e];
-        uint8_t* g = s_grid + my_e * a.cell_stride;
-        for (int ag = 0; ag < N; ++ag) g[(S.pos[ag] >> 8) * a.W + (S.pos[ag] & 255)] &= 0x7F;
-    }
-    if (phases & SSD_PHASE_SPAWN) __syncthreads();
 
-    // ---- store: state back to HBM
-    if (phases & (SSD_PHASE_MOVES | SSD_PHASE_CONSUME | SSD_PHASE_BEAMS | SSD_PHASE_SPAWN)) {
+    // ---- store: grid tile back to HBM (bit 7 = agent flag of the spawn pass, stripped on the way out)
+    if (phases & (SSD_PHASE_CONSUME | SSD_PHASE_BEAMS | SSD_PHASE_SPAWN)) {
         const int vec_per_env = a.cell_stride / 16;
         uint4* gdst = reinterpret_cast<uint4*>(a.grid + static_cast<size_t>(e0) * a.cell_stride);
         const uint4* gsrc = reinterpret_cast<const uint4*>(s_grid);
-        for (int i = tid; i < E * vec_per_env; i += nthr)
-            if (s_env[i / vec_per_env].active) gdst[i] = gsrc[i];
-        for (int i = tid; i < E * N; i += nthr) {
-            const int e = i / N, ag = i - e * N;
-            const EnvScratch& S = s_env[e];
-            if (!S.active) continue;
-            const size_t gi = static_cast<size_t>(e0 + e) * N + ag;
-            a.agents[gi] = (S.pos[ag] >> 8) | (S.pos[ag] & 255) << 8 | static_cast<uint32_t>(S.ori[ag]) << 16;
-            if (a.rew) a.rew[gi] = S.rew[ag];
-        }
-        if (a.use_beam_buf && (phases & SSD_PHASE_BEAMS) && !(phases & SSD_PHASE_RENDER)) {
-            for (int e = warp; e < E; e += nwarps) {
-                if (!s_env[e].active) continue;
-                const int n = s_env[e].nbeams;
-                for (int i = lane; i < n; i += 32) a.beam_buf[static_cast<size_t>(e0 + e) * a.L.max_beams + i] = s_beams[e * a.L.max_beams + i];
-                if (lane == 0) a.beam_cnt[e0 + e] = n;
-            }
+        for (int i = tid; i < E * vec_per_env; i += nthr) {
+            if (!s_env[i / vec_per_env].active) continue;
+            uint4 v = gsrc[i];
+            v.x &= 0x7F7F7F7Fu; v.y &= 0x7F7F7F7Fu; v.z &= 0x7F7F7F7Fu; v.w &= 0x7F7F7F7Fu;
+            gdst[i] = v;
         }
     }
 
     // ---- phase C: overlay + render + coalesced stores
     if ((phases & SSD_PHASE_RENDER) && a.obs != nullptr) {
         __syncthreads();  // the grid write-back above has read the tile
-        if (env_thread) {  // get_map_with_agents map_env.py:280-302: agents in order, then beams in order
-            EnvScratch& S = s_env[my_e];
-            uint8_t* g = s_grid + my_e * a.cell_stride;
-            for (int ag = 0; ag < N; ++ag) g[(S.pos[ag] >> 8) * a.W + (S.pos[ag] & 255)] = agent_char(ag);
-            const uint32_t* bl = s_beams + my_e * a.L.max_beams;
-            for (int i = 0; i < S.nbeams; ++i) g[bl[i] & 0xffff] = static_cast<uint8_t>(bl[i] >> 16);
+        // get_map_with_agents map_env.py:280-302: agents in agent order (the last one on a cell wins),
+        // then beams in firing order (a later beam overwrites an earlier one)
+        for (int ebase = warp * (32 / G); ebase < E; ebase += slots) {
+            const int e = ebase + lane / G;
+            const bool env_ok = e < E;
+            const EnvScratch& S = s_env[env_ok ? e : 0];
+            uint8_t* g = s_grid + (env_ok ? e : 0) * a.cell_stride;
+            const bool valid = env_ok && al < N;
+            const uint32_t key = valid ? S.pos[al] : 0;
+            const uint32_t same = __match_any_sync(0xffffffffu, valid ? (key | static_cast<uint32_t>(gbase) << 16) : (0x80000000u | lane));
+            if (valid && (31 - __clz(same)) == lane) g[(key >> 8) * a.W + (key & 255)] = agent_char(al);
+            __syncwarp();
+            if (KIND != SSD_KIND_PLAIN) {
+                for (int k = 0; k < N; ++k) {
+                    const uint32_t ch = env_ok ? S.firech[k] : 0;
+                    if (!__any_sync(0xffffffffu, ch != 0)) continue;
+                    if (ch != 0 && al < 3) {
+                        const int ag = S.order[k];
+                        const int ori = S.ori[ag];
+                        const int d0 = (ori == 1) - (ori == 3), d1 = (ori == 2) - (ori == 0);
+                        int r = static_cast<int>(S.pos[ag] >> 8) + d0, c = static_cast<int>(S.pos[ag] & 255) + d1;
+                        if (al == 1) { r += -d1 - d0; c += d0 - d1; }
+                        if (al == 2) { r -= -d1 + d0; c -= d0 + d1; }
+                        const int n = S.raylen[k * 3 + al];
+                        for (int i = 0; i < n; ++i) { g[r * a.W + c] = static_cast<uint8_t>(ch); r += d0; c += d1; }
+                    }
+                    __syncwarp();
+                }
+            }
         }
         uint4* s_view = reinterpret_cast<uint4*>(smem + a.L.view);
         for (int i = tid; i < E * N; i += nthr) s_view[i] = view_param(a, s_env[i / N], i / N, i % N);
         __syncthreads();
         uint8_t* dst = a.obs + static_cast<size_t>(e0) * a.obs_env;
-        bool all_active = (nvalid == E) && (a.mask == nullptr);
+        const bool all_active = (nvalid == E) && (a.mask == nullptr);
         if constexpr (VT > 0) {
             if (all_active) {
                 uint32_t* stage = reinterpret_cast<uint32_t*>(smem + a.L.stage + warp * a.L.stage_stride);
