@@ -42,14 +42,14 @@ uint64_t threshold53(double p) {
 struct SsdEnv {
     SsdConfig cfg{};
     int B = 0, B_pad = 0, E = 0, threads = 128;
-    int HW = 0, cell_stride = 0, V = 0, obs_env = 0, n_apple = 0, n_waste = 0, n_spawn = 0;
+    int HW = 0, Ws = 0, env_bytes = 0, pad_bytes = 0, tile_stride = 0, V = 0, obs_env = 0, n_apple = 0, n_waste = 0, n_spawn = 0;
     uint64_t seed = 0;
     uint32_t t = 0;
     int64_t launches = 0;
     ssd::SmemLayout L{};
     // device allocations
     std::vector<void*> allocs;
-    uint32_t* d_wall = nullptr; uint16_t* d_apple = nullptr; uint8_t* d_apple_nb = nullptr;
+    uint16_t* d_apple = nullptr;
     uint16_t* d_waste = nullptr; uint16_t* d_spawn = nullptr; uint32_t* d_color = nullptr;
     uint64_t* d_hthr = nullptr; double* d_hp = nullptr;
     uint64_t* d_athr = nullptr; double* d_ap = nullptr; uint64_t* d_wthr = nullptr; double* d_wp = nullptr;
@@ -90,15 +90,13 @@ ssd::SmemLayout make_layout(const SsdEnv& h, int E, int threads) {
     ssd::SmemLayout L{};
     uint32_t off = 0;
     L.mbar = off; off += 16;
-    L.grid = off; off += static_cast<uint32_t>(E) * h.cell_stride;
-    L.wall = off; off += up16(((h.HW + 31) / 32) * 4);
+    L.grid = off; off += static_cast<uint32_t>(E) * h.tile_stride + 16;
     L.color = off; off += 512;
     L.apple = off; off += up16(h.n_apple * 2);
-    L.apple_nb = off; off += up16(h.n_apple);
     L.env = off; off += static_cast<uint32_t>(E) * sizeof(ssd::EnvScratch);
     L.list_stride = up16(std::max(h.n_apple * 2, h.n_waste * 4));
     L.list = off; off += (threads / 32) * L.list_stride;
-    L.view = off; off += static_cast<uint32_t>(E) * h.cfg.num_agents * 16;
+    L.view = off; off += up16(static_cast<uint32_t>(E) * h.cfg.num_agents * 8);
     L.stage_stride = up16(32u * 3u * h.V);
     L.stage = off; off += (threads / 32) * L.stage_stride;
     L.stats = off; off += 32;
@@ -110,16 +108,15 @@ void fill_args(SsdEnv* h, ssd::StepArgs& a) {
     memset(&a, 0, sizeof a);
     const SsdConfig& c = h->cfg;
     a.kind = c.kind; a.H = c.height; a.W = c.width; a.N = c.num_agents; a.r = c.view_radius; a.V = h->V;
-    a.beam_len = c.beam_len; a.HW = h->HW; a.cell_stride = h->cell_stride;
+    a.beam_len = c.beam_len; a.Ws = h->Ws; a.env_bytes = h->env_bytes; a.pad_bytes = h->pad_bytes; a.tile_stride = h->tile_stride;
     a.n_apple = h->n_apple; a.n_waste = h->n_waste; a.area = c.potential_waste_area;
     a.obs_env = h->obs_env;
-    a.nv_magic = static_cast<uint32_t>((1ull << 32) / static_cast<uint32_t>(a.N * a.V) + 1);
     a.E = h->E; a.G = h->cfg.num_agents <= 8 ? 8 : 16; a.env_begin = 0; a.env_end = h->B;
     a.phases = SSD_PHASE_ALL; a.rotate = 1; a.spawn_stream = ssd::STREAM_SPAWN;
     a.key0 = static_cast<uint32_t>(h->seed); a.key1 = static_cast<uint32_t>(h->seed >> 32); a.t = h->t;
     a.env_id0 = c.env_id_offset;
     a.L = h->L;
-    a.wall_bits = h->d_wall; a.apple_cell = h->d_apple; a.apple_nb = h->d_apple_nb; a.waste_cell = h->d_waste;
+    a.apple_cell = h->d_apple; a.waste_cell = h->d_waste;
     a.color = h->d_color; a.harvest_thr = h->d_hthr; a.harvest_p = h->d_hp;
     a.apple_thr = h->d_athr; a.apple_p = h->d_ap; a.waste_thr = h->d_wthr; a.waste_p = h->d_wp;
     a.grid = h->d_grid; a.agents = h->d_agents; a.beam_buf = h->d_beam_buf;
@@ -180,36 +177,29 @@ int ssd_create(const SsdConfig* cfg, ssd_handle* out) {
     SsdEnv* h = new (std::nothrow) SsdEnv();
     if (!h) return fail(SSD_ERR_INVALID, "out of host memory");
     h->cfg = *cfg;
-    h->B = cfg->num_envs; h->HW = H * W; h->cell_stride = static_cast<int>(up16(h->HW));
+    h->B = cfg->num_envs; h->HW = H * W;
+    h->Ws = static_cast<int>(up16(W + cfg->view_radius));  // >= r zero bytes after the W cells of every row
+    h->env_bytes = H * h->Ws; h->pad_bytes = cfg->view_radius * h->Ws; h->tile_stride = (H + 2 * cfg->view_radius) * h->Ws;
     h->V = 2 * cfg->view_radius + 1; h->obs_env = N * h->V * h->V * 3;
+    if (h->tile_stride > 65535) { delete h; return fail(SSD_ERR_UNSUPPORTED, "map tile of %d bytes exceeds the 16-bit cell index range", h->tile_stride); }
 
     // static tables
-    std::vector<uint32_t> wall((h->HW + 31) / 32, 0), color(128, 0);
+    std::vector<uint32_t> color(128, 0);
     std::vector<uint16_t> apple, waste, spawn;
-    std::vector<uint8_t> apple_nb, init_grid(h->cell_stride, 0);
+    std::vector<uint8_t> init_grid(h->env_bytes, 0);
     const uint8_t apple_ch = cfg->kind == SSD_KIND_HARVEST ? 'A' : (cfg->kind == SSD_KIND_CLEANUP ? 'B' : 0);
+    const int rr = cfg->view_radius;
     for (int r = 0; r < H; ++r)
         for (int c = 0; c < W; ++c) {
-            const int i = r * W + c;
-            const uint8_t ch = cfg->base_map[i];
+            const uint8_t ch = cfg->base_map[r * W + c];
+            const uint16_t tile_cell = static_cast<uint16_t>((r + rr) * h->Ws + c);
             uint8_t g = ' ';  // reset_map + build_walls + custom_reset (map_env.py:560-564, harvest.py:57-60, cleanup.py:84-92)
-            if (ch == '@') { wall[i >> 5] |= 1u << (i & 31); g = '@'; }
+            if (ch == '@') g = '@';
             else if (cfg->kind == SSD_KIND_HARVEST && ch == 'A') g = 'A';
             else if (cfg->kind == SSD_KIND_CLEANUP && (ch == 'H' || ch == 'R' || ch == 'S')) g = ch;
-            init_grid[i] = g;
-            if (apple_ch && ch == apple_ch) {
-                apple.push_back(static_cast<uint16_t>(i));
-                uint8_t m = 0;
-                int bit = 0;
-                for (int dr = -1; dr <= 1; ++dr)
-                    for (int dc = -1; dc <= 1; ++dc) {
-                        if (dr == 0 && dc == 0) continue;
-                        if (r + dr >= 0 && r + dr < H && c + dc >= 0 && c + dc < W) m |= 1u << bit;
-                        ++bit;
-                    }
-                apple_nb.push_back(m);
-            }
-            if (cfg->kind == SSD_KIND_CLEANUP && (ch == 'H' || ch == 'R')) waste.push_back(static_cast<uint16_t>(i));
+            init_grid[r * h->Ws + c] = g;
+            if (apple_ch && ch == apple_ch) apple.push_back(tile_cell);
+            if (cfg->kind == SSD_KIND_CLEANUP && (ch == 'H' || ch == 'R')) waste.push_back(tile_cell);
         }
     for (int s = 0; s < cfg->num_spawn_points; ++s)
         spawn.push_back(static_cast<uint16_t>(cfg->spawn_points[2 * s] << 8 | cfg->spawn_points[2 * s + 1]));
@@ -257,20 +247,20 @@ int ssd_create(const SsdConfig* cfg, ssd_handle* out) {
     h->B_pad = (h->B + E - 1) / E * E;
 
     int bad = 0;
-    bad |= h->upload(&h->d_wall, wall); bad |= h->upload(&h->d_apple, apple); bad |= h->upload(&h->d_apple_nb, apple_nb);
+    bad |= h->upload(&h->d_apple, apple);
     bad |= h->upload(&h->d_waste, waste); bad |= h->upload(&h->d_spawn, spawn); bad |= h->upload(&h->d_color, color);
     bad |= h->upload(&h->d_hthr, hthr); bad |= h->upload(&h->d_hp, hp); bad |= h->upload(&h->d_athr, athr);
     bad |= h->upload(&h->d_ap, ap); bad |= h->upload(&h->d_wthr, wthr); bad |= h->upload(&h->d_wp, wp);
     bad |= h->upload(&h->d_init_grid, init_grid);
-    bad |= h->alloc(&h->d_grid, static_cast<size_t>(h->B_pad) * h->cell_stride);
+    bad |= h->alloc(&h->d_grid, static_cast<size_t>(h->B_pad) * h->env_bytes);
     bad |= h->alloc(&h->d_agents, static_cast<size_t>(h->B_pad) * N);
     bad |= h->alloc(&h->d_beam_buf, static_cast<size_t>(h->B_pad) * 64);
     bad |= h->alloc(&h->d_stats, static_cast<size_t>(SSD_NUM_STATS));
     if (bad) { const char* m = cudaGetErrorString(cudaGetLastError()); ssd_destroy(h); return fail(SSD_ERR_CUDA, "device allocation failed: %s", m); }
     // initial state: post-reset_map grid, agents parked on the first spawn point (or cell 1,1)
     {
-        std::vector<uint8_t> g(static_cast<size_t>(h->B_pad) * h->cell_stride);
-        for (int b = 0; b < h->B_pad; ++b) memcpy(g.data() + static_cast<size_t>(b) * h->cell_stride, init_grid.data(), h->cell_stride);
+        std::vector<uint8_t> g(static_cast<size_t>(h->B_pad) * h->env_bytes);
+        for (int b = 0; b < h->B_pad; ++b) memcpy(g.data() + static_cast<size_t>(b) * h->env_bytes, init_grid.data(), h->env_bytes);
         const uint32_t park = spawn.empty() ? (1u | 1u << 8) : ((spawn[0] >> 8) | (spawn[0] & 255u) << 8);
         std::vector<uint32_t> ag(static_cast<size_t>(h->B_pad) * N, park);
         cudaError_t e1 = cudaMemcpy(h->d_grid, g.data(), g.size(), cudaMemcpyHostToDevice);
@@ -338,7 +328,7 @@ int ssd_set_state(ssd_handle h, const uint8_t* grid, const int16_t* pos, const u
         CUDA_TRY(cudaMemcpyAsync(h->d_io_ori, ori, np, cudaMemcpyDefault, st));
         grid = h->d_io_grid; pos = h->d_io_pos; ori = h->d_io_ori;
     }
-    CUDA_TRY(ssd::launch_pack_state(h->B, N, h->HW, h->cell_stride, grid, pos, ori, h->d_grid, h->d_agents, st));
+    CUDA_TRY(ssd::launch_pack_state(h->B, N, h->cfg.height, h->cfg.width, h->Ws, grid, pos, ori, h->d_grid, h->d_agents, st));
     h->launches++;
     return SSD_OK;
 }
@@ -351,7 +341,7 @@ int ssd_get_state(ssd_handle h, uint8_t* grid, int16_t* pos, uint8_t* ori, void*
     const size_t ng = static_cast<size_t>(h->B) * h->HW, np = static_cast<size_t>(h->B) * N;
     const bool dev = (!grid || is_device_ptr(grid)) && (!pos || is_device_ptr(pos)) && (!ori || is_device_ptr(ori));
     if (dev) {
-        CUDA_TRY(ssd::launch_unpack_state(h->B, N, h->HW, h->cell_stride, h->d_grid, h->d_agents, grid, pos, ori, st));
+        CUDA_TRY(ssd::launch_unpack_state(h->B, N, h->cfg.height, h->cfg.width, h->Ws, h->d_grid, h->d_agents, grid, pos, ori, st));
         h->launches++;
         return SSD_OK;
     }
@@ -359,7 +349,7 @@ int ssd_get_state(ssd_handle h, uint8_t* grid, int16_t* pos, uint8_t* ori, void*
         if (h->alloc(&h->d_io_grid, ng) || h->alloc(&h->d_io_pos, np * 2) || h->alloc(&h->d_io_ori, np))
             return fail(SSD_ERR_CUDA, "staging allocation failed");
     }
-    CUDA_TRY(ssd::launch_unpack_state(h->B, N, h->HW, h->cell_stride, h->d_grid, h->d_agents, h->d_io_grid, h->d_io_pos, h->d_io_ori, st));
+    CUDA_TRY(ssd::launch_unpack_state(h->B, N, h->cfg.height, h->cfg.width, h->Ws, h->d_grid, h->d_agents, h->d_io_grid, h->d_io_pos, h->d_io_ori, st));
     h->launches++;
     if (grid) CUDA_TRY(cudaMemcpyAsync(grid, h->d_io_grid, ng, cudaMemcpyDefault, st));
     if (pos) CUDA_TRY(cudaMemcpyAsync(pos, h->d_io_pos, np * 2 * sizeof(int16_t), cudaMemcpyDefault, st));
@@ -374,7 +364,7 @@ int ssd_reset(ssd_handle h, const uint8_t* mask, uint8_t* obs_out, void* stream)
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     ssd::ResetArgs r{};
-    r.N = h->cfg.num_agents; r.n_spawn = h->n_spawn; r.cell_stride = h->cell_stride; r.env_end = h->B;
+    r.N = h->cfg.num_agents; r.n_spawn = h->n_spawn; r.env_bytes = h->env_bytes; r.env_end = h->B;
     r.key0 = static_cast<uint32_t>(h->seed); r.key1 = static_cast<uint32_t>(h->seed >> 32); r.t = h->t;
     r.env_id0 = h->cfg.env_id_offset;
     r.spawn_key = h->d_spawn; r.init_grid = h->d_init_grid; r.mask = mask; r.grid = h->d_grid; r.agents = h->d_agents;

@@ -1,6 +1,7 @@
 // Fused MapEnv.step kernel for sm_100a: one CTA steps E independent environments.
 //
-//   load   grid tile (E x cell_stride bytes) by one TMA bulk copy; agent table, actions by plain loads
+//   load   E grid tiles by TMA bulk copies into zero-padded shared-memory tiles (ssd_internal.h),
+//          agent table and actions straight into registers (one lane per agent)
 //   A      moves (map_env.py:357-543), consume (:178-181), beams (:545-649): ONE LANE PER AGENT, a
 //          group of 8 (or 16) lanes per env.  Conflict-free moves are resolved with shuffles; an env
 //          with any contested / occupied target falls back to the literal sequential emulation of
@@ -20,9 +21,13 @@
 
 namespace ssd {
 
+__device__ __forceinline__ int tile_idx(const StepArgs& a, uint32_t key) {
+    return (static_cast<int>(key >> 8) + a.r) * a.Ws + static_cast<int>(key & 255);
+}
+
 // ====================================================================== phase A: moves
 __device__ __forceinline__ bool occupied(const uint16_t* p, int N, uint32_t key) {
-    bool f = false;
+    bool f = false;  // `x in self.agent_pos` (map_env.py:251-253)
     for (int a = 0; a < N; ++a) f |= (p[a] == key);
     return f;
 }
@@ -32,6 +37,8 @@ __device__ __forceinline__ int by_pos(const uint16_t* p, int N, uint32_t key) {
     return o;
 }
 
+// Literal emulation of the conflict resolution of update_moves (map_env.py:394-543) for one env,
+// run by a single lane.  S.pos / S.tgt hold positions and wall-clipped targets of the movers.
 template <bool TAPE>
 __device__ __noinline__ void moves_slow(const StepArgs& a, EnvScratch& S, uint32_t movers, int local_env,
                                          const PhiloxKey& pk) {
@@ -126,17 +133,15 @@ __device__ __noinline__ void moves_slow(const StepArgs& a, EnvScratch& S, uint32
     }
 }
 
-// ====================================================================== phase A: one lane per agent
 struct AgentLane {
-    uint32_t key;   // row << 8 | col
+    uint32_t key;  // row << 8 | col
     int ori, act, rew;
 };
 
 // update_moves for one group of G lanes (= one env).  All 32 lanes of the warp call this.
 template <bool TAPE>
-__device__ __forceinline__ void moves_group(const StepArgs& a, EnvScratch& S, const uint32_t* s_wall, AgentLane& me,
-                                            bool valid, int al, int G, int local_env, const PhiloxKey& pk) {
-    const int W = a.W;
+__device__ __forceinline__ void moves_group(const StepArgs& a, EnvScratch& S, const uint8_t* g, AgentLane& me, bool valid,
+                                            int al, int G, int local_env, const PhiloxKey& pk) {
     const int act = me.act;
     bool mover = false;
     uint32_t tgt = me.key;
@@ -148,10 +153,8 @@ __device__ __forceinline__ void moves_group(const StepArgs& a, EnvScratch& S, co
             int r0, r1;  // rotate_action map_env.py:701-716
             if (o == 0) { r0 = v0; r1 = v1; } else if (o == 3) { r0 = v1; r1 = -v0; }
             else if (o == 1) { r0 = -v1; r1 = v0; } else { r0 = -v0; r1 = -v1; }
-            const int nr = static_cast<int>(me.key >> 8) + r0, nc = static_cast<int>(me.key & 255) + r1;
-            const int idx = nr * W + nc;
-            const bool wall = (s_wall[idx >> 5] >> (idx & 31)) & 1;  // agent.py:105-113
-            tgt = wall ? me.key : static_cast<uint32_t>(nr << 8 | nc);
+            const uint32_t nkey = static_cast<uint32_t>((static_cast<int>(me.key >> 8) + r0) << 8 | (static_cast<int>(me.key & 255) + r1));
+            tgt = (g[tile_idx(a, nkey)] == '@') ? me.key : nkey;  // agent.py:105-113 you can't walk through walls
             mover = true;
         } else if (act == 5) {
             me.ori = (me.ori + 1) & 3;  // TURN_CLOCKWISE map_env.py:729-737
@@ -161,8 +164,8 @@ __device__ __forceinline__ void moves_group(const StepArgs& a, EnvScratch& S, co
     }
     // Fast path: all targets distinct and no target currently occupied by ANOTHER agent => the
     // contested pass is empty and the first fix-point pass moves everybody (a STAY hits rule (1)
-    // and keeps its place).  Anything else runs the literal emulation below.
-    const uint32_t pos_x = valid ? me.key : 0xFFFF0000u | al;       // never equal to a real cell
+    // and keeps its place).  Anything else runs the literal emulation.
+    const uint32_t pos_x = valid ? me.key : 0xFFFF0000u | al;  // never equal to a real cell
     const uint32_t tgt_x = mover ? tgt : 0xFFFE0000u | al;
     bool conflict = false;
     for (int d = 1; d < G; ++d) {
@@ -171,12 +174,13 @@ __device__ __forceinline__ void moves_group(const StepArgs& a, EnvScratch& S, co
         const uint32_t tgt_y = __shfl_sync(0xffffffffu, tgt_x, src, G);
         conflict |= mover && (pos_y == tgt || tgt_y == tgt);
     }
-    const uint32_t gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << ((threadIdx.x & 31) & ~(G - 1));
+    const int gshift = (threadIdx.x & 31) & ~(G - 1);
+    const uint32_t gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << gshift;
     const uint32_t conf_all = __ballot_sync(0xffffffffu, conflict);
     const uint32_t conf = conf_all & gmask;
-    const uint32_t movers = (__ballot_sync(0xffffffffu, mover) & gmask) >> ((threadIdx.x & 31) & ~(G - 1));
+    const uint32_t movers = (__ballot_sync(0xffffffffu, mover) & gmask) >> gshift;
     if (conf == 0 && mover) me.key = tgt;
-    if (conf_all != 0) {  // warp-uniform branch: the groups without a conflict just keep the barriers company
+    if (conf_all != 0) {  // warp-uniform branch: groups without a conflict just keep the barriers company
         if (conf != 0 && valid) { S.pos[al] = static_cast<uint16_t>(me.key); S.tgt[al] = static_cast<uint16_t>(tgt); }
         __syncwarp();
         if (conf != 0 && al == 0) moves_slow<TAPE>(a, S, movers, local_env, pk);
@@ -185,34 +189,34 @@ __device__ __forceinline__ void moves_group(const StepArgs& a, EnvScratch& S, co
     }
 }
 
-// One firing agent of one env: its three rays walk on the group's lanes 0..2 (map_env.py:566-649).
-// Returns the number of painted cells of this lane's ray.
-__device__ __forceinline__ int ray_walk(const StepArgs& a, EnvScratch& S, uint8_t* g, const uint32_t* s_wall, uint32_t key,
-                                        int ori, int s, bool clean, int& upd, int& hits) {
-    const int N = a.N, H = a.H, W = a.W;
+// One ray of a beam (map_env.py:566-649); the three rays of a firing agent walk on lanes 0..2 of
+// its group.  The map is wall-enclosed (checked by ssd_create), so the reference's bounds test
+// (:615) can never fire before the wall test (:616).  Returns the number of painted cells.
+__device__ __forceinline__ int ray_walk(const StepArgs& a, EnvScratch& S, uint8_t* g, uint32_t key, int ori, int s,
+                                        bool clean, int& upd, int& hits) {
+    const int N = a.N;
     const int d0 = (ori == 1) - (ori == 3), d1 = (ori == 2) - (ori == 0);  // ORIENTATIONS map_env.py:19-22
-    const int rs0 = -d1, rs1 = d0;                                          // rotate_right :607,715
     int r = static_cast<int>(key >> 8) + d0, c = static_cast<int>(key & 255) + d1;  // :608-613
-    if (s == 1) { r += rs0 - d0; c += rs1 - d1; }
-    if (s == 2) { r -= rs0 + d0; c -= rs1 + d1; }
+    if (s == 1) { r += -d1 - d0; c += d0 - d1; }  // start + rotate_right(d) - d   (:607-609)
+    if (s == 2) { r -= -d1 + d0; c -= d0 + d1; }  // start - rotate_right(d) - d
+    const int dp = d0 * a.Ws + d1;
+    int p = (r + a.r) * a.Ws + c;
     int n = 0;
     for (int i = 0; i < a.beam_len; ++i) {
-        if (r < 0 || r >= H || c < 0 || c >= W) break;          // :615, :645
-        const int idx = r * W + c;
-        if ((s_wall[idx >> 5] >> (idx & 31)) & 1) break;       // :616
-        const uint32_t cell = r << 8 | c;
-        const bool isH = clean && g[idx] == 'H';
-        const int hit = by_pos(S.pos, N, cell);                 // :621-622 agents absorb beams
+        const uint8_t cell = g[p];
+        if (cell == '@') break;                                 // :616
+        const bool isH = clean && cell == 'H';
+        const int hit = by_pos(S.pos, N, static_cast<uint32_t>(r << 8 | c));  // :621-622 agents absorb beams
         if (hit >= 0) {
             if (!clean) { S.rew[hit] -= 50; ++hits; }           // agent.py:166-168, 212-214
             ++n;                                                // :624
-            if (isH) upd = idx;                                 // :625-628
+            if (isH) upd = p;                                   // :625-628
             break;
         }
-        if (isH) upd = idx;                                     // :632-634
+        if (isH) upd = p;                                       // :632-634
         ++n;                                                    // :636
         if (isH) break;                                         // blocking_cells :639
-        r += d0; c += d1;
+        r += d0; c += d1; p += dp;
     }
     return n;
 }
@@ -221,10 +225,9 @@ __device__ __forceinline__ int ray_walk(const StepArgs& a, EnvScratch& S, uint8_
 // Agent cells are flagged with bit 7 while the spawn pass runs ("[row, col] not in self.agent_pos",
 // harvest.py:90, cleanup.py:138); consume already turned every apple under an agent into ' '.
 template <bool TAPE>
-__device__ __forceinline__ void harvest_spawn(const StepArgs& a, uint8_t* g, const uint16_t* s_apple,
-                                              const uint8_t* s_apple_nb, uint16_t* list, int local_env,
-                                              const PhiloxKey& pk, int lane, int* s_stats) {
-    const int W = a.W, n_apple = a.n_apple;
+__device__ __forceinline__ void harvest_spawn(const StepArgs& a, uint8_t* g, const uint16_t* s_apple, uint16_t* list,
+                                              int local_env, const PhiloxKey& pk, int lane, int* s_stats) {
+    const int Ws = a.Ws, n_apple = a.n_apple;
     int base = 0;
     for (int i0 = 0; i0 < n_apple; i0 += 32) {  // eligibility scan in row-major apple-point order (harvest.py:87-90)
         const int i = i0 + lane;
@@ -240,17 +243,10 @@ __device__ __forceinline__ void harvest_spawn(const StepArgs& a, uint8_t* g, con
         const int j = j0 + lane;
         if (j < n_draw) {
             const int i = list[j];
-            const int idx = s_apple[i];
-            const uint32_t nbm = s_apple_nb[i];
-            int n = 0;  // 3x3 window, j*j + k*k <= APPLE_RADIUS(2)  (harvest.py:92-99)
-            n += (nbm & 1) && g[idx - W - 1] == 'A';
-            n += (nbm & 2) && g[idx - W] == 'A';
-            n += (nbm & 4) && g[idx - W + 1] == 'A';
-            n += (nbm & 8) && g[idx - 1] == 'A';
-            n += (nbm & 16) && g[idx + 1] == 'A';
-            n += (nbm & 32) && g[idx + W - 1] == 'A';
-            n += (nbm & 64) && g[idx + W] == 'A';
-            n += (nbm & 128) && g[idx + W + 1] == 'A';
+            const uint8_t* q = g + s_apple[i];
+            // 3x3 window, j*j + k*k <= APPLE_RADIUS(2) (harvest.py:92-99); cells outside the map are 0 in the tile
+            int n = (q[-Ws - 1] == 'A') + (q[-Ws] == 'A') + (q[-Ws + 1] == 'A') + (q[-1] == 'A') + (q[1] == 'A') +
+                    (q[Ws - 1] == 'A') + (q[Ws] == 'A') + (q[Ws + 1] == 'A');
             n = n < 3 ? n : 3;
             bool spawn = false;
             if (TAPE) spawn = a.tape_u[static_cast<size_t>(local_env) * a.u_stride + j] < a.harvest_p[n];
@@ -271,8 +267,8 @@ __device__ __forceinline__ void cleanup_spawn(const StepArgs& a, uint8_t* g, con
     const int n_apple = a.n_apple, n_waste = a.n_waste;
     // compute_permitted_area / compute_probabilities, cleanup.py:156-179: count 'H' over the whole grid
     int cnt = 0;
-    for (int i = lane * 16; i < a.cell_stride; i += 512) {
-        const uint4 v = *reinterpret_cast<const uint4*>(g + i);
+    for (int i = lane * 16; i < a.env_bytes; i += 512) {
+        const uint4 v = *reinterpret_cast<const uint4*>(g + a.pad_bytes + i);
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -311,7 +307,11 @@ __device__ __forceinline__ void cleanup_spawn(const StepArgs& a, uint8_t* g, con
                 const int i = i0 + lane;
                 bool el = false;
                 int idx = 0;
-                if (i < n_waste) { idx = wo[i]; el = (g[idx] & 0x7F) != 'H'; }       // :149
+                if (i < n_waste) {  // tape cells are row*W+col of the reference's map
+                    const int cell = wo[i];
+                    idx = (cell / a.W + a.r) * a.Ws + cell % a.W;
+                    el = (g[idx] & 0x7F) != 'H';  // :149
+                }
                 const uint32_t m = __ballot_sync(0xffffffffu, el);
                 bool ok = false;
                 if (el) ok = a.tape_u[static_cast<size_t>(local_env) * a.u_stride + base + __popc(m & lanemask_lt())] < waste_p;
@@ -366,24 +366,18 @@ __device__ __forceinline__ void cleanup_spawn(const StepArgs& a, uint8_t* g, con
 
 // ====================================================================== phase C: rendering
 // Per-agent window geometry (np.rot90 index algebra of rotate_view map_env.py:669-689 folded with
-// return_view utility_funcs.py:59-114): view pixel (i, j) reads tile byte a0 + i*si + j*sj and is
-// inside the map iff ilo <= i < ilo+ilen and jlo <= j < jlo+jlen; everything else is '0' = black.
-__device__ __forceinline__ uint4 view_param(const StepArgs& a, const EnvScratch& S, int e, int ag) {
-    const int pr = S.pos[ag] >> 8, pc = S.pos[ag] & 255, r = a.r, V = a.V, H = a.H, W = a.W;
+// return_view utility_funcs.py:59-114): view pixel (i, j) reads tile byte a0 + i*si + j*sj.  The
+// tile is zero padded by r cells on every side, so no pixel needs a bounds test.
+__device__ __forceinline__ uint2 view_param(const StepArgs& a, const EnvScratch& S, int e, int ag) {
+    const int pr = S.pos[ag] >> 8, pc = S.pos[ag] & 255, r = a.r, Ws = a.Ws;
     const int k = a.rotate ? ((4 - S.ori[ag]) & 3) : 0;  // UP 0, LEFT 1, DOWN 2, RIGHT 3
-    int a0, si, sj, ilo, ihi, jlo, jhi;
-    if (k == 0)      { a0 = (pr - r) * W + pc - r; si = W;  sj = 1;  ilo = r - pr;         ihi = H - 1 - pr + r; jlo = r - pc;         jhi = W - 1 - pc + r; }
-    else if (k == 2) { a0 = (pr + r) * W + pc + r; si = -W; sj = -1; ilo = pr + r - H + 1; ihi = pr + r;         jlo = pc + r - W + 1; jhi = pc + r; }
-    else if (k == 1) { a0 = (pr - r) * W + pc + r; si = -1; sj = W;  ilo = pc + r - W + 1; ihi = pc + r;         jlo = r - pr;         jhi = H - 1 - pr + r; }
-    else             { a0 = (pr + r) * W + pc - r; si = 1;  sj = -W; ilo = r - pc;         ihi = W - 1 - pc + r; jlo = pr + r - H + 1; jhi = pr + r; }
-    ilo = max(ilo, 0); jlo = max(jlo, 0); ihi = min(ihi, V - 1); jhi = min(jhi, V - 1);
-    const int ilen = max(ihi - ilo + 1, 0), jlen = max(jhi - jlo + 1, 0);
-    uint4 p;
-    p.x = static_cast<uint32_t>(a0 + e * a.cell_stride);
-    p.y = (static_cast<uint32_t>(si) & 0xffffu) | static_cast<uint32_t>(sj) << 16;
-    p.z = static_cast<uint32_t>(jlo) | static_cast<uint32_t>(jlen) << 8 | static_cast<uint32_t>(ilo) << 16 | static_cast<uint32_t>(ilen) << 24;
-    p.w = 0;
-    return p;
+    int a0, si, sj;  // in-tile row of map row x is x + r
+    if (k == 0)      { a0 = pr * Ws + pc - r;           si = Ws;  sj = 1; }    // cell (pr-r+i, pc-r+j)
+    else if (k == 2) { a0 = (pr + 2 * r) * Ws + pc + r; si = -Ws; sj = -1; }   // cell (pr+r-i, pc+r-j)
+    else if (k == 1) { a0 = pr * Ws + pc + r;           si = -1;  sj = Ws; }   // cell (pr-r+j, pc+r-i)
+    else             { a0 = (pr + 2 * r) * Ws + pc - r; si = 1;   sj = -Ws; }  // cell (pr+r-j, pc-r+i)
+    return make_uint2(static_cast<uint32_t>(a0 + e * a.tile_stride),
+                      (static_cast<uint32_t>(si) & 0xffffu) | static_cast<uint32_t>(sj) << 16);
 }
 
 // One thread renders one row of one agent's view (V pixels = 3V bytes).  A warp owns 32 consecutive
@@ -392,9 +386,8 @@ __device__ __forceinline__ uint4 view_param(const StepArgs& a, const EnvScratch&
 // phases 0,1,2,3: each thread owns the 32-bit words whose FIRST byte lies in its row and takes the
 // first pixel of the next row from the neighbouring lane), then stored with coalesced 16-byte writes.
 template <int VT>
-__device__ __forceinline__ void render_rows(const StepArgs& a, const uint4* s_view, const uint8_t* s_grid,
-                                            const uint32_t* s_color, uint32_t* stage, uint8_t* dst, int total_rows,
-                                            bool aligned16) {
+__device__ __forceinline__ void render_rows(const uint2* s_view, const uint8_t* s_grid, const uint32_t* s_color,
+                                            uint32_t* stage, uint8_t* dst, int total_rows, bool aligned16) {
     constexpr int RB = 3 * VT;           // bytes per view row
     constexpr int NP = (RB + 3 + 3) / 4; // words covering the row plus the next row's first pixel
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -405,14 +398,11 @@ __device__ __forceinline__ void render_rows(const StepArgs& a, const uint4* s_vi
         for (int j = 0; j < VT + 2; ++j) X[j] = 0;
         if (R < total_rows) {
             const int ga = R / VT, i = R - ga * VT;  // rows are ordered (env, agent, i)
-            const uint4 vp = s_view[ga];
+            const uint2 vp = s_view[ga];
             const int si = static_cast<int16_t>(vp.y & 0xffffu), sj = static_cast<int32_t>(vp.y) >> 16;
-            const uint32_t jlo = vp.z & 255u, jlen = (vp.z >> 8) & 255u, ilo = (vp.z >> 16) & 255u, ilen = vp.z >> 24;
-            const uint32_t len = (static_cast<uint32_t>(i) - ilo < ilen) ? jlen : 0u;
-            const uint32_t mask = ((1u << len) - 1u) << jlo;
             const uint8_t* g = s_grid + static_cast<int32_t>(vp.x) + i * si;
 #pragma unroll
-            for (int j = 0; j < VT; ++j) X[j] = (mask & (1u << j)) ? s_color[g[j * sj]] : 0u;
+            for (int j = 0; j < VT; ++j) X[j] = s_color[g[j * sj]];
         }
         X[VT] = __shfl_down_sync(0xffffffffu, X[0], 1);
         uint32_t P[NP + 1];
@@ -432,12 +422,15 @@ __device__ __forceinline__ void render_rows(const StepArgs& a, const uint4* s_vi
                 if (m < M) stage[w0 + m] = __funnelshift_r(P[m], P[m + 1], 8 * d);
         }
         __syncwarp();
-        const int rows_here = min(32, total_rows - base);
-        const int nbytes = rows_here * RB;
+        const int nbytes = min(32, total_rows - base) * RB;
         uint8_t* out = dst + static_cast<size_t>(base) * RB;
         if (aligned16) {
-            for (int off = lane * 16; off < nbytes; off += 512)
-                *reinterpret_cast<uint4*>(out + off) = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(stage) + off);
+#pragma unroll
+            for (int it = 0; it < (32 * RB + 511) / 512; ++it) {
+                const int off = it * 512 + lane * 16;
+                if (off < nbytes)
+                    *reinterpret_cast<uint4*>(out + off) = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(stage) + off);
+            }
         } else {
             for (int off = lane * 4; off < nbytes; off += 128)
                 *reinterpret_cast<uint32_t*>(out + off) = stage[off >> 2];
@@ -447,21 +440,16 @@ __device__ __forceinline__ void render_rows(const StepArgs& a, const uint4* s_vi
 }
 
 // Any view size / partially valid tiles: one thread per pixel, byte stores straight to HBM.
-__device__ __forceinline__ void render_generic(const StepArgs& a, const EnvScratch* s_env, const uint8_t* s_grid,
-                                               const uint32_t* s_color, uint8_t* dst, int n_envs) {
-    const int V = a.V, N = a.N, r = a.r;
+__device__ __forceinline__ void render_generic(const StepArgs& a, const EnvScratch* s_env, const uint2* s_view,
+                                               const uint8_t* s_grid, const uint32_t* s_color, uint8_t* dst, int n_envs) {
+    const int V = a.V, N = a.N;
     const int total = n_envs * N * V * V;
     for (int p = threadIdx.x; p < total; p += blockDim.x) {
-        const int j = p % V, i = (p / V) % V, ag = (p / (V * V)) % N, e = p / (V * V * N);
-        const EnvScratch& S = s_env[e];
-        if (!S.active) continue;
-        const int k = a.rotate ? ((4 - S.ori[ag]) & 3) : 0;
-        int vi, vj;
-        if (k == 0) { vi = i; vj = j; } else if (k == 1) { vi = j; vj = V - 1 - i; }
-        else if (k == 2) { vi = V - 1 - i; vj = V - 1 - j; } else { vi = V - 1 - j; vj = i; }
-        const int mr = (S.pos[ag] >> 8) - r + vi, mc = (S.pos[ag] & 255) - r + vj;
-        uint32_t c = 0;
-        if (mr >= 0 && mr < a.H && mc >= 0 && mc < a.W) c = s_color[s_grid[e * a.cell_stride + mr * a.W + mc]];
+        const int j = p % V, i = (p / V) % V, ga = p / (V * V);
+        if (!s_env[ga / N].active) continue;
+        const uint2 vp = s_view[ga];
+        const int si = static_cast<int16_t>(vp.y & 0xffffu), sj = static_cast<int32_t>(vp.y) >> 16;
+        const uint32_t c = s_color[s_grid[static_cast<int32_t>(vp.x) + i * si + j * sj]];
         dst[3 * static_cast<size_t>(p)] = c & 255; dst[3 * static_cast<size_t>(p) + 1] = (c >> 8) & 255; dst[3 * static_cast<size_t>(p) + 2] = (c >> 16) & 255;
     }
 }
@@ -482,37 +470,43 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_kernel(const __grid_cons
 
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + a.L.mbar);
     uint8_t* s_grid = smem + a.L.grid;
-    uint32_t* s_wall = reinterpret_cast<uint32_t*>(smem + a.L.wall);
     uint32_t* s_color = reinterpret_cast<uint32_t*>(smem + a.L.color);
     uint16_t* s_apple = reinterpret_cast<uint16_t*>(smem + a.L.apple);
-    uint8_t* s_apple_nb = smem + a.L.apple_nb;
     EnvScratch* s_env = reinterpret_cast<EnvScratch*>(smem + a.L.env);
     int* s_stats = reinterpret_cast<int*>(smem + a.L.stats);
-
     const int phases = a.phases;
-    const uint32_t tile_bytes = static_cast<uint32_t>(E) * a.cell_stride;
 
-    // ---- load: grid tile by TMA, static tables by plain loads while it is in flight
+    // ---- load: one TMA bulk copy per env tile; zero rows and static tables while they are in flight
     if (tid == 0) mbar_init(mbar, 1);
     __syncthreads();
-    if (tid == 0) {
-        mbar_expect_tx(mbar, tile_bytes);
-        bulk_g2s(s_grid, a.grid + static_cast<size_t>(e0) * a.cell_stride, tile_bytes, mbar);
+    if (warp == 0) {
+        if (lane == 0) mbar_expect_tx(mbar, static_cast<uint32_t>(E) * a.env_bytes);
+        __syncwarp();
+        for (int e = lane; e < E; e += 32)
+            bulk_g2s(s_grid + e * a.tile_stride + a.pad_bytes, a.grid + static_cast<size_t>(e0 + e) * a.env_bytes, a.env_bytes, mbar);
     }
-    for (int i = tid; i < (a.HW + 31) / 32; i += nthr) s_wall[i] = a.wall_bits[i];
+    {
+        const int n16 = a.pad_bytes / 16;  // zero rows above and below every tile
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        for (int i = tid; i < E * 2 * n16; i += nthr) {
+            const int e = i / (2 * n16), q = i - e * 2 * n16;
+            const int off = e * a.tile_stride + (q < n16 ? q * 16 : a.pad_bytes + a.env_bytes + (q - n16) * 16);
+            *reinterpret_cast<uint4*>(s_grid + off) = z;
+        }
+    }
     if (phases & SSD_PHASE_RENDER)
         for (int i = tid; i < 128; i += nthr) s_color[i] = a.color[i];
     if (phases & SSD_PHASE_SPAWN)
-        for (int i = tid; i < a.n_apple; i += nthr) { s_apple[i] = a.apple_cell[i]; s_apple_nb[i] = a.apple_nb[i]; }
+        for (int i = tid; i < a.n_apple; i += nthr) s_apple[i] = a.apple_cell[i];
     if (tid < SSD_NUM_STATS) s_stats[tid] = 0;
     __syncthreads();
+    mbar_wait(mbar, 0);  // grid tiles landed
 
     // ---- phase A: one lane per agent, G lanes per env, 32/G envs per warp and pass
     const int G = a.G, al = lane & (G - 1), gbase = lane & ~(G - 1);
     const int slots = nwarps * (32 / G);
     PhiloxKey pk;
     pk.k0 = a.key0; pk.k1 = a.key1; pk.t = a.t;
-    bool grid_ready = false;
     for (int ebase = warp * (32 / G); ebase < E; ebase += slots) {  // warp-uniform trip count
         const int e = ebase + lane / G;
         const bool env_ok = e < E;
@@ -520,8 +514,9 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_kernel(const __grid_cons
         const bool active = env_ok && e < nvalid && (a.mask == nullptr || a.mask[e0 + e] != 0);
         const bool valid = env_ok && al < N;
         const size_t gi = static_cast<size_t>(e0 + (env_ok ? e : 0)) * N + (valid ? al : 0);
+        uint8_t* g = s_grid + (env_ok ? e : 0) * a.tile_stride;
         AgentLane me;
-        me.key = 0; me.ori = 0; me.act = -1; me.rew = 0;
+        me.key = 0x0101; me.ori = 0; me.act = -1; me.rew = 0;
         if (valid) {
             const uint32_t w = a.agents[gi];
             me.key = (w & 255) << 8 | ((w >> 8) & 255);
@@ -536,17 +531,15 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_kernel(const __grid_cons
         pk.env = static_cast<uint32_t>(a.env_id0 + static_cast<uint64_t>(e0 + e));
         __syncwarp();
         if (phases & SSD_PHASE_MOVES) {
-            moves_group<TAPE>(a, S, s_wall, me, valid && active, al, G, e0 + e, pk);
+            moves_group<TAPE>(a, S, g, me, valid && active, al, G, e0 + e, pk);
             if (active && al == 0) atomicAdd(&s_stats[0], 1);
         }
         if (valid) { S.pos[al] = static_cast<uint16_t>(me.key); S.ori[al] = static_cast<uint8_t>(me.ori); }
-        if (!grid_ready) { mbar_wait(mbar, 0); grid_ready = true; }  // grid tile landed
         __syncwarp();
-        uint8_t* g = s_grid + (env_ok ? e : 0) * a.cell_stride;
-        const int my_idx = static_cast<int>(me.key >> 8) * a.W + static_cast<int>(me.key & 255);
+        const int my_idx = tile_idx(a, me.key);
         if (phases & SSD_PHASE_CONSUME) {  // map_env.py:178-181, agent.py:177-183 / 216-222
             const bool on_apple = valid && active && g[my_idx] == 'A';
-            // agents sharing a cell (appendix A.2 quirk): the first one in agent order eats
+            // agents sharing a cell: the first one in agent order eats
             const uint32_t same = __match_any_sync(0xffffffffu, on_apple ? (me.key | static_cast<uint32_t>(gbase) << 16) : (0x80000000u | lane));
             __syncwarp();
             if (on_apple && (__ffs(same) - 1) == lane) { g[my_idx] = ' '; me.rew += 1; atomicAdd(&s_stats[2], 1); }
@@ -562,7 +555,7 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_kernel(const __grid_cons
                 if (!__any_sync(0xffffffffu, fire)) continue;
                 const bool clean = act_k == 8;
                 int upd = -1, hits = 0, n = 0;
-                if (fire && al < 3) n = ray_walk(a, S, g, s_wall, key_k, ori_k, al, clean, upd, hits);
+                if (fire && al < 3) n = ray_walk(a, S, g, key_k, ori_k, al, clean, upd, hits);
                 if (fire && al == ag && !clean) { me.rew -= 1; atomicAdd(&s_stats[3], 1); }  // fire_beam agent.py:170-172
                 __syncwarp();
                 if (fire && al < 3) {
@@ -583,7 +576,6 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_kernel(const __grid_cons
             if (phases & SSD_PHASE_SPAWN) g[my_idx] |= 0x80;  // flag agent cells for the spawn pass
         }
     }
-    if (!grid_ready) mbar_wait(mbar, 0);
     // beams recorded by an earlier phase call of this step (phase-split mode only)
     if (a.use_beam_buf) {
         __syncthreads();
@@ -604,44 +596,46 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_kernel(const __grid_cons
     if ((phases & SSD_PHASE_SPAWN) && KIND != SSD_KIND_PLAIN) {
         for (int e = warp; e < E; e += nwarps) {
             if (!s_env[e].active) continue;
-            uint8_t* g = s_grid + e * a.cell_stride;
+            uint8_t* g = s_grid + e * a.tile_stride;
             pk.env = static_cast<uint32_t>(a.env_id0 + static_cast<uint64_t>(e0 + e));
             void* scratch = smem + a.L.list + warp * a.L.list_stride;
             if (KIND == SSD_KIND_HARVEST)
-                harvest_spawn<TAPE>(a, g, s_apple, s_apple_nb, static_cast<uint16_t*>(scratch), e0 + e, pk, lane, s_stats);
+                harvest_spawn<TAPE>(a, g, s_apple, static_cast<uint16_t*>(scratch), e0 + e, pk, lane, s_stats);
             else
                 cleanup_spawn<TAPE>(a, g, s_apple, static_cast<uint32_t*>(scratch), e0 + e, pk, lane, s_stats);
         }
         __syncthreads();
     }
 
-    // ---- store: grid tile back to HBM (bit 7 = agent flag of the spawn pass, stripped on the way out)
+    // ---- store: grid rows back to HBM (bit 7 = agent flag of the spawn pass, stripped on the way out)
     if (phases & (SSD_PHASE_CONSUME | SSD_PHASE_BEAMS | SSD_PHASE_SPAWN)) {
-        const int vec_per_env = a.cell_stride / 16;
-        uint4* gdst = reinterpret_cast<uint4*>(a.grid + static_cast<size_t>(e0) * a.cell_stride);
-        const uint4* gsrc = reinterpret_cast<const uint4*>(s_grid);
-        for (int i = tid; i < E * vec_per_env; i += nthr) {
-            if (!s_env[i / vec_per_env].active) continue;
-            uint4 v = gsrc[i];
-            v.x &= 0x7F7F7F7Fu; v.y &= 0x7F7F7F7Fu; v.z &= 0x7F7F7F7Fu; v.w &= 0x7F7F7F7Fu;
-            gdst[i] = v;
+        const int vec_per_env = a.env_bytes / 16;
+        for (int e = warp; e < E; e += nwarps) {
+            if (!s_env[e].active) continue;
+            uint4* gdst = reinterpret_cast<uint4*>(a.grid + static_cast<size_t>(e0 + e) * a.env_bytes);
+            const uint4* gsrc = reinterpret_cast<const uint4*>(s_grid + e * a.tile_stride + a.pad_bytes);
+            for (int i = lane; i < vec_per_env; i += 32) {
+                uint4 v = gsrc[i];
+                v.x &= 0x7F7F7F7Fu; v.y &= 0x7F7F7F7Fu; v.z &= 0x7F7F7F7Fu; v.w &= 0x7F7F7F7Fu;
+                gdst[i] = v;
+            }
         }
     }
 
     // ---- phase C: overlay + render + coalesced stores
     if ((phases & SSD_PHASE_RENDER) && a.obs != nullptr) {
-        __syncthreads();  // the grid write-back above has read the tile
+        __syncthreads();  // the grid write-back above has read the tiles
         // get_map_with_agents map_env.py:280-302: agents in agent order (the last one on a cell wins),
         // then beams in firing order (a later beam overwrites an earlier one)
         for (int ebase = warp * (32 / G); ebase < E; ebase += slots) {
             const int e = ebase + lane / G;
             const bool env_ok = e < E;
             const EnvScratch& S = s_env[env_ok ? e : 0];
-            uint8_t* g = s_grid + (env_ok ? e : 0) * a.cell_stride;
+            uint8_t* g = s_grid + (env_ok ? e : 0) * a.tile_stride;
             const bool valid = env_ok && al < N;
-            const uint32_t key = valid ? S.pos[al] : 0;
+            const uint32_t key = valid ? S.pos[al] : 0x0101u;
             const uint32_t same = __match_any_sync(0xffffffffu, valid ? (key | static_cast<uint32_t>(gbase) << 16) : (0x80000000u | lane));
-            if (valid && (31 - __clz(same)) == lane) g[(key >> 8) * a.W + (key & 255)] = agent_char(al);
+            if (valid && (31 - __clz(same)) == lane) g[tile_idx(a, key)] = agent_char(al);
             __syncwarp();
             if (KIND != SSD_KIND_PLAIN) {
                 for (int k = 0; k < N; ++k) {
@@ -654,14 +648,15 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_kernel(const __grid_cons
                         int r = static_cast<int>(S.pos[ag] >> 8) + d0, c = static_cast<int>(S.pos[ag] & 255) + d1;
                         if (al == 1) { r += -d1 - d0; c += d0 - d1; }
                         if (al == 2) { r -= -d1 + d0; c -= d0 + d1; }
-                        const int n = S.raylen[k * 3 + al];
-                        for (int i = 0; i < n; ++i) { g[r * a.W + c] = static_cast<uint8_t>(ch); r += d0; c += d1; }
+                        const int n = S.raylen[k * 3 + al], dp = d0 * a.Ws + d1;
+                        int p = (r + a.r) * a.Ws + c;
+                        for (int i = 0; i < n; ++i) { g[p] = static_cast<uint8_t>(ch); p += dp; }
                     }
                     __syncwarp();
                 }
             }
         }
-        uint4* s_view = reinterpret_cast<uint4*>(smem + a.L.view);
+        uint2* s_view = reinterpret_cast<uint2*>(smem + a.L.view);
         for (int i = tid; i < E * N; i += nthr) s_view[i] = view_param(a, s_env[i / N], i / N, i % N);
         __syncthreads();
         uint8_t* dst = a.obs + static_cast<size_t>(e0) * a.obs_env;
@@ -669,12 +664,12 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_kernel(const __grid_cons
         if constexpr (VT > 0) {
             if (all_active) {
                 uint32_t* stage = reinterpret_cast<uint32_t*>(smem + a.L.stage + warp * a.L.stage_stride);
-                render_rows<VT>(a, s_view, s_grid, s_color, stage, dst, E * N * VT, (reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+                render_rows<VT>(s_view, s_grid, s_color, stage, dst, E * N * VT, (reinterpret_cast<uintptr_t>(dst) & 15) == 0);
             } else {
-                render_generic(a, s_env, s_grid, s_color, dst, nvalid);
+                render_generic(a, s_env, s_view, s_grid, s_color, dst, nvalid);
             }
         } else {
-            render_generic(a, s_env, s_grid, s_color, dst, nvalid);
+            render_generic(a, s_env, s_view, s_grid, s_color, dst, nvalid);
         }
     }
     if (tid < SSD_NUM_STATS && s_stats[tid] != 0 && a.stats != nullptr)
@@ -713,27 +708,29 @@ __global__ void __launch_bounds__(128) ssd_reset_kernel(const ResetArgs a) {
     }
     // reset_map + build_walls + custom_reset (map_env.py:560-564, harvest.py:57-60, cleanup.py:84-92)
     const uint4* src = reinterpret_cast<const uint4*>(a.init_grid);
-    uint4* dst = reinterpret_cast<uint4*>(a.grid + static_cast<size_t>(e) * a.cell_stride);
-    for (int i = 0; i < a.cell_stride / 16; ++i) dst[i] = src[i];
+    uint4* dst = reinterpret_cast<uint4*>(a.grid + static_cast<size_t>(e) * a.env_bytes);
+    for (int i = 0; i < a.env_bytes / 16; ++i) dst[i] = src[i];
 }
 
 // ====================================================================== state pack / unpack, selftest
-__global__ void pack_state_kernel(int B, int N, int HW, int cell_stride, const uint8_t* grid_in, const int16_t* pos_in,
+__global__ void pack_state_kernel(int B, int N, int H, int W, int Ws, const uint8_t* grid_in, const int16_t* pos_in,
                                   const uint8_t* ori_in, uint8_t* grid, uint32_t* agents) {
     const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i < static_cast<size_t>(B) * cell_stride) {
-        const size_t b = i / cell_stride, c = i % cell_stride;
-        grid[i] = c < static_cast<size_t>(HW) ? grid_in[b * HW + c] : 0;
+    const size_t env_bytes = static_cast<size_t>(H) * Ws;
+    if (i < static_cast<size_t>(B) * env_bytes) {
+        const size_t b = i / env_bytes, q = i % env_bytes, r = q / Ws, c = q % Ws;
+        grid[i] = c < static_cast<size_t>(W) ? grid_in[(b * H + r) * W + c] : 0;
     }
     if (i < static_cast<size_t>(B) * N)
         agents[i] = (pos_in[2 * i] & 255) | (pos_in[2 * i + 1] & 255) << 8 | static_cast<uint32_t>(ori_in[i] & 3) << 16;
 }
-__global__ void unpack_state_kernel(int B, int N, int HW, int cell_stride, const uint8_t* grid, const uint32_t* agents,
+__global__ void unpack_state_kernel(int B, int N, int H, int W, int Ws, const uint8_t* grid, const uint32_t* agents,
                                     uint8_t* grid_out, int16_t* pos_out, uint8_t* ori_out) {
     const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const size_t HW = static_cast<size_t>(H) * W;
     if (grid_out != nullptr && i < static_cast<size_t>(B) * HW) {
-        const size_t b = i / HW, c = i % HW;
-        grid_out[i] = grid[b * cell_stride + c];
+        const size_t b = i / HW, q = i % HW, r = q / W, c = q % W;
+        grid_out[i] = grid[(b * H + r) * Ws + c];
     }
     if (i < static_cast<size_t>(B) * N) {
         const uint32_t w = agents[i];
@@ -752,17 +749,17 @@ static cudaError_t launch_v(const StepArgs& a, int threads, cudaStream_t stream,
     const int ctas = (a.env_end - a.env_begin + a.E - 1) / a.E;
     if (ctas <= 0) return cudaSuccess;
     const int vt = fast_rows ? a.V : 0;
-#define SSD_LAUNCH(VT_)                                                                                       \
-    do {                                                                                                      \
-        auto kern = ssd_step_kernel<KIND, TAPE, VT_>;                                                         \
-        static uint32_t smem_set = 0;                                                                         \
-        if (a.L.total > smem_set) {                                                                           \
+#define SSD_LAUNCH(VT_)                                                                                         \
+    do {                                                                                                        \
+        auto kern = ssd_step_kernel<KIND, TAPE, VT_>;                                                           \
+        static uint32_t smem_set = 0;                                                                           \
+        if (a.L.total > smem_set) {                                                                             \
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, a.L.total); \
-            if (e != cudaSuccess) return e;                                                                   \
-            smem_set = a.L.total;                                                                             \
-        }                                                                                                     \
-        kern<<<ctas, threads, a.L.total, stream>>>(a);                                                        \
-        return cudaGetLastError();                                                                            \
+            if (e != cudaSuccess) return e;                                                                     \
+            smem_set = a.L.total;                                                                               \
+        }                                                                                                       \
+        kern<<<ctas, threads, a.L.total, stream>>>(a);                                                          \
+        return cudaGetLastError();                                                                              \
     } while (0)
     switch (vt) {
         case 11: SSD_LAUNCH(11);
@@ -796,16 +793,17 @@ cudaError_t launch_reset(const ResetArgs& a, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
-cudaError_t launch_pack_state(int B, int N, int HW, int cell_stride, const uint8_t* grid_in, const int16_t* pos_in,
+cudaError_t launch_pack_state(int B, int N, int H, int W, int Ws, const uint8_t* grid_in, const int16_t* pos_in,
                               const uint8_t* ori_in, uint8_t* grid, uint32_t* agents, cudaStream_t stream) {
-    const size_t n = static_cast<size_t>(B) * cell_stride;
-    pack_state_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(B, N, HW, cell_stride, grid_in, pos_in, ori_in, grid, agents);
+    const size_t n = static_cast<size_t>(B) * H * Ws;
+    pack_state_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(B, N, H, W, Ws, grid_in, pos_in, ori_in, grid, agents);
     return cudaGetLastError();
 }
-cudaError_t launch_unpack_state(int B, int N, int HW, int cell_stride, const uint8_t* grid, const uint32_t* agents,
+cudaError_t launch_unpack_state(int B, int N, int H, int W, int Ws, const uint8_t* grid, const uint32_t* agents,
                                 uint8_t* grid_out, int16_t* pos_out, uint8_t* ori_out, cudaStream_t stream) {
-    const size_t n = static_cast<size_t>(B) * (HW > N ? HW : N);
-    unpack_state_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(B, N, HW, cell_stride, grid, agents, grid_out, pos_out, ori_out);
+    const size_t hw = static_cast<size_t>(H) * W;
+    const size_t n = static_cast<size_t>(B) * (hw > static_cast<size_t>(N) ? hw : N);
+    unpack_state_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(B, N, H, W, Ws, grid, agents, grid_out, pos_out, ori_out);
     return cudaGetLastError();
 }
 cudaError_t launch_philox_selftest(const uint32_t* ctr_key, uint32_t* out, cudaStream_t stream) {
