@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Sweep the CTA shape of the fused step kernel (SSD_E / SSD_THREADS) on one GPU and
+"""Sweep the CTA shape of the fused step kernel (SSD_THREADS) on one GPU and
 print ms per step for the headline workload.  Usage: python profiles/tune_step.py [game] [B]"""
 import itertools
 import os
@@ -36,9 +36,9 @@ def time_cfg(game, B, steps=60, warm=10, **env):
 if __name__ == "__main__":
     game = sys.argv[1] if len(sys.argv) > 1 else "harvest"
     B = int(sys.argv[2]) if len(sys.argv) > 2 else 65536
-    for E, T in itertools.product((8, 16, 32), (128, 256)):
+    for T in (32, 64, 128, 256):
         try:
-            ms = time_cfg(game, B, SSD_E=E, SSD_THREADS=T)
-            print("E=%2d threads=%3d  %.4f ms/step  %.3f G agent-steps/s" % (E, T, ms, B * 5 / ms / 1e6), flush=True)
+            ms = time_cfg(game, B, SSD_THREADS=T)
+            print("threads=%3d  %.4f ms/step  %.3f G agent-steps/s" % (T, ms, B * 5 / ms / 1e6), flush=True)
         except Exception as ex:
-            print("E=%2d threads=%3d  failed: %s" % (E, T, ex), flush=True)
+            print("threads=%3d  failed: %s" % (T, ex), flush=True)

@@ -42,7 +42,7 @@ uint64_t threshold53(double p) {
 struct SsdEnv {
     SsdConfig cfg{};
     int B = 0, B_pad = 0, E = 0, threads = 128;
-    int HW = 0, Ws = 0, env_bytes = 0, pad_bytes = 0, tile_stride = 0, V = 0, obs_env = 0, n_apple = 0, n_waste = 0, n_spawn = 0;
+    int HW = 0, Ws = 0, env_bytes = 0, pad_bytes = 0, V = 0, obs_env = 0, n_apple = 0, n_waste = 0, n_spawn = 0;
     uint64_t seed = 0;
     uint32_t t = 0;
     int64_t launches = 0;
@@ -86,21 +86,21 @@ bool is_device_ptr(const void* p) {
     return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
 }
 
-ssd::SmemLayout make_layout(const SsdEnv& h, int E, int threads) {
+ssd::SmemLayout make_layout(const SsdEnv& h, int threads) {
     ssd::SmemLayout L{};
+    const uint32_t G = h.cfg.num_agents <= 8 ? 8 : 16, epw = 32 / G;
     uint32_t off = 0;
-    L.mbar = off; off += 16;
-    L.grid = off; off += static_cast<uint32_t>(E) * h.tile_stride + 16;
-    L.color = off; off += 512;
     L.apple = off; off += up16(h.n_apple * 2);
-    L.env = off; off += static_cast<uint32_t>(E) * sizeof(ssd::EnvScratch);
-    L.list_stride = up16(std::max(h.n_apple * 2, h.n_waste * 4));
-    L.list = off; off += (threads / 32) * L.list_stride;
-    L.view = off; off += up16(static_cast<uint32_t>(E) * h.cfg.num_agents * 8);
-    L.stage_stride = up16(32u * 3u * h.V);
-    L.stage = off; off += (threads / 32) * L.stage_stride;
-    L.stats = off; off += 32;
-    L.total = off;
+    L.warp0 = off;
+    uint32_t w = 0;
+    L.w_mbar = w; w += 16;
+    L.w_tiles = w; w += epw * (h.env_bytes + h.pad_bytes) + h.pad_bytes;
+    L.w_env = w; w += epw * sizeof(ssd::EnvScratch);
+    L.w_list = w; w += up16(std::max(h.n_apple * 2, h.n_waste * 4));
+    L.w_view = w; w += up16(epw * h.cfg.num_agents * 8);
+    L.w_stage = w; w += up16(32u * 3u * h.V) + 16;
+    L.warp_stride = w;
+    L.total = off + (threads / 32) * w;
     return L;
 }
 
@@ -108,10 +108,10 @@ void fill_args(SsdEnv* h, ssd::StepArgs& a) {
     memset(&a, 0, sizeof a);
     const SsdConfig& c = h->cfg;
     a.kind = c.kind; a.H = c.height; a.W = c.width; a.N = c.num_agents; a.r = c.view_radius; a.V = h->V;
-    a.beam_len = c.beam_len; a.Ws = h->Ws; a.env_bytes = h->env_bytes; a.pad_bytes = h->pad_bytes; a.tile_stride = h->tile_stride;
+    a.beam_len = c.beam_len; a.Ws = h->Ws; a.env_bytes = h->env_bytes; a.pad_bytes = h->pad_bytes;
     a.n_apple = h->n_apple; a.n_waste = h->n_waste; a.area = c.potential_waste_area;
     a.obs_env = h->obs_env;
-    a.E = h->E; a.G = h->cfg.num_agents <= 8 ? 8 : 16; a.env_begin = 0; a.env_end = h->B;
+    a.G = h->cfg.num_agents <= 8 ? 8 : 16; a.env_begin = 0; a.env_end = h->B;
     a.phases = SSD_PHASE_ALL; a.rotate = 1; a.spawn_stream = ssd::STREAM_SPAWN;
     a.key0 = static_cast<uint32_t>(h->seed); a.key1 = static_cast<uint32_t>(h->seed >> 32); a.t = h->t;
     a.env_id0 = c.env_id_offset;
@@ -178,33 +178,38 @@ int ssd_create(const SsdConfig* cfg, ssd_handle* out) {
     if (!h) return fail(SSD_ERR_INVALID, "out of host memory");
     h->cfg = *cfg;
     h->B = cfg->num_envs; h->HW = H * W;
-    h->Ws = static_cast<int>(up16(W + cfg->view_radius));  // >= r zero bytes after the W cells of every row
-    h->env_bytes = H * h->Ws; h->pad_bytes = cfg->view_radius * h->Ws; h->tile_stride = (H + 2 * cfg->view_radius) * h->Ws;
+    h->Ws = W + cfg->view_radius;  // r zero bytes after the W cells of every row
+    h->env_bytes = static_cast<int>(up16(H * h->Ws));
+    h->pad_bytes = static_cast<int>(up16(cfg->view_radius * h->Ws + cfg->view_radius));
     h->V = 2 * cfg->view_radius + 1; h->obs_env = N * h->V * h->V * 3;
-    if (h->tile_stride > 65535) { delete h; return fail(SSD_ERR_UNSUPPORTED, "map tile of %d bytes exceeds the 16-bit cell index range", h->tile_stride); }
+    if (h->env_bytes > 65535) { delete h; return fail(SSD_ERR_UNSUPPORTED, "map tile of %d bytes exceeds the 16-bit cell index range", h->env_bytes); }
 
     // static tables
-    std::vector<uint32_t> color(128, 0);
+    std::vector<uint32_t> color(ssd::kNumCodes, 0);
     std::vector<uint16_t> apple, waste, spawn;
     std::vector<uint8_t> init_grid(h->env_bytes, 0);
     const uint8_t apple_ch = cfg->kind == SSD_KIND_HARVEST ? 'A' : (cfg->kind == SSD_KIND_CLEANUP ? 'B' : 0);
-    const int rr = cfg->view_radius;
     for (int r = 0; r < H; ++r)
         for (int c = 0; c < W; ++c) {
             const uint8_t ch = cfg->base_map[r * W + c];
-            const uint16_t tile_cell = static_cast<uint16_t>((r + rr) * h->Ws + c);
+            const uint16_t tile_cell = static_cast<uint16_t>(r * h->Ws + c);
             uint8_t g = ' ';  // reset_map + build_walls + custom_reset (map_env.py:560-564, harvest.py:57-60, cleanup.py:84-92)
             if (ch == '@') g = '@';
             else if (cfg->kind == SSD_KIND_HARVEST && ch == 'A') g = 'A';
             else if (cfg->kind == SSD_KIND_CLEANUP && (ch == 'H' || ch == 'R' || ch == 'S')) g = ch;
-            init_grid[r * h->Ws + c] = g;
+            init_grid[r * h->Ws + c] = ssd::ascii_to_cell(g);
             if (apple_ch && ch == apple_ch) apple.push_back(tile_cell);
             if (cfg->kind == SSD_KIND_CLEANUP && (ch == 'H' || ch == 'R')) waste.push_back(tile_cell);
         }
     for (int s = 0; s < cfg->num_spawn_points; ++s)
         spawn.push_back(static_cast<uint16_t>(cfg->spawn_points[2 * s] << 8 | cfg->spawn_points[2 * s + 1]));
-    for (int i = 0; i < 128; ++i)
-        color[i] = cfg->color_lut[3 * i] | cfg->color_lut[3 * i + 1] << 8 | cfg->color_lut[3 * i + 2] << 16;
+    {   // colour table by cell code: every code takes the colour of its ASCII character
+        const char* chars = "0 @AHRSFC123456789";
+        for (int code = 0; chars[code]; ++code) {
+            const int i = static_cast<uint8_t>(chars[code]);
+            color[code] = cfg->color_lut[3 * i] | cfg->color_lut[3 * i + 1] << 8 | cfg->color_lut[3 * i + 2] << 16;
+        }
+    }
     h->n_apple = static_cast<int>(apple.size()); h->n_waste = static_cast<int>(waste.size()); h->n_spawn = static_cast<int>(spawn.size());
     if (h->n_apple >= 0x8000) { delete h; return fail(SSD_ERR_UNSUPPORTED, "too many apple points"); }
     if (cfg->kind == SSD_KIND_CLEANUP && cfg->potential_waste_area < h->n_waste) {
@@ -222,28 +227,26 @@ int ssd_create(const SsdConfig* cfg, ssd_handle* out) {
         ap.push_back(pa); athr.push_back(threshold53(pa)); wp.push_back(pw); wthr.push_back(threshold53(pw));
     }
 
-    // CTA shape: E envs per CTA (largest of {32,16,8,4,2,1} that leaves >= 2 CTAs per SM), 128 threads.
-    // SSD_E / SSD_THREADS override for tuning.
+    // CTA shape: every warp owns 32/G envs; SSD_THREADS (64, 128 or 256) overrides the CTA size for tuning.
     const int smem_max = static_cast<int>(prop.sharedMemPerBlockOptin);
-    const int smem_sm = static_cast<int>(prop.sharedMemPerMultiprocessor);
     auto env_int = [](const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; };
-    int E = env_int("SSD_E", cfg->envs_per_cta);
-    int threads = env_int("SSD_THREADS", 256);
-    if (threads != 128 && threads != 256) { delete h; return fail(SSD_ERR_INVALID, "SSD_THREADS must be 128 or 256"); }
-    if (E != 0 && E != 1 && E != 2 && E != 4 && E != 8 && E != 16 && E != 32) { delete h; return fail(SSD_ERR_INVALID, "envs_per_cta must be 0, 1, 2, 4, 8, 16 or 32"); }
-    if (E == 0) {
-        for (E = 32; E > 1; E >>= 1)
-            if (static_cast<int>(make_layout(*h, E, threads).total) + 1024 <= smem_sm / 2) break;
-        while (E > 1 && E / 2 >= h->B) E >>= 1;  // tiny batches: do not pad 1 env to 32
+    int threads = env_int("SSD_THREADS", 128);
+    if (threads != 32 && threads != 64 && threads != 128 && threads != 256) { delete h; return fail(SSD_ERR_INVALID, "SSD_THREADS must be 32, 64, 128 or 256"); }
+    if (cfg->envs_per_cta != 0) {  // explicit request: must be a whole number of warps
+        const int epw = N <= 8 ? 4 : 2;
+        if (cfg->envs_per_cta % epw != 0 || cfg->envs_per_cta / epw > 8) { delete h; return fail(SSD_ERR_INVALID, "envs_per_cta must be a multiple of %d and at most %d", epw, 8 * epw); }
+        threads = cfg->envs_per_cta / epw * 32;
     }
-    h->E = E;
     h->threads = threads;
-    h->L = make_layout(*h, E, threads);
+    h->L = make_layout(*h, threads);
+    while (static_cast<int>(h->L.total) > smem_max && h->threads > 32) { h->threads >>= 1; h->L = make_layout(*h, h->threads); }
     if (static_cast<int>(h->L.total) > smem_max) {
         const unsigned need = h->L.total;
         delete h;
-        return fail(SSD_ERR_UNSUPPORTED, "a CTA tile of %d envs needs %u bytes of shared memory (limit %d)", E, need, smem_max);
+        return fail(SSD_ERR_UNSUPPORTED, "one warp's tile set needs %u bytes of shared memory (limit %d)", need, smem_max);
     }
+    const int E = (h->threads / 32) * (N <= 8 ? 4 : 2);
+    h->E = E;
     h->B_pad = (h->B + E - 1) / E * E;
 
     int bad = 0;
@@ -328,7 +331,7 @@ int ssd_set_state(ssd_handle h, const uint8_t* grid, const int16_t* pos, const u
         CUDA_TRY(cudaMemcpyAsync(h->d_io_ori, ori, np, cudaMemcpyDefault, st));
         grid = h->d_io_grid; pos = h->d_io_pos; ori = h->d_io_ori;
     }
-    CUDA_TRY(ssd::launch_pack_state(h->B, N, h->cfg.height, h->cfg.width, h->Ws, grid, pos, ori, h->d_grid, h->d_agents, st));
+    CUDA_TRY(ssd::launch_pack_state(h->B, N, h->cfg.height, h->cfg.width, h->Ws, h->env_bytes, grid, pos, ori, h->d_grid, h->d_agents, st));
     h->launches++;
     return SSD_OK;
 }
@@ -341,7 +344,7 @@ int ssd_get_state(ssd_handle h, uint8_t* grid, int16_t* pos, uint8_t* ori, void*
     const size_t ng = static_cast<size_t>(h->B) * h->HW, np = static_cast<size_t>(h->B) * N;
     const bool dev = (!grid || is_device_ptr(grid)) && (!pos || is_device_ptr(pos)) && (!ori || is_device_ptr(ori));
     if (dev) {
-        CUDA_TRY(ssd::launch_unpack_state(h->B, N, h->cfg.height, h->cfg.width, h->Ws, h->d_grid, h->d_agents, grid, pos, ori, st));
+        CUDA_TRY(ssd::launch_unpack_state(h->B, N, h->cfg.height, h->cfg.width, h->Ws, h->env_bytes, h->d_grid, h->d_agents, grid, pos, ori, st));
         h->launches++;
         return SSD_OK;
     }
@@ -349,7 +352,7 @@ int ssd_get_state(ssd_handle h, uint8_t* grid, int16_t* pos, uint8_t* ori, void*
         if (h->alloc(&h->d_io_grid, ng) || h->alloc(&h->d_io_pos, np * 2) || h->alloc(&h->d_io_ori, np))
             return fail(SSD_ERR_CUDA, "staging allocation failed");
     }
-    CUDA_TRY(ssd::launch_unpack_state(h->B, N, h->cfg.height, h->cfg.width, h->Ws, h->d_grid, h->d_agents, h->d_io_grid, h->d_io_pos, h->d_io_ori, st));
+    CUDA_TRY(ssd::launch_unpack_state(h->B, N, h->cfg.height, h->cfg.width, h->Ws, h->env_bytes, h->d_grid, h->d_agents, h->d_io_grid, h->d_io_pos, h->d_io_ori, st));
     h->launches++;
     if (grid) CUDA_TRY(cudaMemcpyAsync(grid, h->d_io_grid, ng, cudaMemcpyDefault, st));
     if (pos) CUDA_TRY(cudaMemcpyAsync(pos, h->d_io_pos, np * 2 * sizeof(int16_t), cudaMemcpyDefault, st));

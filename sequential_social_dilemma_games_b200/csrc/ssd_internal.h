@@ -20,11 +20,33 @@ enum : uint32_t {
     STREAM_RSPAWN = 5  // uniform draws of reset()'s spawn pass   map_env.py:230
 };
 
-// Grid layout.  HBM: [B_pad][H][Ws] bytes, Ws = round_up(W + r, 16): every row carries >= r zero
-// bytes after its W cells.  Shared memory: one tile of (H + 2r) rows x Ws per env -- r zero rows,
-// the H rows bulk-copied from HBM, r zero rows -- so every cell an egocentric (2r+1)^2 window can
-// touch exists and reads as 0 (black, the '0' padding of utility_funcs.py:94-114) outside the map.
-// In-tile index of map cell (row, col): (row + r) * Ws + col.
+// ---------------------------------------------------------------------------------------------
+// Device cell encoding.  A grid byte on the device is (cell code) * 4, i.e. directly the byte offset
+// of the cell's colour in the 32-entry colour table; bit 7 is free and flags "an agent stands here"
+// between the consume and spawn phases.  ssd_set_state / ssd_get_state translate from / to the
+// reference's ASCII characters (map_env.py:24-41, cleanup.py:15-18).
+// ---------------------------------------------------------------------------------------------
+enum : uint8_t {
+    C_PAD = 0,     // '0'  outside the map (utility_funcs.py:94-114)
+    C_EMPTY = 1,   // ' '
+    C_WALL = 2,    // '@'
+    C_APPLE = 3,   // 'A'
+    C_WASTE = 4,   // 'H'
+    C_RIVER = 5,   // 'R'
+    C_STREAM = 6,  // 'S'
+    C_FIRE = 7,    // 'F'  overlay only
+    C_CLEAN = 8,   // 'C'  overlay only
+    C_AGENT = 9,   // '1'..'9' -> 9..17, overlay only
+    C_OTHER = 31,  // any other character handed to ssd_set_state
+    kNumCodes = 32
+};
+__host__ __device__ constexpr uint8_t CB(uint8_t code) { return static_cast<uint8_t>(code * 4); }
+constexpr uint8_t kFlag = 0x80;
+
+// Grid layout.  HBM: [B_pad][env_bytes], row stride Ws = W + r (>= r zero bytes after the W cells of
+// every row), env_bytes = round_up(H * Ws, 16).  Shared memory, per warp: the tiles of its envs
+// separated (and framed) by pad_bytes >= r * Ws + r zero bytes, so every cell an egocentric
+// (2r+1)^2 window can touch exists and reads as C_PAD.  In-tile index of cell (row, col): row * Ws + col.
 
 // Per-environment scratch in shared memory.
 struct EnvScratch {
@@ -36,33 +58,32 @@ struct EnvScratch {
     uint8_t ori[kMaxAgents];
     uint8_t shuf[kMaxAgents];   // movers after np.random.shuffle (:422)
     uint8_t order[kMaxAgents];  // action-dict iteration order
-    uint8_t firech[kMaxAgents]; // [k] beam char of the k-th entry of the action order (0 = did not fire)
+    uint8_t firech[kMaxAgents]; // [k] beam cell byte of the k-th entry of the action order (0 = did not fire)
     uint8_t raylen[3 * kMaxAgents];  // [k*3+s] painted cells of ray s (beam_pos, map_env.py:648)
     int32_t active;             // 0: env masked out of this launch
     int32_t pad[3];
 };
 static_assert(sizeof(EnvScratch) % 16 == 0, "EnvScratch must stay 16-byte sized");
 
-// Byte offsets of the dynamic shared-memory carve-up of one CTA (all 16-byte aligned).
+// Dynamic shared memory: [apple table][warp 0 region][warp 1 region]...; offsets inside a warp region.
 struct SmemLayout {
-    uint32_t mbar, grid, color, apple, env, list, view, stage, stats, total;
-    uint32_t list_stride;  // bytes of spawn scratch per warp
-    uint32_t stage_stride; // bytes of render staging per warp (32 view rows)
+    uint32_t apple;                                  // CTA-shared table
+    uint32_t warp0, warp_stride;                     // first warp region, bytes per warp
+    uint32_t w_mbar, w_tiles, w_env, w_list, w_view, w_stage;  // offsets inside a warp region
+    uint32_t total;
 };
 
 struct StepArgs {
     // ---- static game description
     int kind, H, W, N, r, V, beam_len;
     int Ws;               // grid row stride (bytes)
-    int env_bytes;        // H * Ws: one env's grid in HBM
-    int pad_bytes;        // r * Ws: zero rows above / below the map in the shared-memory tile
-    int tile_stride;      // (H + 2r) * Ws: one env's tile in shared memory
+    int env_bytes;        // round_up(H * Ws, 16): one env's grid in HBM
+    int pad_bytes;        // zero bytes between / around the tiles in shared memory
     int n_apple, n_waste, area;
     int obs_env;          // N*V*V*3 bytes
     // ---- launch description
-    int E;                // envs per CTA
     int G;                // lanes per env in phase A: 8 (N <= 8) or 16
-    int env_begin;        // first local env of this launch (multiple of E)
+    int env_begin;        // first local env of this launch (multiple of the CTA tile)
     int env_end;          // one past the last valid local env
     int phases, rotate;
     uint32_t spawn_stream;
@@ -74,12 +95,12 @@ struct StepArgs {
     // ---- static tables (device)
     const uint16_t* apple_cell; // [n_apple] in-tile cell ids, row-major (harvest.py:22-26, cleanup.py:53-54)
     const uint16_t* waste_cell; // [n_waste] in-tile cell ids, row-major (cleanup.py:59-60)
-    const uint32_t* color;      // [128] 0x00BBGGRR by ASCII code
+    const uint32_t* color;      // [32] 0x00BBGGRR by cell code
     const uint64_t* harvest_thr; const double* harvest_p;  // [4]
     const uint64_t* apple_thr;   const double* apple_p;    // [area+1]
     const uint64_t* waste_thr;   const double* waste_p;    // [area+1]
     // ---- state (device)
-    uint8_t* grid;        // [B_pad][H][Ws]
+    uint8_t* grid;        // [B_pad][env_bytes]
     uint32_t* agents;     // [B_pad][N] row | col<<8 | ori<<16
     uint8_t* beam_buf;    // [B_pad][64] raylen + firech between phase-split calls
     // ---- I/O (device)
@@ -102,10 +123,26 @@ struct ResetArgs {
 // Launchers implemented in ssd_step.cu.
 cudaError_t launch_step(const StepArgs& a, int threads, cudaStream_t stream);
 cudaError_t launch_reset(const ResetArgs& a, cudaStream_t stream);
-cudaError_t launch_pack_state(int B, int N, int H, int W, int Ws, const uint8_t* grid_in, const int16_t* pos_in,
+cudaError_t launch_pack_state(int B, int N, int H, int W, int Ws, int env_bytes, const uint8_t* grid_in, const int16_t* pos_in,
                               const uint8_t* ori_in, uint8_t* grid, uint32_t* agents, cudaStream_t stream);
-cudaError_t launch_unpack_state(int B, int N, int H, int W, int Ws, const uint8_t* grid, const uint32_t* agents,
+cudaError_t launch_unpack_state(int B, int N, int H, int W, int Ws, int env_bytes, const uint8_t* grid, const uint32_t* agents,
                                 uint8_t* grid_out, int16_t* pos_out, uint8_t* ori_out, cudaStream_t stream);
 cudaError_t launch_philox_selftest(const uint32_t* ctr_key, uint32_t* out, cudaStream_t stream);
+
+// ASCII <-> device cell byte (host helpers shared with ssd_capi.cu)
+inline uint8_t ascii_to_cell(uint8_t ch) {
+    switch (ch) {
+        case '0': return CB(C_PAD);
+        case ' ': return CB(C_EMPTY);
+        case '@': return CB(C_WALL);
+        case 'A': return CB(C_APPLE);
+        case 'H': return CB(C_WASTE);
+        case 'R': return CB(C_RIVER);
+        case 'S': return CB(C_STREAM);
+        case 'F': return CB(C_FIRE);
+        case 'C': return CB(C_CLEAN);
+        default: return (ch >= '1' && ch <= '9') ? CB(static_cast<uint8_t>(C_AGENT + ch - '1')) : CB(C_OTHER);
+    }
+}
 
 }  // namespace ssd

@@ -1,16 +1,17 @@
-// Fused MapEnv.step kernel for sm_100a: one CTA steps E independent environments.
+// Fused MapEnv.step kernel for sm_100a.  Every WARP steps its own 32/G environments end to end
+// (no CTA barrier after the table load), so warps in different phases overlap freely:
 //
-//   load   E grid tiles by TMA bulk copies into zero-padded shared-memory tiles (ssd_internal.h),
-//          agent table and actions straight into registers (one lane per agent)
+//   load   the warp's grid tiles by TMA bulk copies into zero-framed shared-memory tiles
+//          (ssd_internal.h), agent table and actions straight into registers (one lane per agent)
 //   A      moves (map_env.py:357-543), consume (:178-181), beams (:545-649): ONE LANE PER AGENT, a
-//          group of 8 (or 16) lanes per env.  Conflict-free moves are resolved with shuffles; an env
-//          with any contested / occupied target falls back to the literal sequential emulation of
-//          update_moves on the group's first lane.  Each firing agent's three rays walk on 3 lanes.
-//   B      custom_map_update (harvest.py:69-104, cleanup.py:113-179): ONE WARP PER ENV, ballot/popc
-//          prefix ranks give every eligible cell its sequential draw index
+//          group of G = 8 (or 16) lanes per env.  Conflict-free moves are resolved with shuffles; an
+//          env with any contested / occupied target falls back to the literal sequential emulation
+//          of update_moves on the group's first lane.  A firing agent's three rays walk on 3 lanes.
+//   B      custom_map_update (harvest.py:69-104, cleanup.py:113-179): the whole warp per env,
+//          ballot/popc prefix ranks give every eligible cell its sequential draw index
 //   store  grid, agent table, rewards back to HBM
 //   C      get_map_with_agents + return_view + map_to_colors + rotate_view (map_env.py:189-199):
-//          one thread per VIEW ROW; a warp packs 32 rows to their exact byte offsets in a private
+//          one lane per VIEW ROW; the warp packs 32 rows to their exact byte offsets in a private
 //          staging buffer and writes them with coalesced 16-byte stores
 //
 // Reference citations are relative to the reference root (social_dilemmas/envs/...).
@@ -22,8 +23,12 @@
 namespace ssd {
 
 __device__ __forceinline__ int tile_idx(const StepArgs& a, uint32_t key) {
-    return (static_cast<int>(key >> 8) + a.r) * a.Ws + static_cast<int>(key & 255);
+    return static_cast<int>(key >> 8) * a.Ws + static_cast<int>(key & 255);
 }
+
+struct Counters {  // per-lane event counts, reduced per warp at the end of the kernel
+    int steps, eaten, fires, hits, cleaned, apples, waste;
+};
 
 // ====================================================================== phase A: moves
 __device__ __forceinline__ bool occupied(const uint16_t* p, int N, uint32_t key) {
@@ -154,7 +159,7 @@ __device__ __forceinline__ void moves_group(const StepArgs& a, EnvScratch& S, co
             if (o == 0) { r0 = v0; r1 = v1; } else if (o == 3) { r0 = v1; r1 = -v0; }
             else if (o == 1) { r0 = -v1; r1 = v0; } else { r0 = -v0; r1 = -v1; }
             const uint32_t nkey = static_cast<uint32_t>((static_cast<int>(me.key >> 8) + r0) << 8 | (static_cast<int>(me.key & 255) + r1));
-            tgt = (g[tile_idx(a, nkey)] == '@') ? me.key : nkey;  // agent.py:105-113 you can't walk through walls
+            tgt = (g[tile_idx(a, nkey)] == CB(C_WALL)) ? me.key : nkey;  // agent.py:105-113 you can't walk through walls
             mover = true;
         } else if (act == 5) {
             me.ori = (me.ori + 1) & 3;  // TURN_CLOCKWISE map_env.py:729-737
@@ -191,24 +196,23 @@ __device__ __forceinline__ void moves_group(const StepArgs& a, EnvScratch& S, co
 
 // One ray of a beam (map_env.py:566-649); the three rays of a firing agent walk on lanes 0..2 of
 // its group.  The map is wall-enclosed (checked by ssd_create), so the reference's bounds test
-// (:615) can never fire before the wall test (:616).  Returns the number of painted cells.
+// (:615) can never fire before the wall test (:616).  Agent cells carry kFlag, so the position
+// table is only searched when a ray actually runs into somebody.  Returns the painted cell count.
 __device__ __forceinline__ int ray_walk(const StepArgs& a, EnvScratch& S, uint8_t* g, uint32_t key, int ori, int s,
                                         bool clean, int& upd, int& hits) {
-    const int N = a.N;
     const int d0 = (ori == 1) - (ori == 3), d1 = (ori == 2) - (ori == 0);  // ORIENTATIONS map_env.py:19-22
     int r = static_cast<int>(key >> 8) + d0, c = static_cast<int>(key & 255) + d1;  // :608-613
     if (s == 1) { r += -d1 - d0; c += d0 - d1; }  // start + rotate_right(d) - d   (:607-609)
     if (s == 2) { r -= -d1 + d0; c -= d0 + d1; }  // start - rotate_right(d) - d
     const int dp = d0 * a.Ws + d1;
-    int p = (r + a.r) * a.Ws + c;
+    int p = r * a.Ws + c;
     int n = 0;
     for (int i = 0; i < a.beam_len; ++i) {
-        const uint8_t cell = g[p];
-        if (cell == '@') break;                                 // :616
-        const bool isH = clean && cell == 'H';
-        const int hit = by_pos(S.pos, N, static_cast<uint32_t>(r << 8 | c));  // :621-622 agents absorb beams
-        if (hit >= 0) {
-            if (!clean) { S.rew[hit] -= 50; ++hits; }           // agent.py:166-168, 212-214
+        const uint8_t raw = g[p], cell = raw & 0x7F;
+        if (cell == CB(C_WALL)) break;                          // :616
+        const bool isH = clean && cell == CB(C_WASTE);
+        if (raw & kFlag) {                                      // :621-629 agents absorb beams
+            if (!clean) { S.rew[by_pos(S.pos, a.N, static_cast<uint32_t>(r << 8 | c))] -= 50; ++hits; }  // agent.py:166-168, 212-214
             ++n;                                                // :624
             if (isH) upd = p;                                   // :625-628
             break;
@@ -226,13 +230,13 @@ __device__ __forceinline__ int ray_walk(const StepArgs& a, EnvScratch& S, uint8_
 // harvest.py:90, cleanup.py:138); consume already turned every apple under an agent into ' '.
 template <bool TAPE>
 __device__ __forceinline__ void harvest_spawn(const StepArgs& a, uint8_t* g, const uint16_t* s_apple, uint16_t* list,
-                                              int local_env, const PhiloxKey& pk, int lane, int* s_stats) {
+                                              int local_env, const PhiloxKey& pk, int lane, Counters& cnt) {
     const int Ws = a.Ws, n_apple = a.n_apple;
     int base = 0;
     for (int i0 = 0; i0 < n_apple; i0 += 32) {  // eligibility scan in row-major apple-point order (harvest.py:87-90)
         const int i = i0 + lane;
         bool el = false;
-        if (i < n_apple) { const uint8_t c = g[s_apple[i]]; el = (c != 'A') && !(c & 0x80); }
+        if (i < n_apple) { const uint8_t c = g[s_apple[i]]; el = (c != CB(C_APPLE)) && !(c & kFlag); }
         const uint32_t m = __ballot_sync(0xffffffffu, el);
         if (el) list[base + __popc(m & lanemask_lt())] = static_cast<uint16_t>(i);
         base += __popc(m);
@@ -245,8 +249,9 @@ __device__ __forceinline__ void harvest_spawn(const StepArgs& a, uint8_t* g, con
             const int i = list[j];
             const uint8_t* q = g + s_apple[i];
             // 3x3 window, j*j + k*k <= APPLE_RADIUS(2) (harvest.py:92-99); cells outside the map are 0 in the tile
-            int n = (q[-Ws - 1] == 'A') + (q[-Ws] == 'A') + (q[-Ws + 1] == 'A') + (q[-1] == 'A') + (q[1] == 'A') +
-                    (q[Ws - 1] == 'A') + (q[Ws] == 'A') + (q[Ws + 1] == 'A');
+            constexpr uint8_t A = CB(C_APPLE);
+            int n = (q[-Ws - 1] == A) + (q[-Ws] == A) + (q[-Ws + 1] == A) + (q[-1] == A) + (q[1] == A) +
+                    (q[Ws - 1] == A) + (q[Ws] == A) + (q[Ws + 1] == A);
             n = n < 3 ? n : 3;
             bool spawn = false;
             if (TAPE) spawn = a.tape_u[static_cast<size_t>(local_env) * a.u_stride + j] < a.harvest_p[n];
@@ -255,50 +260,47 @@ __device__ __forceinline__ void harvest_spawn(const StepArgs& a, uint8_t* g, con
         }
     }
     __syncwarp();  // every read saw the pre-spawn grid; writes happen after the scan (harvest.py:72-73)
-    int n_new = 0;
     for (int j = lane; j < n_draw; j += 32)
-        if (list[j] & 0x8000) { g[s_apple[list[j] & 0x7fff]] = 'A'; ++n_new; }
-    if (n_new) atomicAdd(&s_stats[6], n_new);
+        if (list[j] & 0x8000) { g[s_apple[list[j] & 0x7fff]] = CB(C_APPLE); ++cnt.apples; }
 }
 
 template <bool TAPE>
 __device__ __forceinline__ void cleanup_spawn(const StepArgs& a, uint8_t* g, const uint16_t* s_apple, uint32_t* keys,
-                                              int local_env, const PhiloxKey& pk, int lane, int* s_stats) {
+                                              int local_env, const PhiloxKey& pk, int lane, Counters& cnt) {
     const int n_apple = a.n_apple, n_waste = a.n_waste;
     // compute_permitted_area / compute_probabilities, cleanup.py:156-179: count 'H' over the whole grid
-    int cnt = 0;
+    int nh = 0;
     for (int i = lane * 16; i < a.env_bytes; i += 512) {
-        const uint4 v = *reinterpret_cast<const uint4*>(g + a.pad_bytes + i);
+        const uint4 v = *reinterpret_cast<const uint4*>(g + i);
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const uint32_t x = (w[q] & 0x7F7F7F7Fu) ^ 0x48484848u;          // byte == 0  <=>  cell is 'H'
+            const uint32_t x = (w[q] & 0x7F7F7F7Fu) ^ (0x01010101u * CB(C_WASTE));  // byte == 0  <=>  cell is 'H'
             const uint32_t nz = ((x + 0x7F7F7F7Fu) | x) & 0x80808080u;      // bit 7 set  <=>  byte != 0
-            cnt += 4 - __popc(nz);
+            nh += 4 - __popc(nz);
         }
     }
-    int h = __reduce_add_sync(0xffffffffu, cnt);
+    int h = __reduce_add_sync(0xffffffffu, nh);
     h = h < a.area ? h : a.area;
     const double apple_p = a.apple_p[h], waste_p = a.waste_p[h];
     const uint64_t apple_thr = a.apple_thr[h], waste_thr = a.waste_thr[h];
 
-    int base = 0, n_new = 0;
+    int base = 0;
     for (int i0 = 0; i0 < n_apple; i0 += 32) {  // apple pass, cleanup.py:135-141 (a draw per eligible point)
         const int i = i0 + lane;
         bool el = false;
         int idx = 0;
-        if (i < n_apple) { idx = s_apple[i]; const uint8_t c = g[idx]; el = (c != 'A') && !(c & 0x80); }
+        if (i < n_apple) { idx = s_apple[i]; const uint8_t c = g[idx]; el = (c != CB(C_APPLE)) && !(c & kFlag); }
         const uint32_t m = __ballot_sync(0xffffffffu, el);
         if (el) {
             const int rank = base + __popc(m & lanemask_lt());
             bool spawn;
             if (TAPE) spawn = a.tape_u[static_cast<size_t>(local_env) * a.u_stride + rank] < apple_p;
             else spawn = apple_thr != 0 && philox_u53(pk, a.spawn_stream, rank) < apple_thr;
-            if (spawn) { g[idx] = 'A'; ++n_new; }  // apple cells are never read again in this pass
+            if (spawn) { g[idx] = CB(C_APPLE); ++cnt.apples; }  // apple cells are never read again in this pass
         }
         base += __popc(m);
     }
-    if (n_new) atomicAdd(&s_stats[6], n_new);
 
     if (waste_p != 0.0 && n_waste > 0) {  // `not np.isclose(p, 0)`: p is 0 or wasteSpawnProbability (cleanup.py:144)
         if (TAPE) {
@@ -309,15 +311,15 @@ __device__ __forceinline__ void cleanup_spawn(const StepArgs& a, uint8_t* g, con
                 int idx = 0;
                 if (i < n_waste) {  // tape cells are row*W+col of the reference's map
                     const int cell = wo[i];
-                    idx = (cell / a.W + a.r) * a.Ws + cell % a.W;
-                    el = (g[idx] & 0x7F) != 'H';  // :149
+                    idx = (cell / a.W) * a.Ws + cell % a.W;
+                    el = (g[idx] & 0x7F) != CB(C_WASTE);  // :149
                 }
                 const uint32_t m = __ballot_sync(0xffffffffu, el);
                 bool ok = false;
                 if (el) ok = a.tape_u[static_cast<size_t>(local_env) * a.u_stride + base + __popc(m & lanemask_lt())] < waste_p;
                 const uint32_t s = __ballot_sync(0xffffffffu, ok);
                 if (s) {  // first success spawns and breaks (:151-153); waste may appear under an agent
-                    if (lane == __ffs(s) - 1) { g[idx] = 'H' | (g[idx] & 0x80); atomicAdd(&s_stats[7], 1); }
+                    if (lane == __ffs(s) - 1) { g[idx] = CB(C_WASTE) | (g[idx] & kFlag); ++cnt.waste; }
                     break;
                 }
                 base += __popc(m);
@@ -335,7 +337,7 @@ __device__ __forceinline__ void cleanup_spawn(const StepArgs& a, uint8_t* g, con
                     if (i + 3 < n_waste) keys[i + 3] = k4.w;
                 }
             }
-            for (int i = lane; i < n_waste; i += 32) n_el += (g[a.waste_cell[i]] & 0x7F) != 'H';
+            for (int i = lane; i < n_waste; i += 32) n_el += (g[a.waste_cell[i]] & 0x7F) != CB(C_WASTE);
             n_el = __reduce_add_sync(0xffffffffu, n_el);
             __syncwarp();
             // the k-th scanned non-'H' cell draws uniform #(base + k); the first success wins
@@ -347,7 +349,7 @@ __device__ __forceinline__ void cleanup_spawn(const StepArgs& a, uint8_t* g, con
                 for (int it = 0; it <= kstar; ++it) {
                     uint64_t best = ~0ull;
                     for (int i = lane; i < n_waste; i += 32) {
-                        if ((g[a.waste_cell[i]] & 0x7F) == 'H') continue;
+                        if ((g[a.waste_cell[i]] & 0x7F) == CB(C_WASTE)) continue;
                         const uint64_t kx = static_cast<uint64_t>(keys[i]) << 32 | static_cast<uint32_t>(i);
                         if ((first || kx > prev) && kx < best) best = kx;
                     }
@@ -356,8 +358,8 @@ __device__ __forceinline__ void cleanup_spawn(const StepArgs& a, uint8_t* g, con
                 }
                 if (lane == 0) {
                     const int idx = a.waste_cell[static_cast<uint32_t>(prev)];
-                    g[idx] = 'H' | (g[idx] & 0x80);
-                    atomicAdd(&s_stats[7], 1);
+                    g[idx] = CB(C_WASTE) | (g[idx] & kFlag);
+                    ++cnt.waste;
                 }
             }
         }
@@ -366,32 +368,40 @@ __device__ __forceinline__ void cleanup_spawn(const StepArgs& a, uint8_t* g, con
 
 // ====================================================================== phase C: rendering
 // Per-agent window geometry (np.rot90 index algebra of rotate_view map_env.py:669-689 folded with
-// return_view utility_funcs.py:59-114): view pixel (i, j) reads tile byte a0 + i*si + j*sj.  The
-// tile is zero padded by r cells on every side, so no pixel needs a bounds test.
-__device__ __forceinline__ uint2 view_param(const StepArgs& a, const EnvScratch& S, int e, int ag) {
+// return_view utility_funcs.py:59-114): view pixel (i, j) reads the warp-tile byte a0 + i*si + j*sj.
+// Tiles are framed by >= r*Ws + r zero bytes and rows end in r zero bytes, so no pixel needs a
+// bounds test: everything outside the map reads as C_PAD.
+__device__ __forceinline__ uint2 view_param(const StepArgs& a, const EnvScratch& S, int tile_off, int ag) {
     const int pr = S.pos[ag] >> 8, pc = S.pos[ag] & 255, r = a.r, Ws = a.Ws;
     const int k = a.rotate ? ((4 - S.ori[ag]) & 3) : 0;  // UP 0, LEFT 1, DOWN 2, RIGHT 3
-    int a0, si, sj;  // in-tile row of map row x is x + r
-    if (k == 0)      { a0 = pr * Ws + pc - r;           si = Ws;  sj = 1; }    // cell (pr-r+i, pc-r+j)
-    else if (k == 2) { a0 = (pr + 2 * r) * Ws + pc + r; si = -Ws; sj = -1; }   // cell (pr+r-i, pc+r-j)
-    else if (k == 1) { a0 = pr * Ws + pc + r;           si = -1;  sj = Ws; }   // cell (pr-r+j, pc+r-i)
-    else             { a0 = (pr + 2 * r) * Ws + pc - r; si = 1;   sj = -Ws; }  // cell (pr+r-j, pc-r+i)
-    return make_uint2(static_cast<uint32_t>(a0 + e * a.tile_stride),
-                      (static_cast<uint32_t>(si) & 0xffffu) | static_cast<uint32_t>(sj) << 16);
+    int a0, si, sj;
+    if (k == 0)      { a0 = (pr - r) * Ws + pc - r; si = Ws;  sj = 1; }    // cell (pr-r+i, pc-r+j)
+    else if (k == 2) { a0 = (pr + r) * Ws + pc + r; si = -Ws; sj = -1; }   // cell (pr+r-i, pc+r-j)
+    else if (k == 1) { a0 = (pr - r) * Ws + pc + r; si = -1;  sj = Ws; }   // cell (pr-r+j, pc+r-i)
+    else             { a0 = (pr + r) * Ws + pc - r; si = 1;   sj = -Ws; }  // cell (pr+r-j, pc-r+i)
+    return make_uint2(static_cast<uint32_t>(a0 + tile_off), (static_cast<uint32_t>(si) & 0xffffu) | static_cast<uint32_t>(sj) << 16);
 }
 
-// One thread renders one row of one agent's view (V pixels = 3V bytes).  A warp owns 32 consecutive
-// rows = 96V contiguous, 16-byte-multiple bytes of the obs tensor: rows are packed to their exact
-// byte offsets in a warp-private staging buffer (3V is odd, so consecutive rows start at byte
-// phases 0,1,2,3: each thread owns the 32-bit words whose FIRST byte lies in its row and takes the
-// first pixel of the next row from the neighbouring lane), then stored with coalesced 16-byte writes.
+__device__ __forceinline__ uint32_t cell_color(const uint32_t* s_color, uint8_t cell) {  // cell byte = code * 4
+    return *reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(s_color) + cell);
+}
+
+// One lane renders one row of one agent's view (V pixels = 3V bytes).  The warp owns `total_rows`
+// consecutive rows of the obs tensor starting at `dst` (4-byte aligned); 32 rows = 96V bytes are
+// packed to their exact byte offsets in the warp's staging buffer (3V is odd, so consecutive rows
+// start at byte phases 0,1,2,3: each lane owns the 32-bit words whose FIRST byte lies in its row
+// and takes the first pixel of the next row from the neighbouring lane).  The staging buffer is
+// shifted by (dst & 15) so that shared and global addresses are congruent mod 16 and the body of
+// every chunk leaves with 16-byte stores.
 template <int VT>
-__device__ __forceinline__ void render_rows(const uint2* s_view, const uint8_t* s_grid, const uint32_t* s_color,
-                                            uint32_t* stage, uint8_t* dst, int total_rows, bool aligned16) {
+__device__ __forceinline__ void render_rows(const uint2* s_view, const uint8_t* tiles, const uint32_t* s_color,
+                                            uint32_t* stage, uint8_t* dst, int total_rows) {
     constexpr int RB = 3 * VT;           // bytes per view row
     constexpr int NP = (RB + 3 + 3) / 4; // words covering the row plus the next row's first pixel
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    for (int base = warp * 32; base < total_rows; base += nwarps * 32) {
+    const int lane = threadIdx.x & 31;
+    const int mis = static_cast<int>(reinterpret_cast<uintptr_t>(dst) & 15);  // multiple of 4
+    uint32_t* st = stage + (mis >> 2);
+    for (int base = 0; base < total_rows; base += 32) {
         const int R = base + lane;
         uint32_t X[VT + 2];
 #pragma unroll
@@ -400,9 +410,9 @@ __device__ __forceinline__ void render_rows(const uint2* s_view, const uint8_t* 
             const int ga = R / VT, i = R - ga * VT;  // rows are ordered (env, agent, i)
             const uint2 vp = s_view[ga];
             const int si = static_cast<int16_t>(vp.y & 0xffffu), sj = static_cast<int32_t>(vp.y) >> 16;
-            const uint8_t* g = s_grid + static_cast<int32_t>(vp.x) + i * si;
+            const uint8_t* g = tiles + static_cast<int32_t>(vp.x) + i * si;
 #pragma unroll
-            for (int j = 0; j < VT; ++j) X[j] = s_color[g[j * sj]];
+            for (int j = 0; j < VT; ++j) X[j] = cell_color(s_color, g[j * sj]);
         }
         X[VT] = __shfl_down_sync(0xffffffffu, X[0], 1);
         uint32_t P[NP + 1];
@@ -419,102 +429,103 @@ __device__ __forceinline__ void render_rows(const uint2* s_view, const uint8_t* 
             const int M = w1 - w0 + 1;
 #pragma unroll
             for (int m = 0; m < NP; ++m)
-                if (m < M) stage[w0 + m] = __funnelshift_r(P[m], P[m + 1], 8 * d);
+                if (m < M) st[w0 + m] = __funnelshift_r(P[m], P[m + 1], 8 * d);
         }
         __syncwarp();
-        const int nbytes = min(32, total_rows - base) * RB;
-        uint8_t* out = dst + static_cast<size_t>(base) * RB;
-        if (aligned16) {
+        const int nbytes = min(32, total_rows - base) * RB;  // multiple of 4
+        uint8_t* out = dst + static_cast<size_t>(base) * RB - mis;  // 16-byte aligned
+        const uint8_t* sb = reinterpret_cast<const uint8_t*>(stage);
 #pragma unroll
-            for (int it = 0; it < (32 * RB + 511) / 512; ++it) {
-                const int off = it * 512 + lane * 16;
-                if (off < nbytes)
-                    *reinterpret_cast<uint4*>(out + off) = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(stage) + off);
+        for (int it = 0; it < (32 * RB + 16 + 511) / 512; ++it) {
+            const int off = it * 512 + lane * 16;  // slot [off, off+16) of the shifted chunk [mis, mis+nbytes)
+            if (off >= mis && off + 16 <= mis + nbytes) {
+                *reinterpret_cast<uint4*>(out + off) = *reinterpret_cast<const uint4*>(sb + off);
+            } else if (off + 16 > mis && off < mis + nbytes) {
+#pragma unroll
+                for (int w = 0; w < 16; w += 4)
+                    if (off + w >= mis && off + w < mis + nbytes)
+                        *reinterpret_cast<uint32_t*>(out + off + w) = *reinterpret_cast<const uint32_t*>(sb + off + w);
             }
-        } else {
-            for (int off = lane * 4; off < nbytes; off += 128)
-                *reinterpret_cast<uint32_t*>(out + off) = stage[off >> 2];
         }
         __syncwarp();
     }
 }
 
-// Any view size / partially valid tiles: one thread per pixel, byte stores straight to HBM.
-__device__ __forceinline__ void render_generic(const StepArgs& a, const EnvScratch* s_env, const uint2* s_view,
-                                               const uint8_t* s_grid, const uint32_t* s_color, uint8_t* dst, int n_envs) {
+// Any view size / partially valid warps: one lane per pixel, byte stores straight to HBM.
+__device__ __forceinline__ void render_generic(const StepArgs& a, const EnvScratch* envs, const uint2* s_view,
+                                               const uint8_t* tiles, const uint32_t* s_color, uint8_t* dst, int n_envs) {
     const int V = a.V, N = a.N;
     const int total = n_envs * N * V * V;
-    for (int p = threadIdx.x; p < total; p += blockDim.x) {
+    for (int p = threadIdx.x & 31; p < total; p += 32) {
         const int j = p % V, i = (p / V) % V, ga = p / (V * V);
-        if (!s_env[ga / N].active) continue;
+        if (!envs[ga / N].active) continue;
         const uint2 vp = s_view[ga];
         const int si = static_cast<int16_t>(vp.y & 0xffffu), sj = static_cast<int32_t>(vp.y) >> 16;
-        const uint32_t c = s_color[s_grid[static_cast<int32_t>(vp.x) + i * si + j * sj]];
+        const uint32_t c = cell_color(s_color, tiles[static_cast<int32_t>(vp.x) + i * si + j * sj]);
         dst[3 * static_cast<size_t>(p)] = c & 255; dst[3 * static_cast<size_t>(p) + 1] = (c >> 8) & 255; dst[3 * static_cast<size_t>(p) + 2] = (c >> 16) & 255;
     }
 }
 
-__device__ __forceinline__ uint8_t agent_char(int i) {  // str(int(agent_id[-1]) + 1) in a <U1 array (map_env.py:290,297)
-    const int v = i % 10 + 1;
-    return static_cast<uint8_t>(v == 10 ? '1' : '0' + v);
+__device__ __forceinline__ uint8_t agent_cell(int i) {  // str(int(agent_id[-1]) + 1) in a <U1 array (map_env.py:290,297)
+    const int v = i % 10;  // '1'..'9', and agent-9 / agent-19 alias '1' ('10' truncated)
+    return CB(static_cast<uint8_t>(C_AGENT + (v == 9 ? 0 : v)));
 }
 
 // ====================================================================== the fused kernel
 template <int KIND, bool TAPE, int VT>
 __global__ void __launch_bounds__(kMaxThreads) ssd_step_kernel(const __grid_constant__ StepArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint32_t s_color[kNumCodes];
+    __shared__ int s_cta_stats[SSD_NUM_STATS];
+    __shared__ int s_done;
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
-    const int E = a.E, N = a.N;
-    const int e0 = a.env_begin + blockIdx.x * E;
-    const int nvalid = min(E, a.env_end - e0);
-
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + a.L.mbar);
-    uint8_t* s_grid = smem + a.L.grid;
-    uint32_t* s_color = reinterpret_cast<uint32_t*>(smem + a.L.color);
-    uint16_t* s_apple = reinterpret_cast<uint16_t*>(smem + a.L.apple);
-    EnvScratch* s_env = reinterpret_cast<EnvScratch*>(smem + a.L.env);
-    int* s_stats = reinterpret_cast<int*>(smem + a.L.stats);
+    const int N = a.N, G = a.G, EPW = 32 / G;
     const int phases = a.phases;
+    uint16_t* s_apple = reinterpret_cast<uint16_t*>(smem + a.L.apple);
 
-    // ---- load: one TMA bulk copy per env tile; zero rows and static tables while they are in flight
-    if (tid == 0) mbar_init(mbar, 1);
-    __syncthreads();
-    if (warp == 0) {
-        if (lane == 0) mbar_expect_tx(mbar, static_cast<uint32_t>(E) * a.env_bytes);
-        __syncwarp();
-        for (int e = lane; e < E; e += 32)
-            bulk_g2s(s_grid + e * a.tile_stride + a.pad_bytes, a.grid + static_cast<size_t>(e0 + e) * a.env_bytes, a.env_bytes, mbar);
-    }
-    {
-        const int n16 = a.pad_bytes / 16;  // zero rows above and below every tile
-        const uint4 z = make_uint4(0, 0, 0, 0);
-        for (int i = tid; i < E * 2 * n16; i += nthr) {
-            const int e = i / (2 * n16), q = i - e * 2 * n16;
-            const int off = e * a.tile_stride + (q < n16 ? q * 16 : a.pad_bytes + a.env_bytes + (q - n16) * 16);
-            *reinterpret_cast<uint4*>(s_grid + off) = z;
-        }
-    }
-    if (phases & SSD_PHASE_RENDER)
-        for (int i = tid; i < 128; i += nthr) s_color[i] = a.color[i];
+    // ---- CTA-shared tables, then the only CTA barrier of the kernel
+    if (tid < kNumCodes) s_color[tid] = a.color[tid];
+    if (tid < SSD_NUM_STATS) s_cta_stats[tid] = 0;
+    if (tid == 0) s_done = 0;
     if (phases & SSD_PHASE_SPAWN)
         for (int i = tid; i < a.n_apple; i += nthr) s_apple[i] = a.apple_cell[i];
-    if (tid < SSD_NUM_STATS) s_stats[tid] = 0;
     __syncthreads();
-    mbar_wait(mbar, 0);  // grid tiles landed
 
-    // ---- phase A: one lane per agent, G lanes per env, 32/G envs per warp and pass
-    const int G = a.G, al = lane & (G - 1), gbase = lane & ~(G - 1);
-    const int slots = nwarps * (32 / G);
-    PhiloxKey pk;
-    pk.k0 = a.key0; pk.k1 = a.key1; pk.t = a.t;
-    for (int ebase = warp * (32 / G); ebase < E; ebase += slots) {  // warp-uniform trip count
-        const int e = ebase + lane / G;
-        const bool env_ok = e < E;
-        EnvScratch& S = s_env[env_ok ? e : 0];
-        const bool active = env_ok && e < nvalid && (a.mask == nullptr || a.mask[e0 + e] != 0);
-        const bool valid = env_ok && al < N;
-        const size_t gi = static_cast<size_t>(e0 + (env_ok ? e : 0)) * N + (valid ? al : 0);
-        uint8_t* g = s_grid + (env_ok ? e : 0) * a.tile_stride;
+    // ---- this warp's envs
+    uint8_t* wbase = smem + a.L.warp0 + warp * a.L.warp_stride;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(wbase + a.L.w_mbar);
+    uint8_t* tiles = wbase + a.L.w_tiles;
+    EnvScratch* envs = reinterpret_cast<EnvScratch*>(wbase + a.L.w_env);
+    const int tile_pitch = a.env_bytes + a.pad_bytes;
+    const int we = a.env_begin + (blockIdx.x * nwarps + warp) * EPW;  // first local env of this warp
+    const int nvalid = max(0, min(EPW, a.env_end - we));
+    Counters cnt = {0, 0, 0, 0, 0, 0, 0};
+
+    if (nvalid > 0) {
+        // ---- load: one TMA bulk copy per env tile; zero frames while they are in flight
+        if (lane == 0) { mbar_init(mbar, 1); mbar_expect_tx(mbar, static_cast<uint32_t>(EPW) * a.env_bytes); }
+        __syncwarp();
+        if (lane < EPW)
+            bulk_g2s(tiles + a.pad_bytes + lane * tile_pitch, a.grid + static_cast<size_t>(we + lane) * a.env_bytes, a.env_bytes, mbar);
+        {
+            const uint4 z = make_uint4(0, 0, 0, 0);
+            for (int q = 0; q <= EPW; ++q)
+                for (int i = lane * 16; i < a.pad_bytes; i += 512) *reinterpret_cast<uint4*>(tiles + q * tile_pitch + i) = z;
+        }
+        mbar_wait(mbar, 0);  // tiles landed
+        __syncwarp();
+
+        // ---- phase A: one lane per agent, G lanes per env
+        const int al = lane & (G - 1), gbase = lane & ~(G - 1), j = lane / G;  // j: env slot of this lane's group
+        EnvScratch& S = envs[j];
+        uint8_t* g = tiles + a.pad_bytes + j * tile_pitch;
+        const int e = we + j;
+        const bool active = j < nvalid && (a.mask == nullptr || a.mask[e] != 0);
+        const bool valid = al < N;
+        const size_t gi = static_cast<size_t>(e) * N + (valid ? al : 0);
+        PhiloxKey pk;
+        pk.k0 = a.key0; pk.k1 = a.key1; pk.t = a.t;
+        pk.env = static_cast<uint32_t>(a.env_id0 + static_cast<uint64_t>(e));
         AgentLane me;
         me.key = 0x0101; me.ori = 0; me.act = -1; me.rew = 0;
         if (valid) {
@@ -527,27 +538,28 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_kernel(const __grid_cons
             S.rew[al] = 0;
             S.firech[al] = 0;
         }
-        if (env_ok && al == 0) S.active = active;
-        pk.env = static_cast<uint32_t>(a.env_id0 + static_cast<uint64_t>(e0 + e));
+        if (al == 0) S.active = active;
         __syncwarp();
         if (phases & SSD_PHASE_MOVES) {
-            moves_group<TAPE>(a, S, g, me, valid && active, al, G, e0 + e, pk);
-            if (active && al == 0) atomicAdd(&s_stats[0], 1);
+            moves_group<TAPE>(a, S, g, me, valid && active, al, G, e, pk);
+            cnt.steps += (active && al == 0);
         }
         if (valid) { S.pos[al] = static_cast<uint16_t>(me.key); S.ori[al] = static_cast<uint8_t>(me.ori); }
         __syncwarp();
         const int my_idx = tile_idx(a, me.key);
         if (phases & SSD_PHASE_CONSUME) {  // map_env.py:178-181, agent.py:177-183 / 216-222
-            const bool on_apple = valid && active && g[my_idx] == 'A';
+            const bool on_apple = valid && active && g[my_idx] == CB(C_APPLE);
             // agents sharing a cell: the first one in agent order eats
             const uint32_t same = __match_any_sync(0xffffffffu, on_apple ? (me.key | static_cast<uint32_t>(gbase) << 16) : (0x80000000u | lane));
             __syncwarp();
-            if (on_apple && (__ffs(same) - 1) == lane) { g[my_idx] = ' '; me.rew += 1; atomicAdd(&s_stats[2], 1); }
+            if (on_apple && (__ffs(same) - 1) == lane) { g[my_idx] = CB(C_EMPTY); me.rew += 1; ++cnt.eaten; }
             __syncwarp();
         }
+        if ((phases & (SSD_PHASE_BEAMS | SSD_PHASE_SPAWN)) && valid && active) g[my_idx] |= kFlag;  // "an agent stands here"
+        __syncwarp();
         if ((phases & SSD_PHASE_BEAMS) && KIND != SSD_KIND_PLAIN) {  // update_custom_moves map_env.py:545-552
             for (int k = 0; k < N; ++k) {  // action-dict order
-                const int ag = env_ok ? S.order[k] : 0;
+                const int ag = S.order[k];
                 const int act_k = __shfl_sync(0xffffffffu, me.act, ag, G);
                 const uint32_t key_k = __shfl_sync(0xffffffffu, me.key, ag, G);
                 const int ori_k = __shfl_sync(0xffffffffu, me.ori, ag, G);
@@ -556,13 +568,13 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_kernel(const __grid_cons
                 const bool clean = act_k == 8;
                 int upd = -1, hits = 0, n = 0;
                 if (fire && al < 3) n = ray_walk(a, S, g, key_k, ori_k, al, clean, upd, hits);
-                if (fire && al == ag && !clean) { me.rew -= 1; atomicAdd(&s_stats[3], 1); }  // fire_beam agent.py:170-172
+                if (fire && al == ag && !clean) { me.rew -= 1; ++cnt.fires; }  // fire_beam agent.py:170-172
                 __syncwarp();
                 if (fire && al < 3) {
                     S.raylen[k * 3 + al] = static_cast<uint8_t>(n);
-                    if (al == 0) S.firech[k] = clean ? 'C' : 'F';
-                    if (upd >= 0) { g[upd] = 'R'; atomicAdd(&s_stats[5], 1); }  // update_map :551-558, before the next agent fires
-                    if (hits) atomicAdd(&s_stats[4], hits);
+                    if (al == 0) S.firech[k] = clean ? CB(C_CLEAN) : CB(C_FIRE);
+                    if (upd >= 0) { g[upd] = CB(C_RIVER) | (g[upd] & kFlag); ++cnt.cleaned; }  // update_map :551-558, before the next agent fires
+                    cnt.hits += hits;
                 }
                 __syncwarp();
             }
@@ -573,107 +585,112 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_kernel(const __grid_cons
                 a.agents[gi] = (me.key >> 8) | (me.key & 255) << 8 | static_cast<uint32_t>(me.ori) << 16;
                 if (a.rew) a.rew[gi] = me.rew;
             }
-            if (phases & SSD_PHASE_SPAWN) g[my_idx] |= 0x80;  // flag agent cells for the spawn pass
         }
-    }
-    // beams recorded by an earlier phase call of this step (phase-split mode only)
-    if (a.use_beam_buf) {
-        __syncthreads();
-        const bool load = (phases & SSD_PHASE_RENDER) && !(phases & SSD_PHASE_BEAMS);
-        const bool store = (phases & SSD_PHASE_BEAMS) && !(phases & SSD_PHASE_RENDER);
-        for (int i = tid; i < E * 64; i += nthr) {
-            const int e = i >> 6, q = i & 63;
-            if (!s_env[e].active) continue;
-            uint8_t* p = q < 48 ? &s_env[e].raylen[q] : &s_env[e].firech[q - 48];
-            uint8_t* gp = a.beam_buf + static_cast<size_t>(e0 + e) * 64 + q;
-            if (load) *p = *gp;
-            if (store) *gp = *p;
-        }
-    }
-    __syncthreads();
-
-    // ---- phase B: one warp per env
-    if ((phases & SSD_PHASE_SPAWN) && KIND != SSD_KIND_PLAIN) {
-        for (int e = warp; e < E; e += nwarps) {
-            if (!s_env[e].active) continue;
-            uint8_t* g = s_grid + e * a.tile_stride;
-            pk.env = static_cast<uint32_t>(a.env_id0 + static_cast<uint64_t>(e0 + e));
-            void* scratch = smem + a.L.list + warp * a.L.list_stride;
-            if (KIND == SSD_KIND_HARVEST)
-                harvest_spawn<TAPE>(a, g, s_apple, static_cast<uint16_t*>(scratch), e0 + e, pk, lane, s_stats);
-            else
-                cleanup_spawn<TAPE>(a, g, s_apple, static_cast<uint32_t*>(scratch), e0 + e, pk, lane, s_stats);
-        }
-        __syncthreads();
-    }
-
-    // ---- store: grid rows back to HBM (bit 7 = agent flag of the spawn pass, stripped on the way out)
-    if (phases & (SSD_PHASE_CONSUME | SSD_PHASE_BEAMS | SSD_PHASE_SPAWN)) {
-        const int vec_per_env = a.env_bytes / 16;
-        for (int e = warp; e < E; e += nwarps) {
-            if (!s_env[e].active) continue;
-            uint4* gdst = reinterpret_cast<uint4*>(a.grid + static_cast<size_t>(e0 + e) * a.env_bytes);
-            const uint4* gsrc = reinterpret_cast<const uint4*>(s_grid + e * a.tile_stride + a.pad_bytes);
-            for (int i = lane; i < vec_per_env; i += 32) {
-                uint4 v = gsrc[i];
-                v.x &= 0x7F7F7F7Fu; v.y &= 0x7F7F7F7Fu; v.z &= 0x7F7F7F7Fu; v.w &= 0x7F7F7F7Fu;
-                gdst[i] = v;
-            }
-        }
-    }
-
-    // ---- phase C: overlay + render + coalesced stores
-    if ((phases & SSD_PHASE_RENDER) && a.obs != nullptr) {
-        __syncthreads();  // the grid write-back above has read the tiles
-        // get_map_with_agents map_env.py:280-302: agents in agent order (the last one on a cell wins),
-        // then beams in firing order (a later beam overwrites an earlier one)
-        for (int ebase = warp * (32 / G); ebase < E; ebase += slots) {
-            const int e = ebase + lane / G;
-            const bool env_ok = e < E;
-            const EnvScratch& S = s_env[env_ok ? e : 0];
-            uint8_t* g = s_grid + (env_ok ? e : 0) * a.tile_stride;
-            const bool valid = env_ok && al < N;
-            const uint32_t key = valid ? S.pos[al] : 0x0101u;
-            const uint32_t same = __match_any_sync(0xffffffffu, valid ? (key | static_cast<uint32_t>(gbase) << 16) : (0x80000000u | lane));
-            if (valid && (31 - __clz(same)) == lane) g[tile_idx(a, key)] = agent_char(al);
-            __syncwarp();
-            if (KIND != SSD_KIND_PLAIN) {
-                for (int k = 0; k < N; ++k) {
-                    const uint32_t ch = env_ok ? S.firech[k] : 0;
-                    if (!__any_sync(0xffffffffu, ch != 0)) continue;
-                    if (ch != 0 && al < 3) {
-                        const int ag = S.order[k];
-                        const int ori = S.ori[ag];
-                        const int d0 = (ori == 1) - (ori == 3), d1 = (ori == 2) - (ori == 0);
-                        int r = static_cast<int>(S.pos[ag] >> 8) + d0, c = static_cast<int>(S.pos[ag] & 255) + d1;
-                        if (al == 1) { r += -d1 - d0; c += d0 - d1; }
-                        if (al == 2) { r -= -d1 + d0; c -= d0 + d1; }
-                        const int n = S.raylen[k * 3 + al], dp = d0 * a.Ws + d1;
-                        int p = (r + a.r) * a.Ws + c;
-                        for (int i = 0; i < n; ++i) { g[p] = static_cast<uint8_t>(ch); p += dp; }
-                    }
-                    __syncwarp();
+        // beams recorded by an earlier phase call of this step (phase-split mode only)
+        if (a.use_beam_buf) {
+            const bool load = (phases & SSD_PHASE_RENDER) && !(phases & SSD_PHASE_BEAMS);
+            const bool store = (phases & SSD_PHASE_BEAMS) && !(phases & SSD_PHASE_RENDER);
+            for (int q = 0; q < EPW; ++q) {
+                if (!envs[q].active) continue;
+                for (int i = lane; i < 64; i += 32) {
+                    uint8_t* p = i < 48 ? &envs[q].raylen[i] : &envs[q].firech[i - 48];
+                    uint8_t* gp = a.beam_buf + static_cast<size_t>(we + q) * 64 + i;
+                    if (load) *p = *gp;
+                    if (store) *gp = *p;
                 }
             }
         }
-        uint2* s_view = reinterpret_cast<uint2*>(smem + a.L.view);
-        for (int i = tid; i < E * N; i += nthr) s_view[i] = view_param(a, s_env[i / N], i / N, i % N);
-        __syncthreads();
-        uint8_t* dst = a.obs + static_cast<size_t>(e0) * a.obs_env;
-        const bool all_active = (nvalid == E) && (a.mask == nullptr);
-        if constexpr (VT > 0) {
-            if (all_active) {
-                uint32_t* stage = reinterpret_cast<uint32_t*>(smem + a.L.stage + warp * a.L.stage_stride);
-                render_rows<VT>(s_view, s_grid, s_color, stage, dst, E * N * VT, (reinterpret_cast<uintptr_t>(dst) & 15) == 0);
-            } else {
-                render_generic(a, s_env, s_view, s_grid, s_color, dst, nvalid);
+        __syncwarp();
+
+        // ---- phase B: the whole warp per env
+        if ((phases & SSD_PHASE_SPAWN) && KIND != SSD_KIND_PLAIN) {
+            for (int q = 0; q < EPW; ++q) {
+                if (!envs[q].active) continue;
+                pk.env = static_cast<uint32_t>(a.env_id0 + static_cast<uint64_t>(we + q));
+                void* scratch = wbase + a.L.w_list;
+                if (KIND == SSD_KIND_HARVEST)
+                    harvest_spawn<TAPE>(a, tiles + a.pad_bytes + q * tile_pitch, s_apple, static_cast<uint16_t*>(scratch), we + q, pk, lane, cnt);
+                else
+                    cleanup_spawn<TAPE>(a, tiles + a.pad_bytes + q * tile_pitch, s_apple, static_cast<uint32_t*>(scratch), we + q, pk, lane, cnt);
+                __syncwarp();
             }
-        } else {
-            render_generic(a, s_env, s_view, s_grid, s_color, dst, nvalid);
+        }
+
+        // ---- store: grid rows back to HBM (kFlag stripped on the way out)
+        if (phases & (SSD_PHASE_CONSUME | SSD_PHASE_BEAMS | SSD_PHASE_SPAWN)) {
+            for (int q = 0; q < EPW; ++q) {
+                if (!envs[q].active) continue;
+                uint4* gdst = reinterpret_cast<uint4*>(a.grid + static_cast<size_t>(we + q) * a.env_bytes);
+                const uint4* gsrc = reinterpret_cast<const uint4*>(tiles + a.pad_bytes + q * tile_pitch);
+                for (int i = lane; i < a.env_bytes / 16; i += 32) {
+                    uint4 v = gsrc[i];
+                    v.x &= 0x7F7F7F7Fu; v.y &= 0x7F7F7F7Fu; v.z &= 0x7F7F7F7Fu; v.w &= 0x7F7F7F7Fu;
+                    gdst[i] = v;
+                }
+            }
+        }
+
+        // ---- phase C: overlay + render + coalesced stores
+        if ((phases & SSD_PHASE_RENDER) && a.obs != nullptr) {
+            __syncwarp();  // the write-back above has read the tiles
+            // get_map_with_agents map_env.py:280-302: agents in agent order (the last one on a cell wins),
+            // then beams in firing order (a later beam overwrites an earlier one)
+            {
+                const uint32_t key = valid ? S.pos[al] : 0x0101u;
+                const uint32_t same = __match_any_sync(0xffffffffu, valid ? (key | static_cast<uint32_t>(gbase) << 16) : (0x80000000u | lane));
+                if (valid && (31 - __clz(same)) == lane) g[tile_idx(a, key)] = agent_cell(al);
+                __syncwarp();
+                if (KIND != SSD_KIND_PLAIN) {
+                    for (int k = 0; k < N; ++k) {
+                        const uint32_t ch = S.firech[k];
+                        if (!__any_sync(0xffffffffu, ch != 0)) continue;
+                        if (ch != 0 && al < 3) {
+                            const int ag = S.order[k];
+                            const int ori = S.ori[ag];
+                            const int d0 = (ori == 1) - (ori == 3), d1 = (ori == 2) - (ori == 0);
+                            int r = static_cast<int>(S.pos[ag] >> 8) + d0, c = static_cast<int>(S.pos[ag] & 255) + d1;
+                            if (al == 1) { r += -d1 - d0; c += d0 - d1; }
+                            if (al == 2) { r -= -d1 + d0; c -= d0 + d1; }
+                            const int n = S.raylen[k * 3 + al], dp = d0 * a.Ws + d1;
+                            int p = r * a.Ws + c;
+                            for (int i = 0; i < n; ++i) { g[p] = static_cast<uint8_t>(ch); p += dp; }
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+            uint2* s_view = reinterpret_cast<uint2*>(wbase + a.L.w_view);
+            for (int i = lane; i < EPW * N; i += 32) s_view[i] = view_param(a, envs[i / N], a.pad_bytes + (i / N) * tile_pitch, i % N);
+            __syncwarp();
+            uint8_t* dst = a.obs + static_cast<size_t>(we) * a.obs_env;
+            const bool all_active = (nvalid == EPW) && (a.mask == nullptr);
+            if constexpr (VT > 0) {
+                if (all_active) render_rows<VT>(s_view, tiles, s_color, reinterpret_cast<uint32_t*>(wbase + a.L.w_stage), dst, EPW * N * VT);
+                else render_generic(a, envs, s_view, tiles, s_color, dst, nvalid);
+            } else {
+                render_generic(a, envs, s_view, tiles, s_color, dst, nvalid);
+            }
         }
     }
-    if (tid < SSD_NUM_STATS && s_stats[tid] != 0 && a.stats != nullptr)
-        atomicAdd(&a.stats[tid], static_cast<unsigned long long>(s_stats[tid]));
+
+    // ---- stats: warp -> CTA -> one set of global atomics per CTA (issued by the last warp to finish)
+    if (a.stats != nullptr) {
+        const int v[7] = {cnt.steps, cnt.eaten, cnt.fires, cnt.hits, cnt.cleaned, cnt.apples, cnt.waste};
+        const int slot[7] = {0, 2, 3, 4, 5, 6, 7};
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+            const int tot = __reduce_add_sync(0xffffffffu, v[i]);
+            if (lane == 0 && tot) atomicAdd(&s_cta_stats[slot[i]], tot);
+        }
+        __syncwarp();
+        int last = 0;
+        if (lane == 0) { __threadfence_block(); last = (atomicAdd(&s_done, 1) == nwarps - 1); }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last && lane < SSD_NUM_STATS) {
+            const int tot = *reinterpret_cast<volatile int*>(&s_cta_stats[lane]);
+            if (tot) atomicAdd(&a.stats[lane], static_cast<unsigned long long>(tot));
+        }
+    }
 }
 
 // ====================================================================== reset: setup_agents + reset_map
@@ -713,24 +730,52 @@ __global__ void __launch_bounds__(128) ssd_reset_kernel(const ResetArgs a) {
 }
 
 // ====================================================================== state pack / unpack, selftest
-__global__ void pack_state_kernel(int B, int N, int H, int W, int Ws, const uint8_t* grid_in, const int16_t* pos_in,
+__device__ __forceinline__ uint8_t dev_ascii_to_cell(uint8_t ch) {
+    switch (ch) {
+        case '0': return CB(C_PAD);
+        case ' ': return CB(C_EMPTY);
+        case '@': return CB(C_WALL);
+        case 'A': return CB(C_APPLE);
+        case 'H': return CB(C_WASTE);
+        case 'R': return CB(C_RIVER);
+        case 'S': return CB(C_STREAM);
+        case 'F': return CB(C_FIRE);
+        case 'C': return CB(C_CLEAN);
+        default: return (ch >= '1' && ch <= '9') ? CB(static_cast<uint8_t>(C_AGENT + ch - '1')) : CB(C_OTHER);
+    }
+}
+__device__ __forceinline__ uint8_t dev_cell_to_ascii(uint8_t cell) {
+    const uint8_t code = (cell & 0x7F) >> 2;
+    switch (code) {
+        case C_PAD: return '0';
+        case C_EMPTY: return ' ';
+        case C_WALL: return '@';
+        case C_APPLE: return 'A';
+        case C_WASTE: return 'H';
+        case C_RIVER: return 'R';
+        case C_STREAM: return 'S';
+        case C_FIRE: return 'F';
+        case C_CLEAN: return 'C';
+        default: return (code >= C_AGENT && code < C_AGENT + 9) ? static_cast<uint8_t>('1' + code - C_AGENT) : static_cast<uint8_t>('?');
+    }
+}
+__global__ void pack_state_kernel(int B, int N, int H, int W, int Ws, int env_bytes, const uint8_t* grid_in, const int16_t* pos_in,
                                   const uint8_t* ori_in, uint8_t* grid, uint32_t* agents) {
     const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    const size_t env_bytes = static_cast<size_t>(H) * Ws;
     if (i < static_cast<size_t>(B) * env_bytes) {
         const size_t b = i / env_bytes, q = i % env_bytes, r = q / Ws, c = q % Ws;
-        grid[i] = c < static_cast<size_t>(W) ? grid_in[(b * H + r) * W + c] : 0;
+        grid[i] = (r < static_cast<size_t>(H) && c < static_cast<size_t>(W)) ? dev_ascii_to_cell(grid_in[(b * H + r) * W + c]) : 0;
     }
     if (i < static_cast<size_t>(B) * N)
         agents[i] = (pos_in[2 * i] & 255) | (pos_in[2 * i + 1] & 255) << 8 | static_cast<uint32_t>(ori_in[i] & 3) << 16;
 }
-__global__ void unpack_state_kernel(int B, int N, int H, int W, int Ws, const uint8_t* grid, const uint32_t* agents,
+__global__ void unpack_state_kernel(int B, int N, int H, int W, int Ws, int env_bytes, const uint8_t* grid, const uint32_t* agents,
                                     uint8_t* grid_out, int16_t* pos_out, uint8_t* ori_out) {
     const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     const size_t HW = static_cast<size_t>(H) * W;
     if (grid_out != nullptr && i < static_cast<size_t>(B) * HW) {
         const size_t b = i / HW, q = i % HW, r = q / W, c = q % W;
-        grid_out[i] = grid[(b * H + r) * Ws + c];
+        grid_out[i] = dev_cell_to_ascii(grid[b * env_bytes + r * Ws + c]);
     }
     if (i < static_cast<size_t>(B) * N) {
         const uint32_t w = agents[i];
@@ -746,7 +791,8 @@ __global__ void philox_selftest_kernel(const uint32_t* ck, uint32_t* out) {
 // ====================================================================== launchers
 template <int KIND, bool TAPE>
 static cudaError_t launch_v(const StepArgs& a, int threads, cudaStream_t stream, bool fast_rows) {
-    const int ctas = (a.env_end - a.env_begin + a.E - 1) / a.E;
+    const int envs_per_cta = (threads / 32) * (32 / a.G);
+    const int ctas = (a.env_end - a.env_begin + envs_per_cta - 1) / envs_per_cta;
     if (ctas <= 0) return cudaSuccess;
     const int vt = fast_rows ? a.V : 0;
 #define SSD_LAUNCH(VT_)                                                                                         \
@@ -771,8 +817,8 @@ static cudaError_t launch_v(const StepArgs& a, int threads, cudaStream_t stream,
 }
 
 cudaError_t launch_step(const StepArgs& a, int threads, cudaStream_t stream) {
-    // the packed row renderer needs word-aligned slabs: E % 4 == 0 and a 4-byte aligned obs base
-    const bool fast_rows = (a.E % 4 == 0) && (reinterpret_cast<uintptr_t>(a.obs) % 4 == 0);
+    // the packed row renderer needs every warp's slab of 32/G envs to start 4-byte aligned
+    const bool fast_rows = (((32 / a.G) * a.obs_env) % 4 == 0) && (reinterpret_cast<uintptr_t>(a.obs) % 4 == 0);
     const bool tape = a.tape_u != nullptr || a.tape_move != nullptr;
     switch (a.kind) {
         case SSD_KIND_HARVEST:
@@ -793,17 +839,17 @@ cudaError_t launch_reset(const ResetArgs& a, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
-cudaError_t launch_pack_state(int B, int N, int H, int W, int Ws, const uint8_t* grid_in, const int16_t* pos_in,
+cudaError_t launch_pack_state(int B, int N, int H, int W, int Ws, int env_bytes, const uint8_t* grid_in, const int16_t* pos_in,
                               const uint8_t* ori_in, uint8_t* grid, uint32_t* agents, cudaStream_t stream) {
-    const size_t n = static_cast<size_t>(B) * H * Ws;
-    pack_state_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(B, N, H, W, Ws, grid_in, pos_in, ori_in, grid, agents);
+    const size_t n = static_cast<size_t>(B) * env_bytes;
+    pack_state_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(B, N, H, W, Ws, env_bytes, grid_in, pos_in, ori_in, grid, agents);
     return cudaGetLastError();
 }
-cudaError_t launch_unpack_state(int B, int N, int H, int W, int Ws, const uint8_t* grid, const uint32_t* agents,
+cudaError_t launch_unpack_state(int B, int N, int H, int W, int Ws, int env_bytes, const uint8_t* grid, const uint32_t* agents,
                                 uint8_t* grid_out, int16_t* pos_out, uint8_t* ori_out, cudaStream_t stream) {
     const size_t hw = static_cast<size_t>(H) * W;
     const size_t n = static_cast<size_t>(B) * (hw > static_cast<size_t>(N) ? hw : N);
-    unpack_state_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(B, N, H, W, Ws, grid, agents, grid_out, pos_out, ori_out);
+    unpack_state_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(B, N, H, W, Ws, env_bytes, grid, agents, grid_out, pos_out, ori_out);
     return cudaGetLastError();
 }
 cudaError_t launch_philox_selftest(const uint32_t* ctr_key, uint32_t* out, cudaStream_t stream) {
