@@ -90,6 +90,8 @@ typedef struct SsdTape {
     const double* uniforms;      /* [B][u_stride] np.random.rand(1)[0] in call order (harvest.py:101, cleanup.py:139,150) */
     int32_t u_stride;
     const uint16_t* waste_order; /* [B][num_waste_points] cell ids (row*W+col) after random.shuffle (cleanup.py:145); may be NULL for non-Cleanup */
+    int32_t* n_draws_out;        /* [B] or NULL: number of uniforms the spawn pass consumed, so a caller that feeds
+                                    np.random.rand values can advance its generator by exactly that many draws */
 } SsdTape;
 
 const char* ssd_last_error(void);
@@ -139,6 +141,12 @@ int ssd_step(ssd_handle h, const int8_t* actions, const uint8_t* action_order, c
  * advances when `phases` contains SSD_PHASE_SPAWN. */
 int ssd_step_phases(ssd_handle h, int phases, const int8_t* actions, const uint8_t* action_order,
                     const SsdTape* tape, uint8_t* obs_out, int32_t* reward_out, void* stream);
+
+/* Beam cells of the last SSD_PHASE_BEAMS call that did not render (phase-split stepping), for
+ * MapEnv.beam_pos / test_map (map_env.py:169,275-276,648).  out dev-or-host u8[B][64]:
+ * bytes 0..47 = painted cells of ray s of the k-th action-dict entry at [k*3+s], bytes 48..63 = beam
+ * character of entry k (0 none, 'F', 'C').  Synchronises `stream` when `out` is host memory. */
+int ssd_get_beams(ssd_handle h, uint8_t* out, void* stream);
 
 /* Observations of the current state without beams: rotate != 0 as step renders them
  * (map_env.py:197-198), 0 as reset does (map_env.py:239).  Backs Agent.get_state /

@@ -3,21 +3,21 @@ library is missing the import of this module raises."""
 import ctypes as C
 import os
 
+from ._names import STAT_NAMES  # noqa: F401
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libssd_b200.so")
 
 ABI_VERSION = 1
 MAX_AGENTS = 16
 NUM_STATS = 8
-STAT_NAMES = ("env_steps", "reward_sum", "apples_eaten", "fires", "hits", "cleaned",
-              "apples_spawned", "waste_spawned")
 PHASE_MOVES, PHASE_CONSUME, PHASE_BEAMS, PHASE_SPAWN, PHASE_RENDER, PHASE_ALL = 1, 2, 4, 8, 16, 31
 
 # every symbol include/ssd_b200.h declares (tests/test_cabi.py checks the list against the header)
 SYMBOLS = ("ssd_last_error", "ssd_abi_version", "ssd_create", "ssd_destroy", "ssd_num_apple_points",
            "ssd_num_waste_points", "ssd_obs_bytes_per_env", "ssd_envs_per_cta",
            "ssd_algorithmic_bytes_per_env_step", "ssd_seed", "ssd_get_counter", "ssd_set_state",
-           "ssd_get_state", "ssd_reset", "ssd_step", "ssd_step_phases", "ssd_render", "ssd_step_host",
+           "ssd_get_state", "ssd_reset", "ssd_step", "ssd_step_phases", "ssd_get_beams", "ssd_render", "ssd_step_host",
            "ssd_stats", "ssd_launch_count", "ssd_philox_selftest")
 
 
@@ -34,7 +34,7 @@ class SsdConfig(C.Structure):
 
 class SsdTape(C.Structure):
     _fields_ = [("move_order", C.c_void_p), ("uniforms", C.c_void_p), ("u_stride", C.c_int32),
-                ("waste_order", C.c_void_p)]
+                ("waste_order", C.c_void_p), ("n_draws_out", C.c_void_p)]
 
 
 class SsdError(RuntimeError):
@@ -69,6 +69,7 @@ def _load():
         "ssd_reset": (i32, [vp, vp, vp, vp]),
         "ssd_step": (i32, [vp, vp, vp, C.POINTER(SsdTape), vp, vp, vp]),
         "ssd_step_phases": (i32, [vp, i32, vp, vp, C.POINTER(SsdTape), vp, vp, vp]),
+        "ssd_get_beams": (i32, [vp, vp, vp]),
         "ssd_render": (i32, [vp, i32, vp, vp]),
         "ssd_step_host": (i32, [vp, vp, vp, vp]),
         "ssd_stats": (i32, [vp, vp, vp]),

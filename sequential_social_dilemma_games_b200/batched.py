@@ -131,9 +131,13 @@ class BatchedSSDEnv(object):
                     wo = torch.from_numpy(np.ascontiguousarray(wo, dtype=np.uint16).view(np.int16))
                 wo = wo.to(self.device).contiguous()
                 assert wo.element_size() == 2 and tuple(wo.shape) == (B, len(self.cfg.waste_points))
-            keep = (mo, u, wo)
+            nd = tape.get("n_draws_out")
+            if nd is not None:
+                assert nd.dtype == torch.int32 and nd.is_contiguous() and tuple(nd.shape) == (B,) and nd.is_cuda
+            keep = (mo, u, wo, nd)
             tp = _lib.SsdTape(move_order=mo.data_ptr(), uniforms=u.data_ptr(), u_stride=u.shape[1],
-                              waste_order=wo.data_ptr() if wo is not None else None)
+                              waste_order=wo.data_ptr() if wo is not None else None,
+                              n_draws_out=nd.data_ptr() if nd is not None else None)
         tpp = C.byref(tp) if tp is not None else None
         if phases is None:
             _lib.check(_lib.lib.ssd_step(self._h, _ptr(a), _ptr(o), tpp, _ptr(obs), _ptr(reward_out), self._stream()))
@@ -180,6 +184,12 @@ class BatchedSSDEnv(object):
         o = self._as(ori, torch.uint8, (B, N))
         _lib.check(_lib.lib.ssd_set_state(self._h, _ptr(g), _ptr(p), _ptr(o), self._stream()))
         torch.cuda.current_stream(self.device).synchronize()  # g/p/o may be temporaries
+
+    def get_beams(self):
+        """uint8 [B, 64]: ray lengths and beam characters of the last phase-split BEAMS call (ssd_get_beams)."""
+        out = np.zeros((self.num_envs, 64), dtype=np.uint8)
+        _lib.check(_lib.lib.ssd_get_beams(self._h, out.ctypes.data, self._stream()))
+        return out
 
     def stats(self):
         out = np.zeros(_lib.NUM_STATS, dtype=np.int64)

@@ -396,7 +396,7 @@ int ssd_step_phases(ssd_handle h, int phases, const int8_t* actions, const uint8
     a.use_beam_buf = phases != SSD_PHASE_ALL;
     a.rew_accumulate = phases != SSD_PHASE_ALL;
     a.actions = actions; a.order = action_order; a.obs = obs_out; a.rew = reward_out;
-    if (tape) { a.tape_move = tape->move_order; a.tape_u = tape->uniforms; a.u_stride = tape->u_stride; a.tape_waste = tape->waste_order; }
+    if (tape) { a.tape_move = tape->move_order; a.tape_u = tape->uniforms; a.u_stride = tape->u_stride; a.tape_waste = tape->waste_order; a.n_draws_out = tape->n_draws_out; }
     CUDA_TRY(ssd::launch_step(a, h->threads, static_cast<cudaStream_t>(stream)));
     h->launches++;
     if (phases & SSD_PHASE_SPAWN) h->t++;
@@ -406,6 +406,22 @@ int ssd_step_phases(ssd_handle h, int phases, const int8_t* actions, const uint8
 int ssd_step(ssd_handle h, const int8_t* actions, const uint8_t* action_order, const SsdTape* tape, uint8_t* obs_out,
              int32_t* reward_out, void* stream) {
     return ssd_step_phases(h, SSD_PHASE_ALL, actions, action_order, tape, obs_out, reward_out, stream);
+}
+
+int ssd_get_beams(ssd_handle h, uint8_t* out, void* stream) {
+    if (check_handle(h) || !out) return SSD_ERR_INVALID;
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    std::vector<uint8_t> tmp(static_cast<size_t>(h->B) * 64);
+    CUDA_TRY(cudaMemcpyAsync(tmp.data(), h->d_beam_buf, tmp.size(), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (int b = 0; b < h->B; ++b)  // device cell bytes -> the reference's beam characters
+        for (int k = 48; k < 64; ++k) {
+            uint8_t& c = tmp[static_cast<size_t>(b) * 64 + k];
+            c = c == ssd::CB(ssd::C_FIRE) ? 'F' : (c == ssd::CB(ssd::C_CLEAN) ? 'C' : 0);
+        }
+    CUDA_TRY(cudaMemcpy(out, tmp.data(), tmp.size(), cudaMemcpyDefault));
+    return SSD_OK;
 }
 
 int ssd_render(ssd_handle h, int rotate, uint8_t* obs_out, void* stream) {

@@ -105,7 +105,7 @@ struct StepArgs {
     uint8_t* beam_buf;    // [B_pad][64] raylen + firech between phase-split calls
     // ---- I/O (device)
     const int8_t* actions; const uint8_t* order; const uint8_t* mask;
-    const uint8_t* tape_move; const double* tape_u; int u_stride; const uint16_t* tape_waste;
+    const uint8_t* tape_move; const double* tape_u; int u_stride; const uint16_t* tape_waste; int32_t* n_draws_out;
     uint8_t* obs; int32_t* rew;
     unsigned long long* stats;
 };

@@ -242,6 +242,7 @@ __device__ __forceinline__ void harvest_spawn(const StepArgs& a, uint8_t* g, con
         base += __popc(m);
     }
     const int n_draw = base;  // k-th eligible point consumes the k-th np.random.rand (harvest.py:101)
+    if (TAPE && a.n_draws_out != nullptr && lane == 0) a.n_draws_out[local_env] = n_draw;
     __syncwarp();
     for (int j0 = 0; j0 < n_draw; j0 += 32) {
         const int j = j0 + lane;
@@ -302,6 +303,7 @@ __device__ __forceinline__ void cleanup_spawn(const StepArgs& a, uint8_t* g, con
         base += __popc(m);
     }
 
+    if (TAPE && a.n_draws_out != nullptr && lane == 0) a.n_draws_out[local_env] = base;  // apple pass; the waste pass adds its own
     if (waste_p != 0.0 && n_waste > 0) {  // `not np.isclose(p, 0)`: p is 0 or wasteSpawnProbability (cleanup.py:144)
         if (TAPE) {
             const uint16_t* wo = a.tape_waste + static_cast<size_t>(local_env) * n_waste;  // order after random.shuffle (:145)
@@ -320,10 +322,12 @@ __device__ __forceinline__ void cleanup_spawn(const StepArgs& a, uint8_t* g, con
                 const uint32_t s = __ballot_sync(0xffffffffu, ok);
                 if (s) {  // first success spawns and breaks (:151-153); waste may appear under an agent
                     if (lane == __ffs(s) - 1) { g[idx] = CB(C_WASTE) | (g[idx] & kFlag); ++cnt.waste; }
+                    base += __popc(m & ((2u << (__ffs(s) - 1)) - 1u));  // draws up to and including the winner
                     break;
                 }
                 base += __popc(m);
             }
+            if (a.n_draws_out != nullptr && lane == 0) a.n_draws_out[local_env] = base;
         } else {
             // random.shuffle replacement: canonical waste points ordered by (32-bit key, index).
             int n_el = 0;

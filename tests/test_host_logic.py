@@ -1,0 +1,112 @@
+"""Host logic without a GPU: boards, derived point lists, Cleanup probability table, the sharding
+plan, and the world_size-2 stats reduction over gloo (the N>1 path's only collective)."""
+import hashlib
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_boards_are_the_reference_boards():
+    """SURVEY.md section 0 item 3 (probed on the reference): shapes and point counts; the SHA-256
+    values were taken from social_dilemmas/constants.py when the boards were encoded."""
+    from sequential_social_dilemma_games_b200.maps import CLEANUP_MAP, HARVEST_MAP, tile_map
+    assert (len(HARVEST_MAP), len(HARVEST_MAP[0])) == (16, 38)
+    assert (len(CLEANUP_MAP), len(CLEANUP_MAP[0])) == (25, 18)
+    hm, cm = "".join(HARVEST_MAP), "".join(CLEANUP_MAP)
+    assert (hm.count('A'), hm.count('P'), hm.count('@')) == (155, 20, 104)
+    assert (cm.count('B'), cm.count('H'), cm.count('R'), cm.count('S'), cm.count('@'), cm.count('P')) == (103, 56, 63, 12, 82, 10)
+    assert hashlib.sha256("\n".join(HARVEST_MAP).encode()).hexdigest() == "e741b7be22f6ec1093f5250b916f59855017dee6102362be91dc3b3655fd0ce4"
+    assert hashlib.sha256("\n".join(CLEANUP_MAP).encode()).hexdigest() == "63ae0acace3b26ddd6aa13df7372e1089c5db2fd66db27f8ec157dca380c39e9"
+    t = tile_map(CLEANUP_MAP)  # BASELINE.json config 4
+    assert (len(t), len(t[0])) == (50, 36) and "".join(t).count('B') == 412 and "".join(t).count('P') == 40
+
+
+def test_config_tables():
+    from sequential_social_dilemma_games_b200.config import (EnvConfig, KIND_CLEANUP, KIND_HARVEST, cleanup_probabilities)
+    from sequential_social_dilemma_games_b200.maps import CLEANUP_MAP, HARVEST_MAP
+    h = EnvConfig(KIND_HARVEST, HARVEST_MAP, 5)
+    assert h.obs_shape == (5, 15, 15, 3) and h.num_actions == 8 and len(h.apple_points) == 155
+    assert [tuple(p) for p in h.apple_points[:3]] == [(1, 13), (1, 20), (1, 21)]   # row-major = RNG consumption order
+    assert len(h.spawn_points) == 20
+    c = EnvConfig(KIND_CLEANUP, CLEANUP_MAP, 5)
+    assert c.potential_waste_area == 119 and c.num_actions == 9      # tests/test_envs.py:1009
+    assert len(c.spawn_points) == 20                                 # every 'P' twice (cleanup.py:51-52)
+    # cleanup.py:156-171 on the default board: no spawning at the initial 56 'H'; h = 47 is the first
+    # count below the depletion threshold
+    assert c.cleanup_apple_prob[56] == 0 and c.cleanup_waste_prob[56] == 0
+    assert c.cleanup_waste_prob[48] == 0 and c.cleanup_waste_prob[47] == 0.5
+    assert c.cleanup_apple_prob[0] == 0.05 and 0 < c.cleanup_apple_prob[47] < 0.001
+    # the reference's own expectations (tests/test_envs.py:1149-1182): 0 / 0.5 / 0.025
+    assert cleanup_probabilities(2, 4) == (0, 0)
+    apple, waste = cleanup_probabilities(1, 5)   # density 0.2 -> half of the apple probability
+    assert waste == 0.5 and abs(apple - 0.025) < 1e-15
+    assert h.colour_lut[ord('A')].tolist() == [0, 255, 0] and c.colour_lut[ord('H')].tolist() == [99, 156, 194]
+    g = c.initial_grid()
+    assert (g == ord('H')).sum() == 56 and (g == ord('B')).sum() == 0 and (g == ord('P')).sum() == 0
+    with pytest.raises(ValueError):
+        EnvConfig(KIND_HARVEST, ["@@@", "@ @@", "@@@"], 1)   # ragged board
+    with pytest.raises(ValueError):
+        EnvConfig(KIND_HARVEST, HARVEST_MAP, 17)
+
+
+def test_shard_plan():
+    from sequential_social_dilemma_games_b200.sharding import shard_range, weak_range
+    for total, world in ((65536, 8), (65536, 1), (10, 4), (3, 8), (0, 2), (1000003, 7)):
+        spans = [shard_range(total, world, r) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == total
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))       # contiguous, disjoint, ordered
+        sizes = [e - b for b, e in spans]
+        assert max(sizes) - min(sizes) <= 1
+    assert weak_range(65536, 3) == (3 * 65536, 4 * 65536)
+    with pytest.raises(ValueError):
+        shard_range(8, 2, 2)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from sequential_social_dilemma_games_b200._names import STAT_NAMES
+    from sequential_social_dilemma_games_b200.sharding import max_over_ranks, reduce_stats, shard_range
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    begin, end = shard_range(1001, world, rank)
+    local = {k: 0 for k in STAT_NAMES}
+    local["env_steps"] = (end - begin) * 10
+    local["apples_eaten"] = sum(range(begin, end))   # any per-env quantity: the sum must not depend on the cut
+    local["reward_sum"] = -begin
+    tot = reduce_stats(local)
+    slow = max_over_ranks(1.0 + rank)
+    dist.barrier()
+    dist.destroy_process_group()
+    q.put((rank, tot, slow, (begin, end)))
+
+
+def test_two_rank_stats_reduction_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, t0, s0, span0), (r1, t1, s1, span1) = res
+    assert t0 == t1 and s0 == s1 == 2.0
+    assert span0 == (0, 501) and span1 == (501, 1001)
+    assert t0["env_steps"] == 10010 and t0["apples_eaten"] == sum(range(1001)) and t0["reward_sum"] == -501
