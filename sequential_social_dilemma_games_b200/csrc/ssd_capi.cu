@@ -99,6 +99,7 @@ ssd::SmemLayout make_layout(const SsdEnv& h, int threads) {
     L.w_list = w; w += up16(std::max(h.n_apple * 2, h.n_waste * 4));
     L.w_view = w; w += up16(epw * h.cfg.num_agents * 8);
     L.w_stage = w; w += up16(32u * 3u * h.V) + 16;
+    if (const char* x = getenv("SSD_EXTRA_SMEM")) w += up16(static_cast<uint32_t>(atoi(x)));  // occupancy experiments
     L.warp_stride = w;
     L.total = off + (threads / 32) * w;
     return L;
