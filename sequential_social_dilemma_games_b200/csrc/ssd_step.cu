@@ -16,6 +16,7 @@
 //
 // Reference citations are relative to the reference root (social_dilemmas/envs/...).
 #include <cstdio>
+#include <cstdlib>
 
 #include "ssd_device.cuh"
 #include "ssd_internal.h"
@@ -697,6 +698,300 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_kernel(const __grid_cons
     }
 }
 
+// ====================================================================== the fast path of a full step
+// Same algorithm as ssd_step_kernel, specialised for what a production step is: all phases, every env
+// stepped (no mask), actions in agent order, N <= 8 (8 lanes per env, 4 envs per warp), a packed
+// row renderer for this view size and only whole warps (the launcher sends any tail envs through the
+// general kernel).  What the specialisation buys: no per-env / per-phase flag tests, fire flags from
+// one ballot, view geometry straight from the agent registers, and observation rows that leave
+// shared memory as TMA bulk stores instead of LDS.128 / STG.128 pairs.
+
+// Packed rows with TMA copy-out.  As render_rows, but every chunk of 32 rows (32 * 3V bytes, a multiple
+// of 16) is written by ONE cp.async.bulk from the staging buffer.  The warp's slab starts at `dst`
+// = 16-byte aligned base + mis; the buffer holds the aligned image [base + c*CH, base + (c+1)*CH) of
+// chunk c: the mis/4 words that spill over the end of a chunk are kept in registers by lane 31
+// (they are its last words) and stored at the head of the next chunk's image.  Only the first
+// 16 - mis and the last mis bytes of the slab are written with plain 4-byte stores.
+__host__ __device__ constexpr int row_words(int o, int RB) { return ((o + RB - 1) >> 2) - ((o + 3) >> 2) + 1; }
+__host__ __device__ constexpr int row_words_min(int RB) {
+    int m = row_words(0, RB);
+    for (int r = 1; r < 4; ++r) m = row_words(r, RB) < m ? row_words(r, RB) : m;
+    return m;
+}
+
+template <int VT>
+__device__ __forceinline__ void render_rows_tma(const uint2* s_view, const uint8_t* tiles, const uint32_t* s_color,
+                                                uint32_t* stage, uint8_t* dst, int total_rows) {
+    constexpr int RB = 3 * VT;            // bytes per view row
+    constexpr int CH = 32 * RB;           // bytes per chunk
+    constexpr int NP = (RB + 3 + 3) / 4;  // words covering the row plus the next row's first pixel
+    constexpr int O31 = 31 * RB, M31 = ((O31 + RB - 1) >> 2) - ((O31 + 3) >> 2) + 1;  // lane 31 owns the chunk's last words
+    constexpr int MMIN = row_words_min(RB);  // every lane owns at least this many words of a chunk
+    static_assert(M31 >= 3 && M31 <= NP, "carry words must all live in lane 31");
+    const int lane = threadIdx.x & 31;
+    const int mis = static_cast<int>(reinterpret_cast<uintptr_t>(dst) & 15);  // multiple of 4
+    const int mis4 = mis >> 2;
+    const uint32_t o = static_cast<uint32_t>(lane) * RB;
+    const uint32_t d8 = 8u * ((4u - (o & 3u)) & 3u);
+    const uint32_t w0 = (o + 3) >> 2, w1 = (o + RB - 1) >> 2;
+    const int M = static_cast<int>(w1 - w0) + 1;  // NP - 1 or NP - 2 ... per-lane constant
+    uint32_t* st = stage + mis4 + w0;
+    uint8_t* const base = dst - mis;
+    uint32_t c0 = 0, c1 = 0, c2 = 0;
+    for (int row0 = 0; row0 < total_rows; row0 += 32) {
+        const int R = min(row0 + lane, total_rows - 1);  // lanes past the end redo the last row; their words are never copied out
+        const int ga = R / VT, i = R - ga * VT;           // rows are ordered (env, agent, i)
+        uint32_t X[VT + 2];
+        {
+            const uint2 vp = s_view[ga];
+            const int si = static_cast<int16_t>(vp.y & 0xffffu), sj = static_cast<int32_t>(vp.y) >> 16;
+            const uint8_t* g = tiles + static_cast<int32_t>(vp.x) + i * si;
+#pragma unroll
+            for (int j = 0; j < VT; ++j) X[j] = cell_color(s_color, g[j * sj]);
+        }
+        X[VT] = __shfl_down_sync(0xffffffffu, X[0], 1);
+        X[VT + 1] = 0;
+        uint32_t P[NP + 1];
+#pragma unroll
+        for (int w = 0; w < NP; ++w) {
+            const int p = (4 * w) / 3, ph = (4 * w) % 3;
+            P[w] = __byte_perm(X[p], X[p + 1], ph == 0 ? 0x4210u : (ph == 1 ? 0x5421u : 0x6542u));
+        }
+        P[NP] = 0;
+        uint32_t Q[NP];
+#pragma unroll
+        for (int m = 0; m < NP; ++m) Q[m] = __funnelshift_r(P[m], P[m + 1], d8);
+        // the previous chunk's bulk store must have finished READING the buffer
+        if (row0 != 0) {
+            if (lane == 0) bulk_wait_read();
+            __syncwarp();
+        }
+#pragma unroll
+        for (int m = 0; m < NP; ++m)
+            if (m < MMIN || m < M) st[m] = Q[m];
+        if (lane == 31 && row0 != 0) {  // head of this chunk's image = the words that spilled over the previous chunk
+            if (mis4 >= 1) stage[mis4 - 1] = c2;
+            if (mis4 >= 2) stage[mis4 - 2] = c1;
+            if (mis4 >= 3) stage[mis4 - 3] = c0;
+        }
+        c0 = Q[M31 - 3]; c1 = Q[M31 - 2]; c2 = Q[M31 - 1];
+        fence_async_smem();
+        __syncwarp();
+        const int nbytes = min(32, total_rows - row0) * RB;  // multiple of 4 (the launcher checks the slab size)
+        const int end = mis + nbytes;                         // valid image bytes: [row0 ? 0 : mis, end)
+        const int lo = (row0 == 0 && mis != 0) ? 16 : 0;
+        const int hi = min(CH, end & ~15);
+        uint8_t* out = base + static_cast<size_t>(row0) * RB;
+        if (lane == 0 && hi > lo) {
+            bulk_s2g(out + lo, reinterpret_cast<const uint8_t*>(stage) + lo, static_cast<uint32_t>(hi - lo));
+            bulk_commit();
+        }
+        if (row0 == 0 && lane >= mis4 && lane < 4 && mis != 0)  // first bytes of the slab
+            *reinterpret_cast<uint32_t*>(out + 4 * lane) = stage[lane];
+        if (row0 + 32 >= total_rows) {                          // last bytes of the slab
+            const int off = hi + 4 * lane;
+            if (off < end) *reinterpret_cast<uint32_t*>(out + off) = stage[off >> 2];
+        }
+    }
+    if (lane == 0) bulk_wait_read();  // shared memory must outlive the last bulk read
+}
+
+template <int KIND, bool TAPE, int VT>
+__global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid_constant__ StepArgs a) {
+    constexpr int G = 8, EPW = 4;
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint32_t s_color[kNumCodes];
+    __shared__ int s_cta_stats[SSD_NUM_STATS];
+    __shared__ int s_done;
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
+    const int N = a.N;
+    uint16_t* s_apple = reinterpret_cast<uint16_t*>(smem + a.L.apple);
+
+    if (tid < kNumCodes) s_color[tid] = a.color[tid];
+    if (tid < SSD_NUM_STATS) s_cta_stats[tid] = 0;
+    if (tid == 0) s_done = 0;
+    if (KIND != SSD_KIND_PLAIN)
+#pragma unroll 1
+        for (int i = tid; i < a.n_apple; i += nthr) s_apple[i] = a.apple_cell[i];
+    __syncthreads();
+
+    uint8_t* wbase = smem + a.L.warp0 + warp * a.L.warp_stride;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(wbase + a.L.w_mbar);
+    uint8_t* tiles = wbase + a.L.w_tiles;
+    EnvScratch* envs = reinterpret_cast<EnvScratch*>(wbase + a.L.w_env);
+    const int tile_pitch = a.env_bytes + a.pad_bytes;
+    const int we = a.env_begin + (blockIdx.x * nwarps + warp) * EPW;  // the launcher only sends whole warps
+    Counters cnt = {0, 0, 0, 0, 0, 0, 0};
+
+    if (we < a.env_end) {
+        // ---- load: one TMA bulk copy per env tile; zero the frames while they are in flight
+        if (lane == 0) { mbar_init(mbar, 1); mbar_expect_tx(mbar, static_cast<uint32_t>(EPW) * a.env_bytes); }
+        __syncwarp();
+        if (lane < EPW)
+            bulk_g2s(tiles + a.pad_bytes + lane * tile_pitch, a.grid + static_cast<size_t>(we + lane) * a.env_bytes, a.env_bytes, mbar);
+        {
+            const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int q = 0; q <= EPW; ++q)
+#pragma unroll 1
+                for (int i = lane * 16; i < a.pad_bytes; i += 512) *reinterpret_cast<uint4*>(tiles + q * tile_pitch + i) = z;
+        }
+        // agent words and actions travel while the tiles do
+        const int al = lane & (G - 1), gbase = lane & ~(G - 1), j = lane >> 3;
+        EnvScratch& S = envs[j];
+        uint8_t* g = tiles + a.pad_bytes + j * tile_pitch;
+        const int e = we + j;
+        const bool valid = al < N;
+        const size_t gi = static_cast<size_t>(e) * N + (valid ? al : 0);
+        PhiloxKey pk;
+        pk.k0 = a.key0; pk.k1 = a.key1; pk.t = a.t;
+        pk.env = static_cast<uint32_t>(a.env_id0 + static_cast<uint64_t>(e));
+        AgentLane me;
+        me.key = 0x0101; me.ori = 0; me.act = -1; me.rew = 0;
+        if (valid) {
+            const uint32_t w = a.agents[gi];
+            me.act = a.actions[gi];
+            me.key = (w & 255) << 8 | ((w >> 8) & 255);
+            me.ori = (w >> 16) & 3;
+            S.order[al] = static_cast<uint8_t>(al);
+            S.rew[al] = 0;
+        }
+        mbar_wait(mbar, 0);  // tiles landed
+        __syncwarp();
+
+        // ---- phase A: one lane per agent
+        moves_group<TAPE>(a, S, g, me, valid, al, G, e, pk);
+        cnt.steps += (al == 0);
+        if (valid) S.pos[al] = static_cast<uint16_t>(me.key);
+        const int my_idx = tile_idx(a, me.key);
+        {   // consume, map_env.py:178-181: of agents sharing a cell (appendix A.2 quirk) the first in agent order eats
+            const bool on_apple = valid && g[my_idx] == CB(C_APPLE);
+            const uint32_t same = __match_any_sync(0xffffffffu, on_apple ? (me.key | static_cast<uint32_t>(gbase) << 16) : (0x80000000u | lane));
+            if (on_apple && (__ffs(same) - 1) == lane) { g[my_idx] = CB(C_EMPTY); me.rew += 1; ++cnt.eaten; }
+        }
+        __syncwarp();
+        if (KIND != SSD_KIND_PLAIN && valid) g[my_idx] |= kFlag;  // "an agent stands here"
+        __syncwarp();
+        uint32_t fmask = 0;  // bit (8 * env slot + agent): that agent fires
+        if (KIND != SSD_KIND_PLAIN) {  // update_custom_moves map_env.py:545-552, agents fire in action (= agent) order
+            fmask = __ballot_sync(0xffffffffu, me.act == 7 || (KIND == SSD_KIND_CLEANUP && me.act == 8));
+            for (int k = 0; k < N; ++k) {
+                if (!((fmask >> k) & 0x01010101u)) continue;  // nobody in this warp fires in slot k
+                const bool fire = (fmask >> (gbase + k)) & 1u;
+                const int act_k = __shfl_sync(0xffffffffu, me.act, k, G);
+                const uint32_t key_k = __shfl_sync(0xffffffffu, me.key, k, G);
+                const int ori_k = __shfl_sync(0xffffffffu, me.ori, k, G);
+                const bool clean = act_k == 8;
+                int upd = -1, hits = 0, n = 0;
+                if (fire && al < 3) n = ray_walk(a, S, g, key_k, ori_k, al, clean, upd, hits);
+                if (fire && al == k && !clean) { me.rew -= 1; ++cnt.fires; }  // fire_beam agent.py:170-172
+                __syncwarp();
+                if (fire && al < 3) {
+                    S.raylen[k * 3 + al] = static_cast<uint8_t>(n);
+                    if (upd >= 0) { g[upd] = CB(C_RIVER) | (g[upd] & kFlag); ++cnt.cleaned; }  // update_map :551-558, before the next agent fires
+                    cnt.hits += hits;
+                }
+                __syncwarp();
+            }
+        }
+        if (valid) {
+            me.rew += S.rew[al];  // -50 per hit taken
+            a.agents[gi] = (me.key >> 8) | (me.key & 255) << 8 | static_cast<uint32_t>(me.ori) << 16;
+            a.rew[gi] = me.rew;
+        }
+
+        // ---- phase B: the whole warp per env
+        if (KIND != SSD_KIND_PLAIN) {
+            void* scratch = wbase + a.L.w_list;
+#pragma unroll 1
+            for (int q = 0; q < EPW; ++q) {
+                pk.env = static_cast<uint32_t>(a.env_id0 + static_cast<uint64_t>(we + q));
+                if (KIND == SSD_KIND_HARVEST)
+                    harvest_spawn<TAPE>(a, tiles + a.pad_bytes + q * tile_pitch, s_apple, static_cast<uint16_t*>(scratch), we + q, pk, lane, cnt);
+                else
+                    cleanup_spawn<TAPE>(a, tiles + a.pad_bytes + q * tile_pitch, s_apple, static_cast<uint32_t*>(scratch), we + q, pk, lane, cnt);
+                __syncwarp();
+            }
+            if (valid) g[my_idx] &= 0x7F;  // agents sharing a cell all write the same byte
+            __syncwarp();
+        }
+
+        // ---- store: grid tiles back to HBM
+        {
+            const int n16 = a.env_bytes >> 4;
+#pragma unroll
+            for (int q = 0; q < EPW; ++q) {
+                uint4* gdst = reinterpret_cast<uint4*>(a.grid + static_cast<size_t>(we + q) * a.env_bytes);
+                const uint4* gsrc = reinterpret_cast<const uint4*>(tiles + a.pad_bytes + q * tile_pitch);
+#pragma unroll 1
+                for (int i = lane; i < n16; i += 32) gdst[i] = gsrc[i];
+            }
+        }
+        __syncwarp();  // the write-back above has read the tiles
+
+        // ---- phase C: overlay (get_map_with_agents map_env.py:280-302), view geometry, packed rows
+        {
+            const uint32_t same = __match_any_sync(0xffffffffu, valid ? (me.key | static_cast<uint32_t>(gbase) << 16) : (0x80000000u | lane));
+            if (valid && (31 - __clz(same)) == lane) g[my_idx] = agent_cell(al);  // the last agent on a cell wins
+            __syncwarp();
+            if (KIND != SSD_KIND_PLAIN) {  // beams in firing order: a later beam overwrites an earlier one
+                for (int k = 0; k < N; ++k) {
+                    if (!((fmask >> k) & 0x01010101u)) continue;
+                    const uint32_t key_k = __shfl_sync(0xffffffffu, me.key, k, G);
+                    const int ori_k = __shfl_sync(0xffffffffu, me.ori, k, G);
+                    const int act_k = __shfl_sync(0xffffffffu, me.act, k, G);
+                    if (((fmask >> (gbase + k)) & 1u) && al < 3) {
+                        const int d0 = (ori_k == 1) - (ori_k == 3), d1 = (ori_k == 2) - (ori_k == 0);
+                        int r = static_cast<int>(key_k >> 8) + d0, c = static_cast<int>(key_k & 255) + d1;
+                        if (al == 1) { r += -d1 - d0; c += d0 - d1; }
+                        if (al == 2) { r -= -d1 + d0; c -= d0 + d1; }
+                        const int n = S.raylen[k * 3 + al], dp = d0 * a.Ws + d1;
+                        const uint8_t ch = act_k == 8 ? CB(C_CLEAN) : CB(C_FIRE);
+                        int p = r * a.Ws + c;
+#pragma unroll 1
+                        for (int i = 0; i < n; ++i) { g[p] = ch; p += dp; }
+                    }
+                    __syncwarp();
+                }
+            }
+            uint2* s_view = reinterpret_cast<uint2*>(wbase + a.L.w_view);
+            if (valid) {  // rot90 folded into strides, see view_param
+                const int pr = me.key >> 8, pc = me.key & 255, r = a.r, Ws = a.Ws;
+                const int k = (4 - me.ori) & 3;
+                int a0, si, sj;
+                if (k == 0)      { a0 = (pr - r) * Ws + pc - r; si = Ws;  sj = 1; }
+                else if (k == 2) { a0 = (pr + r) * Ws + pc + r; si = -Ws; sj = -1; }
+                else if (k == 1) { a0 = (pr - r) * Ws + pc + r; si = -1;  sj = Ws; }
+                else             { a0 = (pr + r) * Ws + pc - r; si = 1;   sj = -Ws; }
+                s_view[j * N + al] = make_uint2(static_cast<uint32_t>(a0 + a.pad_bytes + j * tile_pitch),
+                                                (static_cast<uint32_t>(si) & 0xffffu) | static_cast<uint32_t>(sj) << 16);
+            }
+            __syncwarp();
+            render_rows_tma<VT>(s_view, tiles, s_color, reinterpret_cast<uint32_t*>(wbase + a.L.w_stage),
+                                a.obs + static_cast<size_t>(we) * a.obs_env, EPW * N * VT);
+        }
+    }
+
+    // ---- stats: warp -> CTA -> one set of global atomics per CTA (issued by the last warp to finish)
+    if (a.stats != nullptr) {
+        const int v[7] = {cnt.steps, cnt.eaten, cnt.fires, cnt.hits, cnt.cleaned, cnt.apples, cnt.waste};
+        const int slot[7] = {0, 2, 3, 4, 5, 6, 7};
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+            const int tot = __reduce_add_sync(0xffffffffu, v[i]);
+            if (lane == 0 && tot) atomicAdd(&s_cta_stats[slot[i]], tot);
+        }
+        __syncwarp();
+        int last = 0;
+        if (lane == 0) { __threadfence_block(); last = (atomicAdd(&s_done, 1) == nwarps - 1); }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last && lane < SSD_NUM_STATS) {
+            const int tot = *reinterpret_cast<volatile int*>(&s_cta_stats[lane]);
+            if (tot) atomicAdd(&a.stats[lane], static_cast<unsigned long long>(tot));
+        }
+    }
+}
+
 // ====================================================================== reset: setup_agents + reset_map
 // map_env.py:214-229: spawn_point (:651-662) with the shuffle replaced by a (key, index) order --
 // the reference takes the LAST free entry of the shuffled list = the free entry with the largest
@@ -820,9 +1115,32 @@ static cudaError_t launch_v(const StepArgs& a, int threads, cudaStream_t stream,
 #undef SSD_LAUNCH
 }
 
-cudaError_t launch_step(const StepArgs& a, int threads, cudaStream_t stream) {
-    // the packed row renderer needs every warp's slab of 32/G envs to start 4-byte aligned
-    const bool fast_rows = (((32 / a.G) * a.obs_env) % 4 == 0) && (reinterpret_cast<uintptr_t>(a.obs) % 4 == 0);
+template <int KIND, bool TAPE>
+static cudaError_t launch_fast(const StepArgs& a, int threads, cudaStream_t stream) {
+    const int envs_per_cta = (threads / 32) * 4;
+    const int ctas = (a.env_end - a.env_begin + envs_per_cta - 1) / envs_per_cta;
+    if (ctas <= 0) return cudaSuccess;
+#define SSD_LAUNCH_FAST(VT_)                                                                                    \
+    do {                                                                                                        \
+        auto kern = ssd_step_fast_kernel<KIND, TAPE, VT_>;                                                      \
+        static uint32_t smem_set = 0;                                                                           \
+        if (a.L.total > smem_set) {                                                                             \
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, a.L.total); \
+            if (e != cudaSuccess) return e;                                                                     \
+            smem_set = a.L.total;                                                                               \
+        }                                                                                                       \
+        kern<<<ctas, threads, a.L.total, stream>>>(a);                                                          \
+        return cudaGetLastError();                                                                              \
+    } while (0)
+    switch (a.V) {
+        case 11: SSD_LAUNCH_FAST(11);
+        case 15: SSD_LAUNCH_FAST(15);
+        default: SSD_LAUNCH_FAST(21);
+    }
+#undef SSD_LAUNCH_FAST
+}
+
+static cudaError_t launch_general(const StepArgs& a, int threads, cudaStream_t stream, bool fast_rows) {
     const bool tape = a.tape_u != nullptr || a.tape_move != nullptr;
     switch (a.kind) {
         case SSD_KIND_HARVEST:
@@ -835,6 +1153,36 @@ cudaError_t launch_step(const StepArgs& a, int threads, cudaStream_t stream) {
             return tape ? launch_v<SSD_KIND_PLAIN, true>(a, threads, stream, fast_rows)
                         : launch_v<SSD_KIND_PLAIN, false>(a, threads, stream, fast_rows);
     }
+}
+
+cudaError_t launch_step(const StepArgs& a, int threads, cudaStream_t stream) {
+    // the packed row renderers need every warp's slab of 32/G envs to start 4-byte aligned
+    const bool fast_rows = (((32 / a.G) * a.obs_env) % 4 == 0) && (reinterpret_cast<uintptr_t>(a.obs) % 4 == 0);
+    const bool tape = a.tape_u != nullptr || a.tape_move != nullptr;
+    // a production step: everything the specialised kernel assumes (see ssd_step_fast_kernel)
+    static const bool no_fast = getenv("SSD_NO_FAST") != nullptr;
+    const bool full = !no_fast && a.phases == SSD_PHASE_ALL && a.mask == nullptr && a.order == nullptr && !a.use_beam_buf &&
+                      !a.rew_accumulate && a.obs != nullptr && a.rew != nullptr && a.actions != nullptr && a.G == 8 && fast_rows &&
+                      (a.V == 11 || a.V == 15 || a.V == 21) && a.env_begin % 4 == 0;
+    if (!full) return launch_general(a, threads, stream, fast_rows);
+    StepArgs f = a;
+    f.env_end = a.env_begin + (a.env_end - a.env_begin) / 4 * 4;  // whole warps
+    cudaError_t e = cudaSuccess;
+    switch (a.kind) {
+        case SSD_KIND_HARVEST:
+            e = tape ? launch_fast<SSD_KIND_HARVEST, true>(f, threads, stream) : launch_fast<SSD_KIND_HARVEST, false>(f, threads, stream);
+            break;
+        case SSD_KIND_CLEANUP:
+            e = tape ? launch_fast<SSD_KIND_CLEANUP, true>(f, threads, stream) : launch_fast<SSD_KIND_CLEANUP, false>(f, threads, stream);
+            break;
+        default:
+            e = tape ? launch_fast<SSD_KIND_PLAIN, true>(f, threads, stream) : launch_fast<SSD_KIND_PLAIN, false>(f, threads, stream);
+            break;
+    }
+    if (e != cudaSuccess || f.env_end == a.env_end) return e;
+    StepArgs tail = a;  // the last 1..3 envs
+    tail.env_begin = f.env_end;
+    return launch_general(tail, threads, stream, fast_rows);
 }
 
 cudaError_t launch_reset(const ResetArgs& a, cudaStream_t stream) {
