@@ -44,6 +44,7 @@ struct SsdEnv {
     int B = 0, B_pad = 0, E = 0, threads = 128;
     int HW = 0, Ws = 0, env_bytes = 0, pad_bytes = 0, V = 0, obs_env = 0, n_apple = 0, n_waste = 0, n_spawn = 0;
     uint64_t seed = 0;
+    int harvest_nz = 0;
     uint32_t t = 0;
     int64_t launches = 0;
     ssd::SmemLayout L{};
@@ -90,15 +91,18 @@ ssd::SmemLayout make_layout(const SsdEnv& h, int threads) {
     ssd::SmemLayout L{};
     const uint32_t G = h.cfg.num_agents <= 8 ? 8 : 16, epw = 32 / G;
     uint32_t off = 0;
-    L.apple = off; off += up16(h.n_apple * 2);
+    L.apple = off; off += up16(((h.n_apple + 31) & ~31) * 2);  // padded to whole warps
     L.warp0 = off;
     uint32_t w = 0;
     L.w_mbar = w; w += 16;
     L.w_tiles = w; w += epw * (h.env_bytes + h.pad_bytes) + h.pad_bytes;
     L.w_env = w; w += epw * sizeof(ssd::EnvScratch);
-    L.w_list = w; w += up16(std::max(h.n_apple * 2, h.n_waste * 4));
-    L.w_view = w; w += up16(epw * h.cfg.num_agents * 8);
-    L.w_stage = w; w += up16(32u * 3u * h.V) + 16;
+    L.w_union = w;
+    L.u_stage = up16(epw * h.cfg.num_agents * 8);                          // view params first
+    const uint32_t u_render = L.u_stage + up16(32u * 3u * h.V) + 16;       // + staging of 32 view rows
+    const uint32_t u_spawn = up16(std::max(h.n_apple * 4, h.n_waste * 4)); // need-list / waste keys
+    const uint32_t u_moves = epw * sizeof(ssd::MoveScratch);
+    w += std::max(u_render, std::max(u_spawn, u_moves));
     if (const char* x = getenv("SSD_EXTRA_SMEM")) w += up16(static_cast<uint32_t>(atoi(x)));  // occupancy experiments
     L.warp_stride = w;
     L.total = off + (threads / 32) * w;
@@ -111,6 +115,7 @@ void fill_args(SsdEnv* h, ssd::StepArgs& a) {
     a.kind = c.kind; a.H = c.height; a.W = c.width; a.N = c.num_agents; a.r = c.view_radius; a.V = h->V;
     a.beam_len = c.beam_len; a.Ws = h->Ws; a.env_bytes = h->env_bytes; a.pad_bytes = h->pad_bytes;
     a.n_apple = h->n_apple; a.n_waste = h->n_waste; a.area = c.potential_waste_area;
+    a.harvest_nz = h->harvest_nz;
     a.obs_env = h->obs_env;
     a.G = h->cfg.num_agents <= 8 ? 8 : 16; a.env_begin = 0; a.env_end = h->B;
     a.phases = SSD_PHASE_ALL; a.rotate = 1; a.spawn_stream = ssd::STREAM_SPAWN;
@@ -212,7 +217,7 @@ int ssd_create(const SsdConfig* cfg, ssd_handle* out) {
         }
     }
     h->n_apple = static_cast<int>(apple.size()); h->n_waste = static_cast<int>(waste.size()); h->n_spawn = static_cast<int>(spawn.size());
-    if (h->n_apple >= 0x8000) { delete h; return fail(SSD_ERR_UNSUPPORTED, "too many apple points"); }
+    if (h->n_apple >= 0x4000) { delete h; return fail(SSD_ERR_UNSUPPORTED, "too many apple points"); }
     if (cfg->kind == SSD_KIND_CLEANUP && cfg->potential_waste_area < h->n_waste) {
         delete h;
         return fail(SSD_ERR_INVALID, "potential_waste_area %d smaller than the number of 'H'/'R' cells %d", cfg->potential_waste_area, h->n_waste);
@@ -220,7 +225,7 @@ int ssd_create(const SsdConfig* cfg, ssd_handle* out) {
     std::vector<uint64_t> hthr(4, 0), athr, wthr;
     std::vector<double> hp(4, 0.0), ap, wp;
     if (cfg->harvest_spawn_prob)
-        for (int i = 0; i < 4; ++i) { hp[i] = cfg->harvest_spawn_prob[i]; hthr[i] = threshold53(hp[i]); }
+        for (int i = 0; i < 4; ++i) { hp[i] = cfg->harvest_spawn_prob[i]; hthr[i] = threshold53(hp[i]); h->harvest_nz |= (hthr[i] != 0) << i; }
     const int area = cfg->kind == SSD_KIND_CLEANUP ? cfg->potential_waste_area : 0;
     for (int i = 0; i <= area; ++i) {
         const double pa = cfg->kind == SSD_KIND_CLEANUP ? cfg->cleanup_apple_prob[i] : 0.0;

@@ -48,15 +48,11 @@ constexpr uint8_t kFlag = 0x80;
 // separated (and framed) by pad_bytes >= r * Ws + r zero bytes, so every cell an egocentric
 // (2r+1)^2 window can touch exists and reads as C_PAD.  In-tile index of cell (row, col): row * Ws + col.
 
-// Per-environment scratch in shared memory.
+// Per-environment scratch in shared memory that lives for the whole step.
 struct EnvScratch {
     uint16_t pos[kMaxAgents];   // row << 8 | col (live positions)
-    uint16_t tgt[kMaxAgents];   // agent_moves values (map_env.py:400)
-    uint16_t orig[kMaxAgents];  // search_list: targets frozen before the contested pass (:426)
-    uint16_t snap[kMaxAgents];  // agent_by_pos snapshot of one fix-point pass (:495)
-    int32_t rew[kMaxAgents];    // -50 per 'F' hit taken in this step (agent.py:166-168)
+    int16_t rew[kMaxAgents];    // -50 per 'F' hit taken in this step (agent.py:166-168)
     uint8_t ori[kMaxAgents];
-    uint8_t shuf[kMaxAgents];   // movers after np.random.shuffle (:422)
     uint8_t order[kMaxAgents];  // action-dict iteration order
     uint8_t firech[kMaxAgents]; // [k] beam cell byte of the k-th entry of the action order (0 = did not fire)
     uint8_t raylen[3 * kMaxAgents];  // [k*3+s] painted cells of ray s (beam_pos, map_env.py:648)
@@ -65,11 +61,23 @@ struct EnvScratch {
 };
 static_assert(sizeof(EnvScratch) % 16 == 0, "EnvScratch must stay 16-byte sized");
 
+// Scratch of the literal update_moves emulation (moves_slow); lives in the per-warp phase union.
+struct MoveScratch {
+    uint16_t tgt[kMaxAgents];   // agent_moves values (map_env.py:400)
+    uint16_t orig[kMaxAgents];  // search_list: targets frozen before the contested pass (:426)
+    uint16_t snap[kMaxAgents];  // agent_by_pos snapshot of one fix-point pass (:495)
+    uint8_t shuf[kMaxAgents];   // movers after np.random.shuffle (:422)
+};
+static_assert(sizeof(MoveScratch) % 16 == 0, "MoveScratch must stay 16-byte sized");
+
 // Dynamic shared memory: [apple table][warp 0 region][warp 1 region]...; offsets inside a warp region.
+// The phases of a step never overlap inside a warp, so their scratch shares one union:
+//   moves:  MoveScratch per env        spawn: need-list / waste keys        render: view params + staging
 struct SmemLayout {
     uint32_t apple;                                  // CTA-shared table
     uint32_t warp0, warp_stride;                     // first warp region, bytes per warp
-    uint32_t w_mbar, w_tiles, w_env, w_list, w_view, w_stage;  // offsets inside a warp region
+    uint32_t w_mbar, w_tiles, w_env, w_union;        // offsets inside a warp region
+    uint32_t u_stage;                                // staging buffer inside the union (after the view params)
     uint32_t total;
 };
 
@@ -80,6 +88,7 @@ struct StepArgs {
     int env_bytes;        // round_up(H * Ws, 16): one env's grid in HBM
     int pad_bytes;        // zero bytes between / around the tiles in shared memory
     int n_apple, n_waste, area;
+    int harvest_nz;       // bit n: SPAWN_PROB[n] != 0 (harvest.py:13)
     int obs_env;          // N*V*V*3 bytes
     // ---- launch description
     int G;                // lanes per env in phase A: 8 (N <= 8) or 16

@@ -46,11 +46,11 @@ __device__ __forceinline__ int by_pos(const uint16_t* p, int N, uint32_t key) {
 // Literal emulation of the conflict resolution of update_moves (map_env.py:394-543) for one env,
 // run by a single lane.  S.pos / S.tgt hold positions and wall-clipped targets of the movers.
 template <bool TAPE>
-__device__ __noinline__ void moves_slow(const StepArgs& a, EnvScratch& S, uint32_t movers, int local_env,
+__device__ __noinline__ void moves_slow(const StepArgs& a, EnvScratch& S, MoveScratch& M, uint32_t movers, int local_env,
                                          const PhiloxKey& pk) {
     const int N = a.N;
     // mover list in action order (agent_moves is an insertion-ordered dict, map_env.py:400-412)
-    uint8_t* shuf = S.shuf;
+    uint8_t* shuf = M.shuf;
     int n_mov = 0;
     for (int k = 0; k < N; ++k) {
         const int ag = S.order[k];
@@ -69,14 +69,14 @@ __device__ __noinline__ void moves_slow(const StepArgs& a, EnvScratch& S, uint32
             const uint8_t tmp = shuf[i]; shuf[i] = shuf[j]; shuf[j] = tmp;
         }
     }
-    for (int ag = 0; ag < N; ++ag) S.orig[ag] = (movers >> ag & 1) ? S.tgt[ag] : 0xFFFFu;
+    for (int ag = 0; ag < N; ++ag) M.orig[ag] = (movers >> ag & 1) ? M.tgt[ag] : 0xFFFFu;
 
     // contested cells in lexicographic (row, col) order == ascending key (np.unique axis=0, :424)
     int prev = -1;
     while (true) {
         int cell = 0x10000, cnt = 0;
         for (int ag = 0; ag < N; ++ag) {
-            const int o = S.orig[ag];
+            const int o = M.orig[ag];
             if (o != 0xFFFF && o > prev) {
                 if (o < cell) { cell = o; cnt = 1; } else if (o == cell) ++cnt;
             }
@@ -88,43 +88,43 @@ __device__ __noinline__ void moves_slow(const StepArgs& a, EnvScratch& S, uint32
         int winner = -1;
         for (int i = 0; i < n_mov; ++i) {  // conflicting agents in shuffled order (:441-442)
             const int ag = shuf[i];
-            if (S.orig[ag] != cell) continue;
+            if (M.orig[ag] != cell) continue;
             if (winner < 0) winner = ag;  // agent_to_slot[index]: first occurrence (:481)
             if (occupied(S.pos, N, cell)) {                       // :449
                 const int o = by_pos(S.pos, N, cell);             // :452 (rebuilt after every update)
                 const uint32_t cpos = S.pos[o];
                 const bool o_moves = movers >> o & 1;
-                const uint32_t cmove = o_moves ? S.tgt[o] : cpos; // :456
+                const uint32_t cmove = o_moves ? M.tgt[o] : cpos; // :456
                 if (ag == o) cell_free = false;                                   // (1) :460
                 else if (!o_moves || cpos == cmove) cell_free = false;            // (2) :466
-                else if (S.tgt[o] == S.pos[ag] && cell == (int)S.pos[o]) cell_free = false;  // (3) :472
+                else if (M.tgt[o] == S.pos[ag] && cell == (int)S.pos[o]) cell_free = false;  // (3) :472
             }
         }
         if (cell_free) S.pos[winner] = static_cast<uint16_t>(cell);  // :480-483
         for (int i = 0; i < n_mov; ++i) {                            // :486-491
             const int ag = shuf[i];
-            if (S.orig[ag] == cell) S.tgt[ag] = S.pos[ag];
+            if (M.orig[ag] == cell) M.tgt[ag] = S.pos[ag];
         }
     }
 
     // remaining moves: fix-point loop, map_env.py:494-543
     uint32_t alive = movers;
     while (alive) {
-        for (int ag = 0; ag < N; ++ag) S.snap[ag] = S.pos[ag];  // agent_by_pos snapshot (:495)
+        for (int ag = 0; ag < N; ++ag) M.snap[ag] = S.pos[ag];  // agent_by_pos snapshot (:495)
         const uint32_t in_copy = alive;                         // moves_copy (:498)
         uint32_t deleted = 0;
         for (int k = 0; k < N; ++k) {
             const int ag = S.order[k];
             if (!(in_copy >> ag & 1) || (deleted >> ag & 1)) continue;
-            const uint32_t mv = S.tgt[ag];
+            const uint32_t mv = M.tgt[ag];
             if (occupied(S.pos, N, mv)) {                   // :503 live positions
-                const int o = by_pos(S.snap, N, mv);        // :506 snapshot
+                const int o = by_pos(M.snap, N, mv);        // :506 snapshot
                 if (o < 0) continue;                        // reference would KeyError; unreachable
                 const uint32_t cpos = S.pos[o];
-                const uint32_t cmove = (alive >> o & 1) ? S.tgt[o] : cpos;  // :509 live agent_moves
+                const uint32_t cmove = (alive >> o & 1) ? M.tgt[o] : cpos;  // :509 live agent_moves
                 if (ag == o) { alive &= ~(1u << ag); deleted |= 1u << ag; }                                  // (1)
                 else if (!(in_copy >> o & 1) || cpos == cmove) { alive &= ~(1u << ag); deleted |= 1u << ag; }  // (2)
-                else if (S.tgt[o] == S.pos[ag] && mv == S.pos[o]) {                                           // (3)
+                else if (M.tgt[o] == S.pos[ag] && mv == S.pos[o]) {                                           // (3)
                     alive &= ~((1u << ag) | (1u << o)); deleted |= (1u << ag) | (1u << o);
                 }
             } else {
@@ -133,7 +133,7 @@ __device__ __noinline__ void moves_slow(const StepArgs& a, EnvScratch& S, uint32
             }
         }
         if (alive == in_copy) {  // nobody could move freely: move them all (:540-543)
-            for (int ag = 0; ag < N; ++ag) if (alive >> ag & 1) S.pos[ag] = S.tgt[ag];
+            for (int ag = 0; ag < N; ++ag) if (alive >> ag & 1) S.pos[ag] = M.tgt[ag];
             break;
         }
     }
@@ -146,7 +146,7 @@ struct AgentLane {
 
 // update_moves for one group of G lanes (= one env).  All 32 lanes of the warp call this.
 template <bool TAPE>
-__device__ __forceinline__ void moves_group(const StepArgs& a, EnvScratch& S, const uint8_t* g, AgentLane& me, bool valid,
+__device__ __forceinline__ void moves_group(const StepArgs& a, EnvScratch& S, MoveScratch& M, const uint8_t* g, AgentLane& me, bool valid,
                                             int al, int G, int local_env, const PhiloxKey& pk) {
     const int act = me.act;
     bool mover = false;
@@ -187,9 +187,9 @@ __device__ __forceinline__ void moves_group(const StepArgs& a, EnvScratch& S, co
     const uint32_t movers = (__ballot_sync(0xffffffffu, mover) & gmask) >> gshift;
     if (conf == 0 && mover) me.key = tgt;
     if (conf_all != 0) {  // warp-uniform branch: groups without a conflict just keep the barriers company
-        if (conf != 0 && valid) { S.pos[al] = static_cast<uint16_t>(me.key); S.tgt[al] = static_cast<uint16_t>(tgt); }
+        if (conf != 0 && valid) { S.pos[al] = static_cast<uint16_t>(me.key); M.tgt[al] = static_cast<uint16_t>(tgt); }
         __syncwarp();
-        if (conf != 0 && al == 0) moves_slow<TAPE>(a, S, movers, local_env, pk);
+        if (conf != 0 && al == 0) moves_slow<TAPE>(a, S, M, movers, local_env, pk);
         __syncwarp();
         if (conf != 0 && valid) me.key = S.pos[al];
     }
@@ -230,40 +230,51 @@ __device__ __forceinline__ int ray_walk(const StepArgs& a, EnvScratch& S, uint8_
 // Agent cells are flagged with bit 7 while the spawn pass runs ("[row, col] not in self.agent_pos",
 // harvest.py:90, cleanup.py:138); consume already turned every apple under an agent into ' '.
 template <bool TAPE>
-__device__ __forceinline__ void harvest_spawn(const StepArgs& a, uint8_t* g, const uint16_t* s_apple, uint16_t* list,
+__device__ __forceinline__ void harvest_spawn(const StepArgs& a, uint8_t* g, const uint16_t* s_apple, uint32_t* list,
                                               int local_env, const PhiloxKey& pk, int lane, Counters& cnt) {
     const int Ws = a.Ws, n_apple = a.n_apple;
-    int base = 0;
-    for (int i0 = 0; i0 < n_apple; i0 += 32) {  // eligibility scan in row-major apple-point order (harvest.py:87-90)
+    constexpr uint8_t A = CB(C_APPLE);
+    // One scan in row-major apple-point order (harvest.py:87-101).  The apple table is padded to a
+    // multiple of 32 with a harmless interior cell, so every lane loads unconditionally.  `base`
+    // counts eligible points: the k-th eligible point consumes the k-th np.random.rand.  Only points
+    // whose spawn probability is not zero (n apple neighbours with SPAWN_PROB[n] != 0) can spawn; they
+    // are compacted into `list` as cell | n << 16 | draw index << 18 and drawn for afterwards.
+    int base = 0, n_need = 0;
+#pragma unroll 1
+    for (int i0 = 0; i0 < n_apple; i0 += 32) {
         const int i = i0 + lane;
-        bool el = false;
-        if (i < n_apple) { const uint8_t c = g[s_apple[i]]; el = (c != CB(C_APPLE)) && !(c & kFlag); }
+        const uint32_t cell = s_apple[i];
+        const uint8_t* q = g + cell;
+        const uint8_t c = q[0];
+        const bool el = (i < n_apple) & (c != A) & (c < kFlag);  // not an apple, no agent on it (harvest.py:90)
         const uint32_t m = __ballot_sync(0xffffffffu, el);
-        if (el) list[base + __popc(m & lanemask_lt())] = static_cast<uint16_t>(i);
+        if (m == 0) continue;
+        // 3x3 window, j*j + k*k <= APPLE_RADIUS(2) (harvest.py:92-99); cells outside the map are 0 in the tile
+        int n = (q[-Ws - 1] == A) + (q[-Ws] == A) + (q[-Ws + 1] == A) + (q[-1] == A) + (q[1] == A) +
+                (q[Ws - 1] == A) + (q[Ws] == A) + (q[Ws + 1] == A);
+        n = n < 3 ? n : 3;
+        const bool need = el & ((a.harvest_nz >> n) & 1);
+        const uint32_t m2 = __ballot_sync(0xffffffffu, need);
+        if (need) list[n_need + __popc(m2 & lanemask_lt())] = cell | static_cast<uint32_t>(n) << 16 |
+                                                               static_cast<uint32_t>(base + __popc(m & lanemask_lt())) << 18;
         base += __popc(m);
+        n_need += __popc(m2);
     }
-    const int n_draw = base;  // k-th eligible point consumes the k-th np.random.rand (harvest.py:101)
-    if (TAPE && a.n_draws_out != nullptr && lane == 0) a.n_draws_out[local_env] = n_draw;
-    __syncwarp();
-    for (int j0 = 0; j0 < n_draw; j0 += 32) {
+    if (TAPE && a.n_draws_out != nullptr && lane == 0) a.n_draws_out[local_env] = base;
+    __syncwarp();  // every read saw the pre-spawn grid; writes happen after the scan (harvest.py:72-73)
+#pragma unroll 1
+    for (int j0 = 0; j0 < n_need; j0 += 32) {
         const int j = j0 + lane;
-        if (j < n_draw) {
-            const int i = list[j];
-            const uint8_t* q = g + s_apple[i];
-            // 3x3 window, j*j + k*k <= APPLE_RADIUS(2) (harvest.py:92-99); cells outside the map are 0 in the tile
-            constexpr uint8_t A = CB(C_APPLE);
-            int n = (q[-Ws - 1] == A) + (q[-Ws] == A) + (q[-Ws + 1] == A) + (q[-1] == A) + (q[1] == A) +
-                    (q[Ws - 1] == A) + (q[Ws] == A) + (q[Ws + 1] == A);
-            n = n < 3 ? n : 3;
-            bool spawn = false;
-            if (TAPE) spawn = a.tape_u[static_cast<size_t>(local_env) * a.u_stride + j] < a.harvest_p[n];
-            else if (n > 0) spawn = philox_u53(pk, a.spawn_stream, j) < a.harvest_thr[n];  // u < p  <=>  u53 < ceil(p * 2^53)
-            if (spawn) list[j] = static_cast<uint16_t>(i | 0x8000);
+        if (j < n_need) {
+            const uint32_t en = list[j];
+            const int n = (en >> 16) & 3;
+            const uint32_t k = en >> 18;
+            bool spawn;
+            if (TAPE) spawn = a.tape_u[static_cast<size_t>(local_env) * a.u_stride + k] < a.harvest_p[n];
+            else spawn = philox_u53(pk, a.spawn_stream, k) < a.harvest_thr[n];  // u < p  <=>  u53 < ceil(p * 2^53)
+            if (spawn) { g[en & 0xffffu] = A; ++cnt.apples; }
         }
     }
-    __syncwarp();  // every read saw the pre-spawn grid; writes happen after the scan (harvest.py:72-73)
-    for (int j = lane; j < n_draw; j += 32)
-        if (list[j] & 0x8000) { g[s_apple[list[j] & 0x7fff]] = CB(C_APPLE); ++cnt.apples; }
 }
 
 template <bool TAPE>
@@ -493,7 +504,7 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_kernel(const __grid_cons
     if (tid < SSD_NUM_STATS) s_cta_stats[tid] = 0;
     if (tid == 0) s_done = 0;
     if (phases & SSD_PHASE_SPAWN)
-        for (int i = tid; i < a.n_apple; i += nthr) s_apple[i] = a.apple_cell[i];
+        for (int i = tid; i < ((a.n_apple + 31) & ~31); i += nthr) s_apple[i] = i < a.n_apple ? a.apple_cell[i] : static_cast<uint16_t>(a.Ws + 1);
     __syncthreads();
 
     // ---- this warp's envs
@@ -546,7 +557,7 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_kernel(const __grid_cons
         if (al == 0) S.active = active;
         __syncwarp();
         if (phases & SSD_PHASE_MOVES) {
-            moves_group<TAPE>(a, S, g, me, valid && active, al, G, e, pk);
+            moves_group<TAPE>(a, S, reinterpret_cast<MoveScratch*>(wbase + a.L.w_union)[j], g, me, valid && active, al, G, e, pk);
             cnt.steps += (active && al == 0);
         }
         if (valid) { S.pos[al] = static_cast<uint16_t>(me.key); S.ori[al] = static_cast<uint8_t>(me.ori); }
@@ -612,9 +623,9 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_kernel(const __grid_cons
             for (int q = 0; q < EPW; ++q) {
                 if (!envs[q].active) continue;
                 pk.env = static_cast<uint32_t>(a.env_id0 + static_cast<uint64_t>(we + q));
-                void* scratch = wbase + a.L.w_list;
+                void* scratch = wbase + a.L.w_union;
                 if (KIND == SSD_KIND_HARVEST)
-                    harvest_spawn<TAPE>(a, tiles + a.pad_bytes + q * tile_pitch, s_apple, static_cast<uint16_t*>(scratch), we + q, pk, lane, cnt);
+                    harvest_spawn<TAPE>(a, tiles + a.pad_bytes + q * tile_pitch, s_apple, static_cast<uint32_t*>(scratch), we + q, pk, lane, cnt);
                 else
                     cleanup_spawn<TAPE>(a, tiles + a.pad_bytes + q * tile_pitch, s_apple, static_cast<uint32_t*>(scratch), we + q, pk, lane, cnt);
                 __syncwarp();
@@ -664,13 +675,13 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_kernel(const __grid_cons
                     }
                 }
             }
-            uint2* s_view = reinterpret_cast<uint2*>(wbase + a.L.w_view);
+            uint2* s_view = reinterpret_cast<uint2*>(wbase + a.L.w_union);
             for (int i = lane; i < EPW * N; i += 32) s_view[i] = view_param(a, envs[i / N], a.pad_bytes + (i / N) * tile_pitch, i % N);
             __syncwarp();
             uint8_t* dst = a.obs + static_cast<size_t>(we) * a.obs_env;
             const bool all_active = (nvalid == EPW) && (a.mask == nullptr);
             if constexpr (VT > 0) {
-                if (all_active) render_rows<VT>(s_view, tiles, s_color, reinterpret_cast<uint32_t*>(wbase + a.L.w_stage), dst, EPW * N * VT);
+                if (all_active) render_rows<VT>(s_view, tiles, s_color, reinterpret_cast<uint32_t*>(wbase + a.L.w_union + a.L.u_stage), dst, EPW * N * VT);
                 else render_generic(a, envs, s_view, tiles, s_color, dst, nvalid);
             } else {
                 render_generic(a, envs, s_view, tiles, s_color, dst, nvalid);
@@ -734,13 +745,18 @@ __device__ __forceinline__ void render_rows_tma(const uint2* s_view, const uint8
     const uint32_t o = static_cast<uint32_t>(lane) * RB;
     const uint32_t d8 = 8u * ((4u - (o & 3u)) & 3u);
     const uint32_t w0 = (o + 3) >> 2, w1 = (o + RB - 1) >> 2;
-    const int M = static_cast<int>(w1 - w0) + 1;  // NP - 1 or NP - 2 ... per-lane constant
+    const bool extra = static_cast<int>(w1 - w0) + 1 > MMIN;  // this lane owns MMIN + 1 words of every chunk
     uint32_t* st = stage + mis4 + w0;
-    uint8_t* const base = dst - mis;
+    const uint8_t* stage_b = reinterpret_cast<const uint8_t*>(stage);
+    const int n_chunks = (total_rows + 31) >> 5;
+    const int end_last = mis + (total_rows - (n_chunks - 1) * 32) * RB;  // valid image bytes of the last chunk (multiple of 4)
+    const int hi_last = min(CH, end_last & ~15);
+    uint8_t* out = dst - mis;  // 16-byte aligned image of chunk 0
     uint32_t c0 = 0, c1 = 0, c2 = 0;
-    for (int row0 = 0; row0 < total_rows; row0 += 32) {
-        const int R = min(row0 + lane, total_rows - 1);  // lanes past the end redo the last row; their words are never copied out
-        const int ga = R / VT, i = R - ga * VT;           // rows are ordered (env, agent, i)
+#pragma unroll 1
+    for (int c = 0; c < n_chunks; ++c, out += CH) {
+        const int R = min(c * 32 + lane, total_rows - 1);  // lanes past the end redo the last row; their words are never copied out
+        const int ga = R / VT, i = R - ga * VT;            // rows are ordered (env, agent, i)
         uint32_t X[VT + 2];
         {
             const uint2 vp = s_view[ga];
@@ -758,18 +774,17 @@ __device__ __forceinline__ void render_rows_tma(const uint2* s_view, const uint8
             P[w] = __byte_perm(X[p], X[p + 1], ph == 0 ? 0x4210u : (ph == 1 ? 0x5421u : 0x6542u));
         }
         P[NP] = 0;
-        uint32_t Q[NP];
+        uint32_t Q[MMIN + 1];
 #pragma unroll
-        for (int m = 0; m < NP; ++m) Q[m] = __funnelshift_r(P[m], P[m + 1], d8);
-        // the previous chunk's bulk store must have finished READING the buffer
-        if (row0 != 0) {
+        for (int m = 0; m <= MMIN; ++m) Q[m] = __funnelshift_r(P[m], P[m + 1], d8);
+        if (c != 0) {  // the previous chunk's bulk store must have finished READING the buffer
             if (lane == 0) bulk_wait_read();
             __syncwarp();
         }
 #pragma unroll
-        for (int m = 0; m < NP; ++m)
-            if (m < MMIN || m < M) st[m] = Q[m];
-        if (lane == 31 && row0 != 0) {  // head of this chunk's image = the words that spilled over the previous chunk
+        for (int m = 0; m < MMIN; ++m) st[m] = Q[m];
+        if (extra) st[MMIN] = Q[MMIN];
+        if (lane == 31 && c != 0) {  // head of this chunk's image = the words that spilled over the previous chunk
             if (mis4 >= 1) stage[mis4 - 1] = c2;
             if (mis4 >= 2) stage[mis4 - 2] = c1;
             if (mis4 >= 3) stage[mis4 - 3] = c0;
@@ -777,21 +792,20 @@ __device__ __forceinline__ void render_rows_tma(const uint2* s_view, const uint8
         c0 = Q[M31 - 3]; c1 = Q[M31 - 2]; c2 = Q[M31 - 1];
         fence_async_smem();
         __syncwarp();
-        const int nbytes = min(32, total_rows - row0) * RB;  // multiple of 4 (the launcher checks the slab size)
-        const int end = mis + nbytes;                         // valid image bytes: [row0 ? 0 : mis, end)
-        const int lo = (row0 == 0 && mis != 0) ? 16 : 0;
-        const int hi = min(CH, end & ~15);
-        uint8_t* out = base + static_cast<size_t>(row0) * RB;
-        if (lane == 0 && hi > lo) {
-            bulk_s2g(out + lo, reinterpret_cast<const uint8_t*>(stage) + lo, static_cast<uint32_t>(hi - lo));
-            bulk_commit();
+        if (lane == 0) {
+            const int lo = (c == 0 && mis != 0) ? 16 : 0;
+            const int hi = (c == n_chunks - 1) ? hi_last : CH;
+            if (hi > lo) {
+                bulk_s2g(out + lo, stage_b + lo, static_cast<uint32_t>(hi - lo));
+                bulk_commit();
+            }
         }
-        if (row0 == 0 && lane >= mis4 && lane < 4 && mis != 0)  // first bytes of the slab
+        if (c == 0 && lane >= mis4 && lane < 4 && mis != 0)  // first bytes of the slab
             *reinterpret_cast<uint32_t*>(out + 4 * lane) = stage[lane];
-        if (row0 + 32 >= total_rows) {                          // last bytes of the slab
-            const int off = hi + 4 * lane;
-            if (off < end) *reinterpret_cast<uint32_t*>(out + off) = stage[off >> 2];
-        }
+    }
+    {   // last bytes of the slab (out was advanced once past the last chunk)
+        const int off = hi_last + 4 * lane;
+        if (off < end_last) *reinterpret_cast<uint32_t*>(out - CH + off) = stage[off >> 2];
     }
     if (lane == 0) bulk_wait_read();  // shared memory must outlive the last bulk read
 }
@@ -812,7 +826,7 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
     if (tid == 0) s_done = 0;
     if (KIND != SSD_KIND_PLAIN)
 #pragma unroll 1
-        for (int i = tid; i < a.n_apple; i += nthr) s_apple[i] = a.apple_cell[i];
+        for (int i = tid; i < ((a.n_apple + 31) & ~31); i += nthr) s_apple[i] = i < a.n_apple ? a.apple_cell[i] : static_cast<uint16_t>(a.Ws + 1);
     __syncthreads();
 
     uint8_t* wbase = smem + a.L.warp0 + warp * a.L.warp_stride;
@@ -860,7 +874,7 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
         __syncwarp();
 
         // ---- phase A: one lane per agent
-        moves_group<TAPE>(a, S, g, me, valid, al, G, e, pk);
+        moves_group<TAPE>(a, S, reinterpret_cast<MoveScratch*>(wbase + a.L.w_union)[j], g, me, valid, al, G, e, pk);
         cnt.steps += (al == 0);
         if (valid) S.pos[al] = static_cast<uint16_t>(me.key);
         const int my_idx = tile_idx(a, me.key);
@@ -902,12 +916,12 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
 
         // ---- phase B: the whole warp per env
         if (KIND != SSD_KIND_PLAIN) {
-            void* scratch = wbase + a.L.w_list;
+            void* scratch = wbase + a.L.w_union;
 #pragma unroll 1
             for (int q = 0; q < EPW; ++q) {
                 pk.env = static_cast<uint32_t>(a.env_id0 + static_cast<uint64_t>(we + q));
                 if (KIND == SSD_KIND_HARVEST)
-                    harvest_spawn<TAPE>(a, tiles + a.pad_bytes + q * tile_pitch, s_apple, static_cast<uint16_t*>(scratch), we + q, pk, lane, cnt);
+                    harvest_spawn<TAPE>(a, tiles + a.pad_bytes + q * tile_pitch, s_apple, static_cast<uint32_t*>(scratch), we + q, pk, lane, cnt);
                 else
                     cleanup_spawn<TAPE>(a, tiles + a.pad_bytes + q * tile_pitch, s_apple, static_cast<uint32_t*>(scratch), we + q, pk, lane, cnt);
                 __syncwarp();
@@ -954,7 +968,7 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
                     __syncwarp();
                 }
             }
-            uint2* s_view = reinterpret_cast<uint2*>(wbase + a.L.w_view);
+            uint2* s_view = reinterpret_cast<uint2*>(wbase + a.L.w_union);
             if (valid) {  // rot90 folded into strides, see view_param
                 const int pr = me.key >> 8, pc = me.key & 255, r = a.r, Ws = a.Ws;
                 const int k = (4 - me.ori) & 3;
@@ -967,7 +981,7 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
                                                 (static_cast<uint32_t>(si) & 0xffffu) | static_cast<uint32_t>(sj) << 16);
             }
             __syncwarp();
-            render_rows_tma<VT>(s_view, tiles, s_color, reinterpret_cast<uint32_t*>(wbase + a.L.w_stage),
+            render_rows_tma<VT>(s_view, tiles, s_color, reinterpret_cast<uint32_t*>(wbase + a.L.w_union + a.L.u_stage),
                                 a.obs + static_cast<size_t>(we) * a.obs_env, EPW * N * VT);
         }
     }
