@@ -47,7 +47,7 @@ struct SsdEnv {
     int harvest_nz = 0;
     uint32_t t = 0;
     int64_t launches = 0;
-    ssd::SmemLayout L{};
+    ssd::SmemLayout L{}, Lf{};
     // device allocations
     std::vector<void*> allocs;
     uint16_t* d_apple = nullptr;
@@ -87,7 +87,7 @@ bool is_device_ptr(const void* p) {
     return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
 }
 
-ssd::SmemLayout make_layout(const SsdEnv& h, int threads) {
+ssd::SmemLayout make_layout(const SsdEnv& h, int threads, bool fast = false) {
     ssd::SmemLayout L{};
     const uint32_t G = h.cfg.num_agents <= 8 ? 8 : 16, epw = 32 / G;
     uint32_t off = 0;
@@ -96,10 +96,10 @@ ssd::SmemLayout make_layout(const SsdEnv& h, int threads) {
     uint32_t w = 0;
     L.w_mbar = w; w += 16;
     L.w_tiles = w; w += epw * (h.env_bytes + h.pad_bytes) + h.pad_bytes;
-    L.w_env = w; w += epw * sizeof(ssd::EnvScratch);
+    L.w_env = w; w += epw * (fast ? sizeof(ssd::FastScratch) : sizeof(ssd::EnvScratch));
     L.w_union = w;
     L.u_stage = up16(epw * h.cfg.num_agents * 8);                          // view params first
-    const uint32_t u_render = L.u_stage + up16(32u * 3u * h.V) + 16;       // + staging of 32 view rows
+    const uint32_t u_render = L.u_stage + up16(32u * 3u * h.V) + 32;       // + staging of 32 view rows, spill and dummy words
     const uint32_t u_spawn = up16(std::max(h.n_apple * 4, h.n_waste * 4)); // need-list / waste keys
     const uint32_t u_moves = epw * sizeof(ssd::MoveScratch);
     w += std::max(u_render, std::max(u_spawn, u_moves));
@@ -116,12 +116,13 @@ void fill_args(SsdEnv* h, ssd::StepArgs& a) {
     a.beam_len = c.beam_len; a.Ws = h->Ws; a.env_bytes = h->env_bytes; a.pad_bytes = h->pad_bytes;
     a.n_apple = h->n_apple; a.n_waste = h->n_waste; a.area = c.potential_waste_area;
     a.harvest_nz = h->harvest_nz;
+    { static const int dbg = getenv("SSD_DEBUG_SKIP") ? atoi(getenv("SSD_DEBUG_SKIP")) : 0; a.debug = dbg; }
     a.obs_env = h->obs_env;
     a.G = h->cfg.num_agents <= 8 ? 8 : 16; a.env_begin = 0; a.env_end = h->B;
     a.phases = SSD_PHASE_ALL; a.rotate = 1; a.spawn_stream = ssd::STREAM_SPAWN;
     a.key0 = static_cast<uint32_t>(h->seed); a.key1 = static_cast<uint32_t>(h->seed >> 32); a.t = h->t;
     a.env_id0 = c.env_id_offset;
-    a.L = h->L;
+    a.L = h->L; a.Lf = h->Lf;
     a.apple_cell = h->d_apple; a.waste_cell = h->d_waste;
     a.color = h->d_color; a.harvest_thr = h->d_hthr; a.harvest_p = h->d_hp;
     a.apple_thr = h->d_athr; a.apple_p = h->d_ap; a.waste_thr = h->d_wthr; a.waste_p = h->d_wp;
@@ -191,7 +192,7 @@ int ssd_create(const SsdConfig* cfg, ssd_handle* out) {
     if (h->env_bytes > 65535) { delete h; return fail(SSD_ERR_UNSUPPORTED, "map tile of %d bytes exceeds the 16-bit cell index range", h->env_bytes); }
 
     // static tables
-    std::vector<uint32_t> color(ssd::kNumCodes, 0);
+    std::vector<uint32_t> color(ssd::kLutEntries, 0);
     std::vector<uint16_t> apple, waste, spawn;
     std::vector<uint8_t> init_grid(h->env_bytes, 0);
     const uint8_t apple_ch = cfg->kind == SSD_KIND_HARVEST ? 'A' : (cfg->kind == SSD_KIND_CLEANUP ? 'B' : 0);
@@ -207,13 +208,25 @@ int ssd_create(const SsdConfig* cfg, ssd_handle* out) {
             if (apple_ch && ch == apple_ch) apple.push_back(tile_cell);
             if (cfg->kind == SSD_KIND_CLEANUP && (ch == 'H' || ch == 'R')) waste.push_back(tile_cell);
         }
+    if (cfg->kind == SSD_KIND_HARVEST)  // cached neighbourhood counts (ssd_internal.h: device cell encoding)
+        for (int r = 1; r + 1 < H; ++r)
+            for (int c = 1; c + 1 < W; ++c) {
+                uint8_t& g = init_grid[r * h->Ws + c];
+                if (g != ssd::CB(ssd::C_EMPTY) && g != ssd::CB(ssd::C_APPLE)) continue;
+                int n = 0;
+                for (int dr = -1; dr <= 1; ++dr)
+                    for (int dc = -1; dc <= 1; ++dc)
+                        n += (dr || dc) && (init_grid[(r + dr) * h->Ws + c + dc] & ssd::kCodeMask) == ssd::CB(ssd::C_APPLE);
+                g |= static_cast<uint8_t>(n < 3 ? n : 3);
+            }
     for (int s = 0; s < cfg->num_spawn_points; ++s)
         spawn.push_back(static_cast<uint16_t>(cfg->spawn_points[2 * s] << 8 | cfg->spawn_points[2 * s + 1]));
     {   // colour table by cell code: every code takes the colour of its ASCII character
         const char* chars = "0 @AHRSFC123456789";
         for (int code = 0; chars[code]; ++code) {
             const int i = static_cast<uint8_t>(chars[code]);
-            color[code] = cfg->color_lut[3 * i] | cfg->color_lut[3 * i + 1] << 8 | cfg->color_lut[3 * i + 2] << 16;
+            for (int nb = 0; nb < 4; ++nb)  // the table is indexed by the grid byte: code << 2 | neighbour count
+                color[4 * code + nb] = cfg->color_lut[3 * i] | cfg->color_lut[3 * i + 1] << 8 | cfg->color_lut[3 * i + 2] << 16;
         }
     }
     h->n_apple = static_cast<int>(apple.size()); h->n_waste = static_cast<int>(waste.size()); h->n_spawn = static_cast<int>(spawn.size());
@@ -251,6 +264,7 @@ int ssd_create(const SsdConfig* cfg, ssd_handle* out) {
         delete h;
         return fail(SSD_ERR_UNSUPPORTED, "one warp's tile set needs %u bytes of shared memory (limit %d)", need, smem_max);
     }
+    h->Lf = make_layout(*h, h->threads, true);
     const int E = (h->threads / 32) * (N <= 8 ? 4 : 2);
     h->E = E;
     h->B_pad = (h->B + E - 1) / E * E;
@@ -337,7 +351,7 @@ int ssd_set_state(ssd_handle h, const uint8_t* grid, const int16_t* pos, const u
         CUDA_TRY(cudaMemcpyAsync(h->d_io_ori, ori, np, cudaMemcpyDefault, st));
         grid = h->d_io_grid; pos = h->d_io_pos; ori = h->d_io_ori;
     }
-    CUDA_TRY(ssd::launch_pack_state(h->B, N, h->cfg.height, h->cfg.width, h->Ws, h->env_bytes, grid, pos, ori, h->d_grid, h->d_agents, st));
+    CUDA_TRY(ssd::launch_pack_state(h->cfg.kind, h->B, N, h->cfg.height, h->cfg.width, h->Ws, h->env_bytes, grid, pos, ori, h->d_grid, h->d_agents, st));
     h->launches++;
     return SSD_OK;
 }

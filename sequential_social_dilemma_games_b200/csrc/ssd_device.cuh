@@ -75,6 +75,9 @@ __device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, u
                  "r"(bytes)
                  : "memory");
 }
+__device__ __forceinline__ void bulk_s2g_u32(void* gmem_dst, uint32_t smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 // make generic-proxy shared-memory writes visible to the async proxy (TMA) before a bulk store

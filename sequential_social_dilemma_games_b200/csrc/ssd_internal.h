@@ -21,10 +21,14 @@ enum : uint32_t {
 };
 
 // ---------------------------------------------------------------------------------------------
-// Device cell encoding.  A grid byte on the device is (cell code) * 4, i.e. directly the byte offset
-// of the cell's colour in the 32-entry colour table; bit 7 is free and flags "an agent stands here"
-// between the consume and spawn phases.  ssd_set_state / ssd_get_state translate from / to the
-// reference's ASCII characters (map_env.py:24-41, cleanup.py:15-18).
+// Device cell encoding.  A grid byte on the device is (cell code) << 2 | nb:
+//   bits 2..6  cell code (below)
+//   bits 0..1  nb, Harvest only, ' ' and 'A' cells only: min(3, number of 'A' cells among the 8
+//              neighbours) -- the neighbourhood count of spawn_apples (harvest.py:92-100) cached in
+//              the grid and refreshed around every cell that gains or loses an apple; 0 elsewhere
+//   bit 7      transient "an agent stands here" flag between the consume and spawn phases
+// The byte (without bit 7) indexes the colour table directly.  ssd_set_state / ssd_get_state
+// translate from / to the reference's ASCII characters (map_env.py:24-41, cleanup.py:15-18).
 // ---------------------------------------------------------------------------------------------
 enum : uint8_t {
     C_PAD = 0,     // '0'  outside the map (utility_funcs.py:94-114)
@@ -37,11 +41,13 @@ enum : uint8_t {
     C_FIRE = 7,    // 'F'  overlay only
     C_CLEAN = 8,   // 'C'  overlay only
     C_AGENT = 9,   // '1'..'9' -> 9..17, overlay only
-    C_OTHER = 31,  // any other character handed to ssd_set_state
-    kNumCodes = 32
+    C_OTHER = 18,  // any other character handed to ssd_set_state
+    kNumCodes = 19,
+    kLutEntries = 4 * kNumCodes  // colour table indexed by the grid byte
 };
 __host__ __device__ constexpr uint8_t CB(uint8_t code) { return static_cast<uint8_t>(code * 4); }
 constexpr uint8_t kFlag = 0x80;
+constexpr uint8_t kCodeMask = 0x7C;  // cell code without the neighbour count and the agent flag
 
 // Grid layout.  HBM: [B_pad][env_bytes], row stride Ws = W + r (>= r zero bytes after the W cells of
 // every row), env_bytes = round_up(H * Ws, 16).  Shared memory, per warp: the tiles of its envs
@@ -60,6 +66,15 @@ struct EnvScratch {
     int32_t pad[3];
 };
 static_assert(sizeof(EnvScratch) % 16 == 0, "EnvScratch must stay 16-byte sized");
+
+// The same for the specialised full-step kernel (N <= 8, actions in agent order).
+struct FastScratch {
+    uint16_t pos[8];
+    int16_t rew[8];
+    uint8_t raylen[24];
+    uint8_t order[8];
+};
+static_assert(sizeof(FastScratch) % 16 == 0, "FastScratch must stay 16-byte sized");
 
 // Scratch of the literal update_moves emulation (moves_slow); lives in the per-warp phase union.
 struct MoveScratch {
@@ -89,6 +104,7 @@ struct StepArgs {
     int pad_bytes;        // zero bytes between / around the tiles in shared memory
     int n_apple, n_waste, area;
     int harvest_nz;       // bit n: SPAWN_PROB[n] != 0 (harvest.py:13)
+    int debug;            // SSD_DEBUG_SKIP bits (profiling experiments only; 0 in production)
     int obs_env;          // N*V*V*3 bytes
     // ---- launch description
     int G;                // lanes per env in phase A: 8 (N <= 8) or 16
@@ -100,7 +116,8 @@ struct StepArgs {
     int rew_accumulate;
     uint32_t key0, key1, t;
     uint64_t env_id0;     // global id of local env 0
-    SmemLayout L;
+    SmemLayout L;         // general kernel
+    SmemLayout Lf;        // specialised full-step kernel
     // ---- static tables (device)
     const uint16_t* apple_cell; // [n_apple] in-tile cell ids, row-major (harvest.py:22-26, cleanup.py:53-54)
     const uint16_t* waste_cell; // [n_waste] in-tile cell ids, row-major (cleanup.py:59-60)
@@ -132,7 +149,7 @@ struct ResetArgs {
 // Launchers implemented in ssd_step.cu.
 cudaError_t launch_step(const StepArgs& a, int threads, cudaStream_t stream);
 cudaError_t launch_reset(const ResetArgs& a, cudaStream_t stream);
-cudaError_t launch_pack_state(int B, int N, int H, int W, int Ws, int env_bytes, const uint8_t* grid_in, const int16_t* pos_in,
+cudaError_t launch_pack_state(int kind, int B, int N, int H, int W, int Ws, int env_bytes, const uint8_t* grid_in, const int16_t* pos_in,
                               const uint8_t* ori_in, uint8_t* grid, uint32_t* agents, cudaStream_t stream);
 cudaError_t launch_unpack_state(int B, int N, int H, int W, int Ws, int env_bytes, const uint8_t* grid, const uint32_t* agents,
                                 uint8_t* grid_out, int16_t* pos_out, uint8_t* ori_out, cudaStream_t stream);

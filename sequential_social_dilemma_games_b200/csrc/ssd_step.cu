@@ -27,6 +27,34 @@ __device__ __forceinline__ int tile_idx(const StepArgs& a, uint32_t key) {
     return static_cast<int>(key >> 8) * a.Ws + static_cast<int>(key & 255);
 }
 
+__device__ __forceinline__ bool is_apple(uint8_t c) { return (c & kCodeMask) == CB(C_APPLE); }
+
+// Harvest keeps min(3, #apple neighbours) in the low two bits of every ' ' / 'A' cell (ssd_internal.h).
+// Recompute it for the cell at `q` from the codes around it; called for the 8 neighbours of every
+// cell that gained or lost an apple.
+__device__ __forceinline__ void recount(uint8_t* q, int Ws) {
+    const uint8_t c = *q, code = c & kCodeMask;
+    if (code == CB(C_EMPTY) || code == CB(C_APPLE)) {
+        int n = is_apple(q[-Ws - 1]) + is_apple(q[-Ws]) + is_apple(q[-Ws + 1]) + is_apple(q[-1]) + is_apple(q[1]) +
+                is_apple(q[Ws - 1]) + is_apple(q[Ws]) + is_apple(q[Ws + 1]);
+        *q = static_cast<uint8_t>((c & 0xFC) | (n < 3 ? n : 3));
+    }
+}
+// All lanes call this with the warp-wide ballot of lanes whose cell base[my_off] just changed its apple
+// state (`base` is warp-uniform); lanes 0..7 refresh the eight neighbours of one event at a time.
+__device__ __forceinline__ void recount_events(uint32_t events, int my_off, uint8_t* base, int Ws) {
+    const int lane = threadIdx.x & 31;
+    const int t = lane & 7;
+    const int nb = (t < 3 ? -Ws - 1 + t : (t == 3 ? -1 : (t == 4 ? 1 : Ws - 6 + t)));  // -Ws-1,-Ws,-Ws+1,-1,+1,Ws-1,Ws,Ws+1
+    while (events) {
+        const int src = __ffs(events) - 1;
+        events &= events - 1;
+        const int off = __shfl_sync(0xffffffffu, my_off, src);
+        if (lane < 8) recount(base + off + nb, Ws);
+        __syncwarp();
+    }
+}
+
 struct Counters {  // per-lane event counts, reduced per warp at the end of the kernel
     int steps, eaten, fires, hits, cleaned, apples, waste;
 };
@@ -45,8 +73,8 @@ __device__ __forceinline__ int by_pos(const uint16_t* p, int N, uint32_t key) {
 
 // Literal emulation of the conflict resolution of update_moves (map_env.py:394-543) for one env,
 // run by a single lane.  S.pos / S.tgt hold positions and wall-clipped targets of the movers.
-template <bool TAPE>
-__device__ __noinline__ void moves_slow(const StepArgs& a, EnvScratch& S, MoveScratch& M, uint32_t movers, int local_env,
+template <bool TAPE, class ES>
+__device__ __noinline__ void moves_slow(const StepArgs& a, ES& S, MoveScratch& M, uint32_t movers, int local_env,
                                          const PhiloxKey& pk) {
     const int N = a.N;
     // mover list in action order (agent_moves is an insertion-ordered dict, map_env.py:400-412)
@@ -145,8 +173,8 @@ struct AgentLane {
 };
 
 // update_moves for one group of G lanes (= one env).  All 32 lanes of the warp call this.
-template <bool TAPE>
-__device__ __forceinline__ void moves_group(const StepArgs& a, EnvScratch& S, MoveScratch& M, const uint8_t* g, AgentLane& me, bool valid,
+template <bool TAPE, class ES>
+__device__ __forceinline__ void moves_group(const StepArgs& a, ES& S, MoveScratch& M, const uint8_t* g, AgentLane& me, bool valid,
                                             int al, int G, int local_env, const PhiloxKey& pk) {
     const int act = me.act;
     bool mover = false;
@@ -189,7 +217,7 @@ __device__ __forceinline__ void moves_group(const StepArgs& a, EnvScratch& S, Mo
     if (conf_all != 0) {  // warp-uniform branch: groups without a conflict just keep the barriers company
         if (conf != 0 && valid) { S.pos[al] = static_cast<uint16_t>(me.key); M.tgt[al] = static_cast<uint16_t>(tgt); }
         __syncwarp();
-        if (conf != 0 && al == 0) moves_slow<TAPE>(a, S, M, movers, local_env, pk);
+        if (conf != 0 && al == 0 && !(a.debug & 16)) moves_slow<TAPE, ES>(a, S, M, movers, local_env, pk);
         __syncwarp();
         if (conf != 0 && valid) me.key = S.pos[al];
     }
@@ -199,7 +227,8 @@ __device__ __forceinline__ void moves_group(const StepArgs& a, EnvScratch& S, Mo
 // its group.  The map is wall-enclosed (checked by ssd_create), so the reference's bounds test
 // (:615) can never fire before the wall test (:616).  Agent cells carry kFlag, so the position
 // table is only searched when a ray actually runs into somebody.  Returns the painted cell count.
-__device__ __forceinline__ int ray_walk(const StepArgs& a, EnvScratch& S, uint8_t* g, uint32_t key, int ori, int s,
+template <class ES>
+__device__ __forceinline__ int ray_walk(const StepArgs& a, ES& S, uint8_t* g, uint32_t key, int ori, int s,
                                         bool clean, int& upd, int& hits) {
     const int d0 = (ori == 1) - (ori == 3), d1 = (ori == 2) - (ori == 0);  // ORIENTATIONS map_env.py:19-22
     int r = static_cast<int>(key >> 8) + d0, c = static_cast<int>(key & 255) + d1;  // :608-613
@@ -232,27 +261,23 @@ __device__ __forceinline__ int ray_walk(const StepArgs& a, EnvScratch& S, uint8_
 template <bool TAPE>
 __device__ __forceinline__ void harvest_spawn(const StepArgs& a, uint8_t* g, const uint16_t* s_apple, uint32_t* list,
                                               int local_env, const PhiloxKey& pk, int lane, Counters& cnt) {
-    const int Ws = a.Ws, n_apple = a.n_apple;
+    const int n_apple = a.n_apple;
     constexpr uint8_t A = CB(C_APPLE);
     // One scan in row-major apple-point order (harvest.py:87-101).  The apple table is padded to a
     // multiple of 32 with a harmless interior cell, so every lane loads unconditionally.  `base`
-    // counts eligible points: the k-th eligible point consumes the k-th np.random.rand.  Only points
-    // whose spawn probability is not zero (n apple neighbours with SPAWN_PROB[n] != 0) can spawn; they
-    // are compacted into `list` as cell | n << 16 | draw index << 18 and drawn for afterwards.
+    // counts eligible points: the k-th eligible point consumes the k-th np.random.rand.  The number
+    // of apples in the 3x3 window (harvest.py:92-100) is cached in the low bits of the cell, so the
+    // scan is one byte load per point.  Only points with SPAWN_PROB[n] != 0 can spawn; they are
+    // compacted into `list` as cell | n << 16 | draw index << 18 and drawn for afterwards.
     int base = 0, n_need = 0;
 #pragma unroll 1
     for (int i0 = 0; i0 < n_apple; i0 += 32) {
         const int i = i0 + lane;
         const uint32_t cell = s_apple[i];
-        const uint8_t* q = g + cell;
-        const uint8_t c = q[0];
-        const bool el = (i < n_apple) & (c != A) & (c < kFlag);  // not an apple, no agent on it (harvest.py:90)
+        const uint8_t c = g[cell];
+        const bool el = (i < n_apple) & ((c & 0xFC) != A) & (c < kFlag);  // not an apple, no agent on it (harvest.py:90)
         const uint32_t m = __ballot_sync(0xffffffffu, el);
-        if (m == 0) continue;
-        // 3x3 window, j*j + k*k <= APPLE_RADIUS(2) (harvest.py:92-99); cells outside the map are 0 in the tile
-        int n = (q[-Ws - 1] == A) + (q[-Ws] == A) + (q[-Ws + 1] == A) + (q[-1] == A) + (q[1] == A) +
-                (q[Ws - 1] == A) + (q[Ws] == A) + (q[Ws + 1] == A);
-        n = n < 3 ? n : 3;
+        const int n = c & 3;
         const bool need = el & ((a.harvest_nz >> n) & 1);
         const uint32_t m2 = __ballot_sync(0xffffffffu, need);
         if (need) list[n_need + __popc(m2 & lanemask_lt())] = cell | static_cast<uint32_t>(n) << 16 |
@@ -261,18 +286,24 @@ __device__ __forceinline__ void harvest_spawn(const StepArgs& a, uint8_t* g, con
         n_need += __popc(m2);
     }
     if (TAPE && a.n_draws_out != nullptr && lane == 0) a.n_draws_out[local_env] = base;
-    __syncwarp();  // every read saw the pre-spawn grid; writes happen after the scan (harvest.py:72-73)
+    __syncwarp();  // every count was read from the pre-spawn grid; writes happen after the scan (harvest.py:72-73)
 #pragma unroll 1
     for (int j0 = 0; j0 < n_need; j0 += 32) {
         const int j = j0 + lane;
+        bool spawn = false;
+        uint32_t en = 0;
         if (j < n_need) {
-            const uint32_t en = list[j];
+            en = list[j];
             const int n = (en >> 16) & 3;
             const uint32_t k = en >> 18;
-            bool spawn;
             if (TAPE) spawn = a.tape_u[static_cast<size_t>(local_env) * a.u_stride + k] < a.harvest_p[n];
             else spawn = philox_u53(pk, a.spawn_stream, k) < a.harvest_thr[n];  // u < p  <=>  u53 < ceil(p * 2^53)
-            if (spawn) { g[en & 0xffffu] = A; ++cnt.apples; }
+            if (spawn) { g[en & 0xffffu] = static_cast<uint8_t>(A | n); ++cnt.apples; }
+        }
+        const uint32_t ms = __ballot_sync(0xffffffffu, spawn);
+        if (ms) {  // refresh the cached counts around the new apples
+            __syncwarp();
+            recount_events(ms, static_cast<int>(en & 0xffffu), g, a.Ws);
         }
     }
 }
@@ -398,8 +429,8 @@ __device__ __forceinline__ uint2 view_param(const StepArgs& a, const EnvScratch&
     return make_uint2(static_cast<uint32_t>(a0 + tile_off), (static_cast<uint32_t>(si) & 0xffffu) | static_cast<uint32_t>(sj) << 16);
 }
 
-__device__ __forceinline__ uint32_t cell_color(const uint32_t* s_color, uint8_t cell) {  // cell byte = code * 4
-    return *reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(s_color) + cell);
+__device__ __forceinline__ uint32_t cell_color(const uint32_t* s_color, uint8_t cell) {  // table indexed by the grid byte
+    return s_color[cell];
 }
 
 // One lane renders one row of one agent's view (V pixels = 3V bytes).  The warp owns `total_rows`
@@ -491,7 +522,7 @@ __device__ __forceinline__ uint8_t agent_cell(int i) {  // str(int(agent_id[-1])
 template <int KIND, bool TAPE, int VT>
 __global__ void __launch_bounds__(kMaxThreads) ssd_step_kernel(const __grid_constant__ StepArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ uint32_t s_color[kNumCodes];
+    __shared__ uint32_t s_color[kLutEntries];
     __shared__ int s_cta_stats[SSD_NUM_STATS];
     __shared__ int s_done;
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
@@ -500,7 +531,7 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_kernel(const __grid_cons
     uint16_t* s_apple = reinterpret_cast<uint16_t*>(smem + a.L.apple);
 
     // ---- CTA-shared tables, then the only CTA barrier of the kernel
-    if (tid < kNumCodes) s_color[tid] = a.color[tid];
+    for (int i = tid; i < kLutEntries; i += nthr) s_color[i] = a.color[i];
     if (tid < SSD_NUM_STATS) s_cta_stats[tid] = 0;
     if (tid == 0) s_done = 0;
     if (phases & SSD_PHASE_SPAWN)
@@ -564,12 +595,15 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_kernel(const __grid_cons
         __syncwarp();
         const int my_idx = tile_idx(a, me.key);
         if (phases & SSD_PHASE_CONSUME) {  // map_env.py:178-181, agent.py:177-183 / 216-222
-            const bool on_apple = valid && active && g[my_idx] == CB(C_APPLE);
+            const uint8_t under = g[my_idx];
+            const bool on_apple = valid && active && is_apple(under);
             // agents sharing a cell: the first one in agent order eats
             const uint32_t same = __match_any_sync(0xffffffffu, on_apple ? (me.key | static_cast<uint32_t>(gbase) << 16) : (0x80000000u | lane));
             __syncwarp();
-            if (on_apple && (__ffs(same) - 1) == lane) { g[my_idx] = CB(C_EMPTY); me.rew += 1; ++cnt.eaten; }
+            const bool ate = on_apple && (__ffs(same) - 1) == lane;
+            if (ate) { g[my_idx] = CB(C_EMPTY) | (under & 3); me.rew += 1; ++cnt.eaten; }
             __syncwarp();
+            if (KIND == SSD_KIND_HARVEST) recount_events(__ballot_sync(0xffffffffu, ate), static_cast<int>(g - tiles) + my_idx, tiles, a.Ws);
         }
         if ((phases & (SSD_PHASE_BEAMS | SSD_PHASE_SPAWN)) && valid && active) g[my_idx] |= kFlag;  // "an agent stands here"
         __syncwarp();
@@ -732,7 +766,7 @@ __host__ __device__ constexpr int row_words_min(int RB) {
 
 template <int VT>
 __device__ __forceinline__ void render_rows_tma(const uint2* s_view, const uint8_t* tiles, const uint32_t* s_color,
-                                                uint32_t* stage, uint8_t* dst, int total_rows) {
+                                                uint32_t* stage, uint8_t* dst, int total_rows, int debug) {
     constexpr int RB = 3 * VT;            // bytes per view row
     constexpr int CH = 32 * RB;           // bytes per chunk
     constexpr int NP = (RB + 3 + 3) / 4;  // words covering the row plus the next row's first pixel
@@ -747,14 +781,19 @@ __device__ __forceinline__ void render_rows_tma(const uint2* s_view, const uint8
     const uint32_t w0 = (o + 3) >> 2, w1 = (o + RB - 1) >> 2;
     const bool extra = static_cast<int>(w1 - w0) + 1 > MMIN;  // this lane owns MMIN + 1 words of every chunk
     uint32_t* st = stage + mis4 + w0;
-    const uint8_t* stage_b = reinterpret_cast<const uint8_t*>(stage);
-    const int n_chunks = (total_rows + 31) >> 5;
+    const int n_chunks = (total_rows + 31) >> 5;  // >= 2: a warp renders at least 4 * VT rows
     const int end_last = mis + (total_rows - (n_chunks - 1) * 32) * RB;  // valid image bytes of the last chunk (multiple of 4)
     const int hi_last = min(CH, end_last & ~15);
     uint8_t* out = dst - mis;  // 16-byte aligned image of chunk 0
+    const uint32_t stage32 = smem_u32(stage);
+    // where lane 31 parks the words that spill over a chunk: the head of the next image, or a dummy slot
+    uint32_t* const k1 = stage + (mis4 >= 1 ? mis4 - 1 : CH / 4 + 5);
+    uint32_t* const k2 = stage + (mis4 >= 2 ? mis4 - 2 : CH / 4 + 6);
+    uint32_t* const k3 = stage + (mis4 >= 3 ? mis4 - 3 : CH / 4 + 7);
+    int lo = mis != 0 ? 16 : 0;  // the first 16 - mis bytes of the slab leave with plain stores
     uint32_t c0 = 0, c1 = 0, c2 = 0;
 #pragma unroll 1
-    for (int c = 0; c < n_chunks; ++c, out += CH) {
+    for (int c = 0; c < n_chunks; ++c) {
         const int R = min(c * 32 + lane, total_rows - 1);  // lanes past the end redo the last row; their words are never copied out
         const int ga = R / VT, i = R - ga * VT;            // rows are ordered (env, agent, i)
         uint32_t X[VT + 2];
@@ -777,51 +816,44 @@ __device__ __forceinline__ void render_rows_tma(const uint2* s_view, const uint8
         uint32_t Q[MMIN + 1];
 #pragma unroll
         for (int m = 0; m <= MMIN; ++m) Q[m] = __funnelshift_r(P[m], P[m + 1], d8);
-        if (c != 0) {  // the previous chunk's bulk store must have finished READING the buffer
-            if (lane == 0) bulk_wait_read();
-            __syncwarp();
-        }
+        bulk_wait_read();  // the previous chunk's bulk store (issued by lane 0) must have finished READING the buffer
+        __syncwarp();
 #pragma unroll
         for (int m = 0; m < MMIN; ++m) st[m] = Q[m];
         if (extra) st[MMIN] = Q[MMIN];
-        if (lane == 31 && c != 0) {  // head of this chunk's image = the words that spilled over the previous chunk
-            if (mis4 >= 1) stage[mis4 - 1] = c2;
-            if (mis4 >= 2) stage[mis4 - 2] = c1;
-            if (mis4 >= 3) stage[mis4 - 3] = c0;
-        }
+        if (lane == 31) { *k1 = c2; *k2 = c1; *k3 = c0; }  // head of this image = spill of the previous chunk (unused for c == 0)
         c0 = Q[M31 - 3]; c1 = Q[M31 - 2]; c2 = Q[M31 - 1];
         fence_async_smem();
         __syncwarp();
-        if (lane == 0) {
-            const int lo = (c == 0 && mis != 0) ? 16 : 0;
-            const int hi = (c == n_chunks - 1) ? hi_last : CH;
-            if (hi > lo) {
-                bulk_s2g(out + lo, stage_b + lo, static_cast<uint32_t>(hi - lo));
-                bulk_commit();
-            }
+        const int hi = (c == n_chunks - 1) ? hi_last : CH;
+        if (lane == 0 && !(debug & 1)) {
+            bulk_s2g_u32(out + lo, stage32 + lo, static_cast<uint32_t>(hi - lo));
+            bulk_commit();
         }
         if (c == 0 && lane >= mis4 && lane < 4 && mis != 0)  // first bytes of the slab
             *reinterpret_cast<uint32_t*>(out + 4 * lane) = stage[lane];
+        lo = 0;
+        out += CH;
     }
     {   // last bytes of the slab (out was advanced once past the last chunk)
         const int off = hi_last + 4 * lane;
         if (off < end_last) *reinterpret_cast<uint32_t*>(out - CH + off) = stage[off >> 2];
     }
-    if (lane == 0) bulk_wait_read();  // shared memory must outlive the last bulk read
+    bulk_wait_read();  // shared memory must outlive the last bulk read
 }
 
 template <int KIND, bool TAPE, int VT>
 __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid_constant__ StepArgs a) {
     constexpr int G = 8, EPW = 4;
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ uint32_t s_color[kNumCodes];
+    __shared__ uint32_t s_color[kLutEntries];
     __shared__ int s_cta_stats[SSD_NUM_STATS];
     __shared__ int s_done;
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
     const int N = a.N;
-    uint16_t* s_apple = reinterpret_cast<uint16_t*>(smem + a.L.apple);
+    uint16_t* s_apple = reinterpret_cast<uint16_t*>(smem + a.Lf.apple);
 
-    if (tid < kNumCodes) s_color[tid] = a.color[tid];
+    for (int i = tid; i < kLutEntries; i += nthr) s_color[i] = a.color[i];
     if (tid < SSD_NUM_STATS) s_cta_stats[tid] = 0;
     if (tid == 0) s_done = 0;
     if (KIND != SSD_KIND_PLAIN)
@@ -829,10 +861,10 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
         for (int i = tid; i < ((a.n_apple + 31) & ~31); i += nthr) s_apple[i] = i < a.n_apple ? a.apple_cell[i] : static_cast<uint16_t>(a.Ws + 1);
     __syncthreads();
 
-    uint8_t* wbase = smem + a.L.warp0 + warp * a.L.warp_stride;
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(wbase + a.L.w_mbar);
-    uint8_t* tiles = wbase + a.L.w_tiles;
-    EnvScratch* envs = reinterpret_cast<EnvScratch*>(wbase + a.L.w_env);
+    uint8_t* wbase = smem + a.Lf.warp0 + warp * a.Lf.warp_stride;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(wbase + a.Lf.w_mbar);
+    uint8_t* tiles = wbase + a.Lf.w_tiles;
+    FastScratch* envs = reinterpret_cast<FastScratch*>(wbase + a.Lf.w_env);
     const int tile_pitch = a.env_bytes + a.pad_bytes;
     const int we = a.env_begin + (blockIdx.x * nwarps + warp) * EPW;  // the launcher only sends whole warps
     Counters cnt = {0, 0, 0, 0, 0, 0, 0};
@@ -852,7 +884,7 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
         }
         // agent words and actions travel while the tiles do
         const int al = lane & (G - 1), gbase = lane & ~(G - 1), j = lane >> 3;
-        EnvScratch& S = envs[j];
+        FastScratch& S = envs[j];
         uint8_t* g = tiles + a.pad_bytes + j * tile_pitch;
         const int e = we + j;
         const bool valid = al < N;
@@ -874,20 +906,24 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
         __syncwarp();
 
         // ---- phase A: one lane per agent
-        moves_group<TAPE>(a, S, reinterpret_cast<MoveScratch*>(wbase + a.L.w_union)[j], g, me, valid, al, G, e, pk);
+        moves_group<TAPE>(a, S, reinterpret_cast<MoveScratch*>(wbase + a.Lf.w_union)[j], g, me, valid, al, G, e, pk);
         cnt.steps += (al == 0);
         if (valid) S.pos[al] = static_cast<uint16_t>(me.key);
         const int my_idx = tile_idx(a, me.key);
         {   // consume, map_env.py:178-181: of agents sharing a cell (appendix A.2 quirk) the first in agent order eats
-            const bool on_apple = valid && g[my_idx] == CB(C_APPLE);
+            const uint8_t under = g[my_idx];
+            const bool on_apple = valid && is_apple(under);
             const uint32_t same = __match_any_sync(0xffffffffu, on_apple ? (me.key | static_cast<uint32_t>(gbase) << 16) : (0x80000000u | lane));
-            if (on_apple && (__ffs(same) - 1) == lane) { g[my_idx] = CB(C_EMPTY); me.rew += 1; ++cnt.eaten; }
+            const bool ate = on_apple && (__ffs(same) - 1) == lane;
+            if (ate) { g[my_idx] = CB(C_EMPTY) | (under & 3); me.rew += 1; ++cnt.eaten; }
+            __syncwarp();
+            if (KIND == SSD_KIND_HARVEST) recount_events(__ballot_sync(0xffffffffu, ate), static_cast<int>(g - tiles) + my_idx, tiles, a.Ws);
         }
         __syncwarp();
         if (KIND != SSD_KIND_PLAIN && valid) g[my_idx] |= kFlag;  // "an agent stands here"
         __syncwarp();
         uint32_t fmask = 0;  // bit (8 * env slot + agent): that agent fires
-        if (KIND != SSD_KIND_PLAIN) {  // update_custom_moves map_env.py:545-552, agents fire in action (= agent) order
+        if (KIND != SSD_KIND_PLAIN && !(a.debug & 8)) {  // update_custom_moves map_env.py:545-552, agents fire in action (= agent) order
             fmask = __ballot_sync(0xffffffffu, me.act == 7 || (KIND == SSD_KIND_CLEANUP && me.act == 8));
             for (int k = 0; k < N; ++k) {
                 if (!((fmask >> k) & 0x01010101u)) continue;  // nobody in this warp fires in slot k
@@ -915,8 +951,8 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
         }
 
         // ---- phase B: the whole warp per env
-        if (KIND != SSD_KIND_PLAIN) {
-            void* scratch = wbase + a.L.w_union;
+        if (KIND != SSD_KIND_PLAIN && !(a.debug & 4)) {
+            void* scratch = wbase + a.Lf.w_union;
 #pragma unroll 1
             for (int q = 0; q < EPW; ++q) {
                 pk.env = static_cast<uint32_t>(a.env_id0 + static_cast<uint64_t>(we + q));
@@ -931,7 +967,7 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
         }
 
         // ---- store: grid tiles back to HBM
-        {
+        if (!(a.debug & 64)) {
             const int n16 = a.env_bytes >> 4;
 #pragma unroll
             for (int q = 0; q < EPW; ++q) {
@@ -968,7 +1004,7 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
                     __syncwarp();
                 }
             }
-            uint2* s_view = reinterpret_cast<uint2*>(wbase + a.L.w_union);
+            uint2* s_view = reinterpret_cast<uint2*>(wbase + a.Lf.w_union);
             if (valid) {  // rot90 folded into strides, see view_param
                 const int pr = me.key >> 8, pc = me.key & 255, r = a.r, Ws = a.Ws;
                 const int k = (4 - me.ori) & 3;
@@ -981,13 +1017,14 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
                                                 (static_cast<uint32_t>(si) & 0xffffu) | static_cast<uint32_t>(sj) << 16);
             }
             __syncwarp();
-            render_rows_tma<VT>(s_view, tiles, s_color, reinterpret_cast<uint32_t*>(wbase + a.L.w_union + a.L.u_stage),
-                                a.obs + static_cast<size_t>(we) * a.obs_env, EPW * N * VT);
+            if (!(a.debug & 2))
+            render_rows_tma<VT>(s_view, tiles, s_color, reinterpret_cast<uint32_t*>(wbase + a.Lf.w_union + a.Lf.u_stage),
+                                a.obs + static_cast<size_t>(we) * a.obs_env, EPW * N * VT, a.debug);
         }
     }
 
     // ---- stats: warp -> CTA -> one set of global atomics per CTA (issued by the last warp to finish)
-    if (a.stats != nullptr) {
+    if (a.stats != nullptr && !(a.debug & 32)) {
         const int v[7] = {cnt.steps, cnt.eaten, cnt.fires, cnt.hits, cnt.cleaned, cnt.apples, cnt.waste};
         const int slot[7] = {0, 2, 3, 4, 5, 6, 7};
 #pragma unroll
@@ -1072,12 +1109,28 @@ __device__ __forceinline__ uint8_t dev_cell_to_ascii(uint8_t cell) {
         default: return (code >= C_AGENT && code < C_AGENT + 9) ? static_cast<uint8_t>('1' + code - C_AGENT) : static_cast<uint8_t>('?');
     }
 }
-__global__ void pack_state_kernel(int B, int N, int H, int W, int Ws, int env_bytes, const uint8_t* grid_in, const int16_t* pos_in,
+__global__ void pack_state_kernel(int kind, int B, int N, int H, int W, int Ws, int env_bytes, const uint8_t* grid_in, const int16_t* pos_in,
                                   const uint8_t* ori_in, uint8_t* grid, uint32_t* agents) {
     const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i < static_cast<size_t>(B) * env_bytes) {
-        const size_t b = i / env_bytes, q = i % env_bytes, r = q / Ws, c = q % Ws;
-        grid[i] = (r < static_cast<size_t>(H) && c < static_cast<size_t>(W)) ? dev_ascii_to_cell(grid_in[(b * H + r) * W + c]) : 0;
+        const size_t b = i / env_bytes, q = i % env_bytes;
+        const int r = static_cast<int>(q / Ws), c = static_cast<int>(q % Ws);
+        uint8_t cell = 0;
+        if (r < H && c < W) {
+            const uint8_t* gi = grid_in + b * H * W;
+            const uint8_t ch = gi[r * W + c];
+            cell = dev_ascii_to_cell(ch);
+            if (kind == SSD_KIND_HARVEST && (ch == ' ' || ch == 'A')) {  // cached neighbourhood count (ssd_internal.h)
+                int n = 0;
+                for (int dr = -1; dr <= 1; ++dr)
+                    for (int dc = -1; dc <= 1; ++dc) {
+                        const int rr = r + dr, cc = c + dc;
+                        n += (dr || dc) && rr >= 0 && rr < H && cc >= 0 && cc < W && gi[rr * W + cc] == 'A';
+                    }
+                cell |= static_cast<uint8_t>(n < 3 ? n : 3);
+            }
+        }
+        grid[i] = cell;
     }
     if (i < static_cast<size_t>(B) * N)
         agents[i] = (pos_in[2 * i] & 255) | (pos_in[2 * i + 1] & 255) << 8 | static_cast<uint32_t>(ori_in[i] & 3) << 16;
@@ -1205,10 +1258,10 @@ cudaError_t launch_reset(const ResetArgs& a, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
-cudaError_t launch_pack_state(int B, int N, int H, int W, int Ws, int env_bytes, const uint8_t* grid_in, const int16_t* pos_in,
+cudaError_t launch_pack_state(int kind, int B, int N, int H, int W, int Ws, int env_bytes, const uint8_t* grid_in, const int16_t* pos_in,
                               const uint8_t* ori_in, uint8_t* grid, uint32_t* agents, cudaStream_t stream) {
     const size_t n = static_cast<size_t>(B) * env_bytes;
-    pack_state_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(B, N, H, W, Ws, env_bytes, grid_in, pos_in, ori_in, grid, agents);
+    pack_state_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(kind, B, N, H, W, Ws, env_bytes, grid_in, pos_in, ori_in, grid, agents);
     return cudaGetLastError();
 }
 cudaError_t launch_unpack_state(int B, int N, int H, int W, int Ws, int env_bytes, const uint8_t* grid, const uint32_t* agents,
