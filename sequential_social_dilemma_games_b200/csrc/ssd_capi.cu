@@ -91,7 +91,7 @@ ssd::SmemLayout make_layout(const SsdEnv& h, int threads, bool fast = false) {
     ssd::SmemLayout L{};
     const uint32_t G = h.cfg.num_agents <= 8 ? 8 : 16, epw = 32 / G;
     uint32_t off = 0;
-    L.apple = off; off += up16(((h.n_apple + 31) & ~31) * 2);  // padded to whole warps
+    L.apple = off; off += up16(((h.n_apple + 63) & ~63) * 2);  // padded to two whole warps
     L.warp0 = off;
     uint32_t w = 0;
     L.w_mbar = w; w += 16;
@@ -102,7 +102,8 @@ ssd::SmemLayout make_layout(const SsdEnv& h, int threads, bool fast = false) {
     const uint32_t u_render = L.u_stage + up16(32u * 3u * h.V) + 32;       // + staging of 32 view rows, spill and dummy words
     const uint32_t u_spawn = up16(std::max(h.n_apple * 4, h.n_waste * 4)); // need-list / waste keys
     const uint32_t u_moves = epw * sizeof(ssd::MoveScratch);
-    w += std::max(u_render, std::max(u_spawn, u_moves));
+    L.u_words = std::max(u_render, std::max(u_spawn, u_moves)) / 4;
+    w += 4 * L.u_words;
     if (const char* x = getenv("SSD_EXTRA_SMEM")) w += up16(static_cast<uint32_t>(atoi(x)));  // occupancy experiments
     L.warp_stride = w;
     L.total = off + (threads / 32) * w;
@@ -230,7 +231,7 @@ int ssd_create(const SsdConfig* cfg, ssd_handle* out) {
         }
     }
     h->n_apple = static_cast<int>(apple.size()); h->n_waste = static_cast<int>(waste.size()); h->n_spawn = static_cast<int>(spawn.size());
-    if (h->n_apple >= 0x4000) { delete h; return fail(SSD_ERR_UNSUPPORTED, "too many apple points"); }
+    if (h->n_apple >= 0x1000) { delete h; return fail(SSD_ERR_UNSUPPORTED, "too many apple points"); }
     if (cfg->kind == SSD_KIND_CLEANUP && cfg->potential_waste_area < h->n_waste) {
         delete h;
         return fail(SSD_ERR_INVALID, "potential_waste_area %d smaller than the number of 'H'/'R' cells %d", cfg->potential_waste_area, h->n_waste);

@@ -70,7 +70,7 @@ static_assert(sizeof(EnvScratch) % 16 == 0, "EnvScratch must stay 16-byte sized"
 // The same for the specialised full-step kernel (N <= 8, actions in agent order).
 struct FastScratch {
     uint16_t pos[8];
-    int16_t rew[8];
+    int32_t rew[8];   // 32-bit: rays of different shooters add their -50 with shared-memory atomics
     uint8_t raylen[24];
     uint8_t order[8];
 };
@@ -93,6 +93,7 @@ struct SmemLayout {
     uint32_t warp0, warp_stride;                     // first warp region, bytes per warp
     uint32_t w_mbar, w_tiles, w_env, w_union;        // offsets inside a warp region
     uint32_t u_stage;                                // staging buffer inside the union (after the view params)
+    uint32_t u_words;                                // 32-bit words in the union
     uint32_t total;
 };
 

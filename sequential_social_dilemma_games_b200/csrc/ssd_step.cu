@@ -227,7 +227,7 @@ __device__ __forceinline__ void moves_group(const StepArgs& a, ES& S, MoveScratc
 // its group.  The map is wall-enclosed (checked by ssd_create), so the reference's bounds test
 // (:615) can never fire before the wall test (:616).  Agent cells carry kFlag, so the position
 // table is only searched when a ray actually runs into somebody.  Returns the painted cell count.
-template <class ES>
+template <class ES, bool ATOMIC = false>
 __device__ __forceinline__ int ray_walk(const StepArgs& a, ES& S, uint8_t* g, uint32_t key, int ori, int s,
                                         bool clean, int& upd, int& hits) {
     const int d0 = (ori == 1) - (ori == 3), d1 = (ori == 2) - (ori == 0);  // ORIENTATIONS map_env.py:19-22
@@ -242,7 +242,11 @@ __device__ __forceinline__ int ray_walk(const StepArgs& a, ES& S, uint8_t* g, ui
         if (cell == CB(C_WALL)) break;                          // :616
         const bool isH = clean && cell == CB(C_WASTE);
         if (raw & kFlag) {                                      // :621-629 agents absorb beams
-            if (!clean) { S.rew[by_pos(S.pos, a.N, static_cast<uint32_t>(r << 8 | c))] -= 50; ++hits; }  // agent.py:166-168, 212-214
+            if (!clean) {  // agent.py:166-168, 212-214
+                const int v = by_pos(S.pos, a.N, static_cast<uint32_t>(r << 8 | c));
+                if constexpr (ATOMIC) atomicAdd(&S.rew[v], -50); else S.rew[v] -= 50;
+                ++hits;
+            }
             ++n;                                                // :624
             if (isH) upd = p;                                   // :625-628
             break;
@@ -298,7 +302,7 @@ __device__ __forceinline__ void harvest_spawn(const StepArgs& a, uint8_t* g, con
             const uint32_t k = en >> 18;
             if (TAPE) spawn = a.tape_u[static_cast<size_t>(local_env) * a.u_stride + k] < a.harvest_p[n];
             else spawn = philox_u53(pk, a.spawn_stream, k) < a.harvest_thr[n];  // u < p  <=>  u53 < ceil(p * 2^53)
-            if (spawn) { g[en & 0xffffu] = static_cast<uint8_t>(A | n); ++cnt.apples; }
+            if (spawn) { g[en & 0xffffu] = static_cast<uint8_t>(A | (g[en & 0xffffu] & 3)); ++cnt.apples; }  // keep the CURRENT cached count
         }
         const uint32_t ms = __ballot_sync(0xffffffffu, spawn);
         if (ms) {  // refresh the cached counts around the new apples
@@ -306,6 +310,79 @@ __device__ __forceinline__ void harvest_spawn(const StepArgs& a, uint8_t* g, con
             recount_events(ms, static_cast<int>(en & 0xffffu), g, a.Ws);
         }
     }
+}
+
+// spawn_apples for all four envs of a warp (specialised kernel).  The scans run env by env, two groups of
+// 32 apple points per trip so that their loads overlap; the candidates of ALL envs go into one list
+// (cell | n << 16 | env slot << 18 | draw index << 20), so the Philox draws of the whole warp are one
+// or two passes instead of one per env.  A list that could overflow is drained between two scans --
+// never inside one: every count must be read from the pre-spawn grid of its env.
+template <bool TAPE>
+__device__ __forceinline__ void harvest_drain(const StepArgs& a, uint8_t* tiles, int tile_pitch, const uint32_t* list, int n_list,
+                                              int we, PhiloxKey pk, int lane, Counters& cnt) {
+    constexpr uint8_t A = CB(C_APPLE);
+    __syncwarp();
+#pragma unroll 1
+    for (int j0 = 0; j0 < n_list; j0 += 32) {
+        const int j = j0 + lane;
+        bool spawn = false;
+        int off = 0;
+        if (j < n_list) {
+            const uint32_t en = list[j];
+            const int n = (en >> 16) & 3, slot = (en >> 18) & 3;
+            const uint32_t k = en >> 20;
+            off = a.pad_bytes + slot * tile_pitch + static_cast<int>(en & 0xffffu);
+            if (TAPE) {
+                spawn = a.tape_u[static_cast<size_t>(we + slot) * a.u_stride + k] < a.harvest_p[n];
+            } else {
+                pk.env = static_cast<uint32_t>(a.env_id0 + static_cast<uint64_t>(we + slot));
+                spawn = philox_u53(pk, a.spawn_stream, k) < a.harvest_thr[n];  // u < p  <=>  u53 < ceil(p * 2^53)
+            }
+            if (spawn) { tiles[off] = static_cast<uint8_t>(A | (tiles[off] & 3)); ++cnt.apples; }  // keep the CURRENT cached count: an earlier batch may have refreshed it
+        }
+        const uint32_t ms = __ballot_sync(0xffffffffu, spawn);
+        if (ms) {  // refresh the cached counts around the new apples
+            __syncwarp();
+            recount_events(ms, off, tiles, a.Ws);
+        }
+    }
+    __syncwarp();
+}
+
+template <bool TAPE>
+__device__ __forceinline__ void harvest_spawn_warp(const StepArgs& a, uint8_t* tiles, int tile_pitch, const uint16_t* __restrict__ s_apple,
+                                                   uint32_t* __restrict__ list, int cap, int we, const PhiloxKey& pk, int lane, Counters& cnt) {
+    const int n_apple = a.n_apple;
+    constexpr uint8_t A = CB(C_APPLE);
+    const uint32_t lt = lanemask_lt();
+    int n_list = 0;
+#pragma unroll 1
+    for (int q = 0; q < 4; ++q) {
+        if (n_list + n_apple > cap) { harvest_drain<TAPE>(a, tiles, tile_pitch, list, n_list, we, pk, lane, cnt); n_list = 0; }
+        const uint8_t* __restrict__ g = tiles + a.pad_bytes + q * tile_pitch;
+        int base = 0;
+#pragma unroll 1
+        for (int i0 = 0; i0 < n_apple; i0 += 64) {  // the table is padded to a multiple of 64 points
+            const int i = i0 + lane;
+            const uint32_t cell0 = s_apple[i], cell1 = s_apple[i + 32];
+            const uint8_t c0 = g[cell0], c1 = g[cell1];
+            const bool el0 = (i < n_apple) & ((c0 & 0xFC) != A) & (c0 < kFlag);  // not an apple, no agent on it (harvest.py:90)
+            const bool el1 = (i + 32 < n_apple) & ((c1 & 0xFC) != A) & (c1 < kFlag);
+            const uint32_t m0 = __ballot_sync(0xffffffffu, el0), m1 = __ballot_sync(0xffffffffu, el1);
+            const int n0 = c0 & 3, n1 = c1 & 3;  // cached count of apples in the 3x3 window (harvest.py:92-100)
+            const bool need0 = el0 & ((a.harvest_nz >> n0) & 1), need1 = el1 & ((a.harvest_nz >> n1) & 1);
+            const uint32_t w0 = __ballot_sync(0xffffffffu, need0), w1 = __ballot_sync(0xffffffffu, need1);
+            const int base1 = base + __popc(m0), nl1 = n_list + __popc(w0);
+            if (need0) list[n_list + __popc(w0 & lt)] = cell0 | static_cast<uint32_t>(n0) << 16 | static_cast<uint32_t>(q) << 18 |
+                                                          static_cast<uint32_t>(base + __popc(m0 & lt)) << 20;
+            if (need1) list[nl1 + __popc(w1 & lt)] = cell1 | static_cast<uint32_t>(n1) << 16 | static_cast<uint32_t>(q) << 18 |
+                                                      static_cast<uint32_t>(base1 + __popc(m1 & lt)) << 20;
+            base = base1 + __popc(m1);
+            n_list = nl1 + __popc(w1);
+        }
+        if (TAPE && a.n_draws_out != nullptr && lane == 0) a.n_draws_out[we + q] = base;
+    }
+    harvest_drain<TAPE>(a, tiles, tile_pitch, list, n_list, we, pk, lane, cnt);
 }
 
 template <bool TAPE>
@@ -535,7 +612,7 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_kernel(const __grid_cons
     if (tid < SSD_NUM_STATS) s_cta_stats[tid] = 0;
     if (tid == 0) s_done = 0;
     if (phases & SSD_PHASE_SPAWN)
-        for (int i = tid; i < ((a.n_apple + 31) & ~31); i += nthr) s_apple[i] = i < a.n_apple ? a.apple_cell[i] : static_cast<uint16_t>(a.Ws + 1);
+        for (int i = tid; i < ((a.n_apple + 63) & ~63); i += nthr) s_apple[i] = i < a.n_apple ? a.apple_cell[i] : static_cast<uint16_t>(a.Ws + 1);
     __syncthreads();
 
     // ---- this warp's envs
@@ -858,7 +935,7 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
     if (tid == 0) s_done = 0;
     if (KIND != SSD_KIND_PLAIN)
 #pragma unroll 1
-        for (int i = tid; i < ((a.n_apple + 31) & ~31); i += nthr) s_apple[i] = i < a.n_apple ? a.apple_cell[i] : static_cast<uint16_t>(a.Ws + 1);
+        for (int i = tid; i < ((a.n_apple + 63) & ~63); i += nthr) s_apple[i] = i < a.n_apple ? a.apple_cell[i] : static_cast<uint16_t>(a.Ws + 1);
     __syncthreads();
 
     uint8_t* wbase = smem + a.Lf.warp0 + warp * a.Lf.warp_stride;
@@ -923,8 +1000,36 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
         if (KIND != SSD_KIND_PLAIN && valid) g[my_idx] |= kFlag;  // "an agent stands here"
         __syncwarp();
         uint32_t fmask = 0;  // bit (8 * env slot + agent): that agent fires
-        if (KIND != SSD_KIND_PLAIN && !(a.debug & 8)) {  // update_custom_moves map_env.py:545-552, agents fire in action (= agent) order
-            fmask = __ballot_sync(0xffffffffu, me.act == 7 || (KIND == SSD_KIND_CLEANUP && me.act == 8));
+        uint32_t* const fire_list = reinterpret_cast<uint32_t*>(wbase + a.Lf.w_union);
+        const int ray_f = lane / 3, ray_s = lane - 3 * ray_f;  // Harvest: ray lane -> (firing agent of the round, ray)
+        uint32_t fire_ent = 0;
+        if (KIND == SSD_KIND_HARVEST && !(a.debug & 8)) {
+            // update_custom_moves map_env.py:545-552.  Harvest has only 'F' beams: they change no cell, so the
+            // firing order is irrelevant and the rays of ALL firing agents of the warp walk at once, 3 lanes each.
+            const bool fire_me = me.act == 7;
+            fmask = __ballot_sync(0xffffffffu, fire_me);
+            if (fmask) {
+                fire_ent = me.key | static_cast<uint32_t>(me.ori) << 16 | static_cast<uint32_t>(j) << 18 | static_cast<uint32_t>(al) << 21;
+                if (fire_me) { fire_list[__popc(fmask & lanemask_lt())] = fire_ent; me.rew -= 1; ++cnt.fires; }  // fire_beam agent.py:170-172
+                __syncwarp();
+                const int nf = __popc(fmask);
+#pragma unroll 1
+                for (int f0 = 0; f0 < nf; f0 += 10) {
+                    if (lane < 30 && f0 + ray_f < nf) {
+                        const uint32_t en = fire_list[f0 + ray_f];
+                        const int slot = (en >> 18) & 3, ag = en >> 21;
+                        int upd = -1, hits = 0;
+                        const int n = ray_walk<FastScratch, true>(a, envs[slot], tiles + a.pad_bytes + slot * tile_pitch, en & 0xffffu,
+                                                                  (en >> 16) & 3, ray_s, false, upd, hits);
+                        envs[slot].raylen[ag * 3 + ray_s] = static_cast<uint8_t>(n);
+                        cnt.hits += hits;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        if (KIND == SSD_KIND_CLEANUP && !(a.debug & 8)) {  // firing order matters: a CLEAN beam turns 'H' into 'R' for the next one
+            fmask = __ballot_sync(0xffffffffu, me.act == 7 || me.act == 8);
             for (int k = 0; k < N; ++k) {
                 if (!((fmask >> k) & 0x01010101u)) continue;  // nobody in this warp fires in slot k
                 const bool fire = (fmask >> (gbase + k)) & 1u;
@@ -953,14 +1058,15 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
         // ---- phase B: the whole warp per env
         if (KIND != SSD_KIND_PLAIN && !(a.debug & 4)) {
             void* scratch = wbase + a.Lf.w_union;
+            if (KIND == SSD_KIND_HARVEST) {
+                harvest_spawn_warp<TAPE>(a, tiles, tile_pitch, s_apple, static_cast<uint32_t*>(scratch), a.Lf.u_words, we, pk, lane, cnt);
+            } else {
 #pragma unroll 1
-            for (int q = 0; q < EPW; ++q) {
-                pk.env = static_cast<uint32_t>(a.env_id0 + static_cast<uint64_t>(we + q));
-                if (KIND == SSD_KIND_HARVEST)
-                    harvest_spawn<TAPE>(a, tiles + a.pad_bytes + q * tile_pitch, s_apple, static_cast<uint32_t*>(scratch), we + q, pk, lane, cnt);
-                else
+                for (int q = 0; q < EPW; ++q) {
+                    pk.env = static_cast<uint32_t>(a.env_id0 + static_cast<uint64_t>(we + q));
                     cleanup_spawn<TAPE>(a, tiles + a.pad_bytes + q * tile_pitch, s_apple, static_cast<uint32_t*>(scratch), we + q, pk, lane, cnt);
-                __syncwarp();
+                    __syncwarp();
+                }
             }
             if (valid) g[my_idx] &= 0x7F;  // agents sharing a cell all write the same byte
             __syncwarp();
@@ -984,7 +1090,28 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
             const uint32_t same = __match_any_sync(0xffffffffu, valid ? (me.key | static_cast<uint32_t>(gbase) << 16) : (0x80000000u | lane));
             if (valid && (31 - __clz(same)) == lane) g[my_idx] = agent_cell(al);  // the last agent on a cell wins
             __syncwarp();
-            if (KIND != SSD_KIND_PLAIN) {  // beams in firing order: a later beam overwrites an earlier one
+            if (KIND == SSD_KIND_HARVEST && fmask) {  // all beams are 'F': the painting order is irrelevant
+                if ((fmask >> lane) & 1u) fire_list[__popc(fmask & lanemask_lt())] = fire_ent;  // the union was reused by the spawn pass
+                __syncwarp();
+                const int nf = __popc(fmask);
+#pragma unroll 1
+                for (int f0 = 0; f0 < nf; f0 += 10) {
+                    if (lane < 30 && f0 + ray_f < nf) {
+                        const uint32_t en = fire_list[f0 + ray_f];
+                        const int slot = (en >> 18) & 3, ag = en >> 21, ori = (en >> 16) & 3;
+                        const int d0 = (ori == 1) - (ori == 3), d1 = (ori == 2) - (ori == 0);
+                        int r = static_cast<int>((en >> 8) & 255) + d0, c = static_cast<int>(en & 255) + d1;
+                        if (ray_s == 1) { r += -d1 - d0; c += d0 - d1; }
+                        if (ray_s == 2) { r -= -d1 + d0; c -= d0 + d1; }
+                        const int n = envs[slot].raylen[ag * 3 + ray_s], dp = d0 * a.Ws + d1;
+                        uint8_t* p = tiles + a.pad_bytes + slot * tile_pitch + r * a.Ws + c;
+#pragma unroll 1
+                        for (int i = 0; i < n; ++i) { *p = CB(C_FIRE); p += dp; }
+                    }
+                }
+                __syncwarp();
+            }
+            if (KIND == SSD_KIND_CLEANUP) {  // beams in firing order: a later beam overwrites an earlier one
                 for (int k = 0; k < N; ++k) {
                     if (!((fmask >> k) & 0x01010101u)) continue;
                     const uint32_t key_k = __shfl_sync(0xffffffffu, me.key, k, G);
@@ -1025,12 +1152,12 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
 
     // ---- stats: warp -> CTA -> one set of global atomics per CTA (issued by the last warp to finish)
     if (a.stats != nullptr && !(a.debug & 32)) {
-        const int v[7] = {cnt.steps, cnt.eaten, cnt.fires, cnt.hits, cnt.cleaned, cnt.apples, cnt.waste};
-        const int slot[7] = {0, 2, 3, 4, 5, 6, 7};
-#pragma unroll
-        for (int i = 0; i < 7; ++i) {
-            const int tot = __reduce_add_sync(0xffffffffu, v[i]);
-            if (lane == 0 && tot) atomicAdd(&s_cta_stats[slot[i]], tot);
+        // per-warp totals are small (4 envs): two packed reductions carry all seven counters
+        const uint32_t r0 = __reduce_add_sync(0xffffffffu, static_cast<uint32_t>(cnt.steps | cnt.eaten << 8 | cnt.fires << 16 | cnt.hits << 24));
+        const uint32_t r1 = __reduce_add_sync(0xffffffffu, static_cast<uint32_t>(cnt.cleaned | cnt.apples << 10 | cnt.waste << 20));
+        if (lane < 7) {
+            const uint32_t v = lane < 4 ? (r0 >> (8 * lane)) & 255u : (lane == 6 ? r1 >> 20 : (r1 >> (10 * (lane - 4))) & 1023u);
+            if (v) atomicAdd(&s_cta_stats[lane == 0 ? 0 : lane + 1], static_cast<int>(v));
         }
         __syncwarp();
         int last = 0;

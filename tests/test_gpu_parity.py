@@ -101,13 +101,17 @@ def _random_actions(rng, cfg, B, p_clean=0.0):
 
 
 @pytest.mark.parametrize("game,B,steps,N,amap", [("harvest", 2048, 60, 5, None), ("cleanup", 2048, 90, 5, None),
-                                                 ("cleanup", 512, 40, 10, "tiled"), ("harvest", 333, 30, 5, None)])
+                                                 ("cleanup", 512, 40, 10, "tiled"), ("harvest", 333, 30, 5, None),
+                                                 ("harvest", 1024, 800, 5, None), ("harvest", 258, 400, 8, "dense")])
 def test_philox_vs_oracle(game, B, steps, N, amap):
-    """Production mode (Philox, device reset) against the CPU oracle on the same seeds."""
+    """Production mode (Philox, device reset) against the CPU oracle on the same seeds.  The long Harvest
+    cases exist for the neighbour counts the device caches in the grid bytes: a stale count only shows
+    up many steps later, when the cell is empty again and draws with the wrong probability."""
     from oracle.oracle import OracleEnv
     from sequential_social_dilemma_games_b200.batched import make_config
     from sequential_social_dilemma_games_b200.maps import CLEANUP_MAP, tile_map
-    cfg = make_config(game, num_agents=N, ascii_map=tile_map(CLEANUP_MAP) if amap == "tiled" else None)
+    dense = ['@@@@@@@@@', '@PPPPAAA@', '@PPAAAAA@', '@AAAPPPA@', '@PPPPPAA@', '@AAAAAPP@', '@@@@@@@@@']
+    cfg = make_config(game, num_agents=N, ascii_map=tile_map(CLEANUP_MAP) if amap == "tiled" else (dense if amap == "dense" else None))
     seed, off = 0xC0FFEE1234567, 77777
     env = _env(cfg, B, seed=seed, env_id_offset=off)
     orc = OracleEnv(cfg, B, seed=seed, env_id_offset=off, n_threads=8)
