@@ -159,6 +159,17 @@ int ssd_render(ssd_handle h, int rotate, uint8_t* obs_out, void* stream);
  * Pinned host memory gives full PCIe bandwidth; pageable memory works but is slower. */
 int ssd_step_host(ssd_handle h, const int8_t* actions_host, uint8_t* obs_host, int32_t* reward_host);
 
+/* Tuning options.
+ * SSD_OPT_CHAIN_STEPS (default 0): when 1, consecutive ssd_step calls on the same stream are launched
+ * with programmatic dependent launch: the kernel of step t+1 starts filling SMs while the last CTAs of
+ * step t are still running, and every warp waits only for the environments IT steps (a per-warp
+ * completion word written by step t).  Results are unchanged.  Precondition: the `actions` of a
+ * chained step must already be complete when the previous ssd_step was enqueued (a rollout with
+ * pre-generated or scripted actions); work enqueued between two chained steps is NOT waited for.
+ * Any other call on the handle (reset, set_state, phases, render, ...) breaks the chain safely. */
+#define SSD_OPT_CHAIN_STEPS 1
+int ssd_set_option(ssd_handle h, int option, int64_t value);
+
 /* Running counters since creation (host i64[SSD_NUM_STATS]); synchronises `stream`. */
 int ssd_stats(ssd_handle h, int64_t* out_host, void* stream);
 

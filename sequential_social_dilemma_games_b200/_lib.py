@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libssd_b200.so")
 ABI_VERSION = 1
 MAX_AGENTS = 16
 NUM_STATS = 8
+OPT_CHAIN_STEPS = 1
 PHASE_MOVES, PHASE_CONSUME, PHASE_BEAMS, PHASE_SPAWN, PHASE_RENDER, PHASE_ALL = 1, 2, 4, 8, 16, 31
 
 # every symbol include/ssd_b200.h declares (tests/test_cabi.py checks the list against the header)
@@ -18,7 +19,7 @@ SYMBOLS = ("ssd_last_error", "ssd_abi_version", "ssd_create", "ssd_destroy", "ss
            "ssd_num_waste_points", "ssd_obs_bytes_per_env", "ssd_envs_per_cta",
            "ssd_algorithmic_bytes_per_env_step", "ssd_seed", "ssd_get_counter", "ssd_set_state",
            "ssd_get_state", "ssd_reset", "ssd_step", "ssd_step_phases", "ssd_get_beams", "ssd_render", "ssd_step_host",
-           "ssd_stats", "ssd_launch_count", "ssd_philox_selftest")
+           "ssd_set_option", "ssd_stats", "ssd_launch_count", "ssd_philox_selftest")
 
 
 class SsdConfig(C.Structure):
@@ -72,6 +73,7 @@ def _load():
         "ssd_get_beams": (i32, [vp, vp, vp]),
         "ssd_render": (i32, [vp, i32, vp, vp]),
         "ssd_step_host": (i32, [vp, vp, vp, vp]),
+        "ssd_set_option": (i32, [vp, i32, i64]),
         "ssd_stats": (i32, [vp, vp, vp]),
         "ssd_launch_count": (i64, [vp]),
         "ssd_philox_selftest": (i32, [i32, vp, vp, vp]),

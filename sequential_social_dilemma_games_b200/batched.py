@@ -191,6 +191,13 @@ class BatchedSSDEnv(object):
         _lib.check(_lib.lib.ssd_get_beams(self._h, out.ctypes.data, self._stream()))
         return out
 
+    def chain_steps(self, on=True):
+        """SSD_OPT_CHAIN_STEPS (include/ssd_b200.h): overlap the kernels of consecutive step() calls with
+        programmatic dependent launch.  Only for rollouts whose actions exist before the previous step was
+        enqueued (pre-generated / scripted actions); results are unchanged."""
+        _lib.check(_lib.lib.ssd_set_option(self._h, _lib.OPT_CHAIN_STEPS, int(bool(on))))
+        return self
+
     def stats(self):
         out = np.zeros(_lib.NUM_STATS, dtype=np.int64)
         _lib.check(_lib.lib.ssd_stats(self._h, out.ctypes.data, self._stream()))

@@ -48,6 +48,7 @@ struct SsdEnv {
     uint32_t t = 0;
     int64_t launches = 0;
     ssd::SmemLayout L{}, Lf{};
+    ssd::ChainState chain{};
     // device allocations
     std::vector<void*> allocs;
     uint16_t* d_apple = nullptr;
@@ -280,6 +281,7 @@ int ssd_create(const SsdConfig* cfg, ssd_handle* out) {
     bad |= h->alloc(&h->d_agents, static_cast<size_t>(h->B_pad) * N);
     bad |= h->alloc(&h->d_beam_buf, static_cast<size_t>(h->B_pad) * 64);
     bad |= h->alloc(&h->d_stats, static_cast<size_t>(SSD_NUM_STATS));
+    bad |= h->alloc(&h->chain.done, static_cast<size_t>(h->B_pad / 4 + 1));
     if (bad) { const char* m = cudaGetErrorString(cudaGetLastError()); ssd_destroy(h); return fail(SSD_ERR_CUDA, "device allocation failed: %s", m); }
     // initial state: post-reset_map grid, agents parked on the first spawn point (or cell 1,1)
     {
@@ -291,6 +293,7 @@ int ssd_create(const SsdConfig* cfg, ssd_handle* out) {
         cudaError_t e2 = cudaMemcpy(h->d_agents, ag.data(), ag.size() * 4, cudaMemcpyHostToDevice);
         cudaError_t e3 = cudaMemset(h->d_stats, 0, SSD_NUM_STATS * sizeof(unsigned long long));
         cudaError_t e4 = cudaMemset(h->d_beam_buf, 0, static_cast<size_t>(h->B_pad) * 64);
+        if (e4 == cudaSuccess) e4 = cudaMemset(h->chain.done, 0, (static_cast<size_t>(h->B_pad) / 4 + 1) * sizeof(uint32_t));
         if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess) {
             ssd_destroy(h);
             return fail(SSD_ERR_CUDA, "state initialisation failed");
@@ -337,6 +340,7 @@ int ssd_get_counter(ssd_handle h, uint32_t* t) {
 
 int ssd_set_state(ssd_handle h, const uint8_t* grid, const int16_t* pos, const uint8_t* ori, void* stream) {
     if (check_handle(h)) return SSD_ERR_INVALID;
+    h->chain.valid = false;
     if (!grid || !pos || !ori) return fail(SSD_ERR_INVALID, "grid, pos and ori are required");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -359,6 +363,7 @@ int ssd_set_state(ssd_handle h, const uint8_t* grid, const int16_t* pos, const u
 
 int ssd_get_state(ssd_handle h, uint8_t* grid, int16_t* pos, uint8_t* ori, void* stream) {
     if (check_handle(h)) return SSD_ERR_INVALID;
+    h->chain.valid = false;
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int N = h->cfg.num_agents;
@@ -384,6 +389,7 @@ int ssd_get_state(ssd_handle h, uint8_t* grid, int16_t* pos, uint8_t* ori, void*
 
 int ssd_reset(ssd_handle h, const uint8_t* mask, uint8_t* obs_out, void* stream) {
     if (check_handle(h)) return SSD_ERR_INVALID;
+    h->chain.valid = false;
     if (h->n_spawn == 0) return fail(SSD_ERR_INVALID, "the map has no 'P' spawn points");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -418,7 +424,7 @@ int ssd_step_phases(ssd_handle h, int phases, const int8_t* actions, const uint8
     a.rew_accumulate = phases != SSD_PHASE_ALL;
     a.actions = actions; a.order = action_order; a.obs = obs_out; a.rew = reward_out;
     if (tape) { a.tape_move = tape->move_order; a.tape_u = tape->uniforms; a.u_stride = tape->u_stride; a.tape_waste = tape->waste_order; a.n_draws_out = tape->n_draws_out; }
-    CUDA_TRY(ssd::launch_step(a, h->threads, static_cast<cudaStream_t>(stream)));
+    CUDA_TRY(ssd::launch_step(a, h->threads, static_cast<cudaStream_t>(stream), &h->chain));
     h->launches++;
     if (phases & SSD_PHASE_SPAWN) h->t++;
     return SSD_OK;
@@ -431,6 +437,7 @@ int ssd_step(ssd_handle h, const int8_t* actions, const uint8_t* action_order, c
 
 int ssd_get_beams(ssd_handle h, uint8_t* out, void* stream) {
     if (check_handle(h) || !out) return SSD_ERR_INVALID;
+    h->chain.valid = false;
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     std::vector<uint8_t> tmp(static_cast<size_t>(h->B) * 64);
@@ -447,6 +454,7 @@ int ssd_get_beams(ssd_handle h, uint8_t* out, void* stream) {
 
 int ssd_render(ssd_handle h, int rotate, uint8_t* obs_out, void* stream) {
     if (check_handle(h)) return SSD_ERR_INVALID;
+    h->chain.valid = false;
     if (!obs_out) return fail(SSD_ERR_INVALID, "obs_out is required");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     ssd::StepArgs a;
@@ -459,6 +467,7 @@ int ssd_render(ssd_handle h, int rotate, uint8_t* obs_out, void* stream) {
 
 int ssd_step_host(ssd_handle h, const int8_t* actions_host, uint8_t* obs_host, int32_t* reward_host) {
     if (check_handle(h)) return SSD_ERR_INVALID;
+    h->chain.valid = false;
     if (!actions_host || !reward_host) return fail(SSD_ERR_INVALID, "actions_host and reward_host are required");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     const int N = h->cfg.num_agents, B = h->B, E = h->E;
@@ -494,6 +503,18 @@ int ssd_step_host(ssd_handle h, const int8_t* actions_host, uint8_t* obs_host, i
     CUDA_TRY(cudaStreamSynchronize(h->hs[1]));
     h->t++;
     return SSD_OK;
+}
+
+int ssd_set_option(ssd_handle h, int option, int64_t value) {
+    if (check_handle(h)) return SSD_ERR_INVALID;
+    switch (option) {
+        case SSD_OPT_CHAIN_STEPS:
+            h->chain.enabled = value != 0;
+            h->chain.valid = false;
+            return SSD_OK;
+        default:
+            return fail(SSD_ERR_INVALID, "unknown option %d", option);
+    }
 }
 
 int ssd_stats(ssd_handle h, int64_t* out_host, void* stream) {

@@ -135,6 +135,21 @@ struct StepArgs {
     const uint8_t* tape_move; const double* tape_u; int u_stride; const uint16_t* tape_waste; int32_t* n_draws_out;
     uint8_t* obs; int32_t* rew;
     unsigned long long* stats;
+    // ---- chained steps (SSD_OPT_CHAIN_STEPS): done[task] = epoch of the last full step that finished the
+    // task's envs (task = 4 consecutive envs = one warp of the specialised kernel)
+    uint32_t* done;
+    uint32_t epoch;
+    int dep_wait;         // wait for done[task] == epoch - 1 instead of relying on stream order
+    int publish;          // write done[task] = epoch when the task's results are visible
+};
+
+// Host-side bookkeeping of the step chain (one per handle).
+struct ChainState {
+    bool enabled = false, valid = false;
+    cudaStream_t stream = nullptr;
+    int env_begin = 0, env_end = 0;
+    uint32_t epoch = 0;
+    uint32_t* done = nullptr;
 };
 
 struct ResetArgs {
@@ -148,7 +163,7 @@ struct ResetArgs {
 };
 
 // Launchers implemented in ssd_step.cu.
-cudaError_t launch_step(const StepArgs& a, int threads, cudaStream_t stream);
+cudaError_t launch_step(const StepArgs& a, int threads, cudaStream_t stream, ChainState* chain = nullptr);
 cudaError_t launch_reset(const ResetArgs& a, cudaStream_t stream);
 cudaError_t launch_pack_state(int kind, int B, int N, int H, int W, int Ws, int env_bytes, const uint8_t* grid_in, const int16_t* pos_in,
                               const uint8_t* ori_in, uint8_t* grid, uint32_t* agents, cudaStream_t stream);

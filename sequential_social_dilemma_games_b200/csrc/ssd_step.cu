@@ -929,6 +929,7 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
     const int N = a.N;
     uint16_t* s_apple = reinterpret_cast<uint16_t*>(smem + a.Lf.apple);
+    pdl_launch_dependents();  // a chained next step may start launching (it waits per task, see below)
 
     for (int i = tid; i < kLutEntries; i += nthr) s_color[i] = a.color[i];
     if (tid < SSD_NUM_STATS) s_cta_stats[tid] = 0;
@@ -948,7 +949,14 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
 
     if (we < a.env_end) {
         // ---- load: one TMA bulk copy per env tile; zero the frames while they are in flight
-        if (lane == 0) { mbar_init(mbar, 1); mbar_expect_tx(mbar, static_cast<uint32_t>(EPW) * a.env_bytes); }
+        if (lane == 0) {
+            mbar_init(mbar, 1);
+            mbar_expect_tx(mbar, static_cast<uint32_t>(EPW) * a.env_bytes);
+            if (a.dep_wait) {  // chained step: the previous step's kernel may still be running; wait for OUR four envs only
+                while (ld_acquire_u32(a.done + (we >> 2)) != a.epoch - 1) __nanosleep(64);
+                fence_async_all();  // its ordinary stores -> our TMA loads
+            }
+        }
         __syncwarp();
         if (lane < EPW)
             bulk_g2s(tiles + a.pad_bytes + lane * tile_pitch, a.grid + static_cast<size_t>(we + lane) * a.env_bytes, a.env_bytes, mbar);
@@ -972,7 +980,7 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
         AgentLane me;
         me.key = 0x0101; me.ori = 0; me.act = -1; me.rew = 0;
         if (valid) {
-            const uint32_t w = a.agents[gi];
+            const uint32_t w = __ldcg(a.agents + gi);  // L2: a chained predecessor may just have written it
             me.act = a.actions[gi];
             me.key = (w & 255) << 8 | ((w >> 8) & 255);
             me.ori = (w >> 16) & 3;
@@ -1148,6 +1156,14 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
             render_rows_tma<VT>(s_view, tiles, s_color, reinterpret_cast<uint32_t*>(wbase + a.Lf.w_union + a.Lf.u_stage),
                                 a.obs + static_cast<size_t>(we) * a.obs_env, EPW * N * VT, a.debug);
         }
+        if (a.publish) {  // everything this task wrote (grid, agent words, rewards, observation rows) is visible before the word is
+            __syncwarp();
+            if (lane == 0) {
+                bulk_wait_all();
+                __threadfence();
+                st_release_u32(a.done + (we >> 2), a.epoch);
+            }
+        }
     }
 
     // ---- stats: warp -> CTA -> one set of global atomics per CTA (issued by the last warp to finish)
@@ -1318,13 +1334,18 @@ static cudaError_t launch_fast(const StepArgs& a, int threads, cudaStream_t stre
     do {                                                                                                        \
         auto kern = ssd_step_fast_kernel<KIND, TAPE, VT_>;                                                      \
         static uint32_t smem_set = 0;                                                                           \
-        if (a.L.total > smem_set) {                                                                             \
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, a.L.total); \
+        if (a.Lf.total > smem_set) {                                                                            \
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, a.Lf.total); \
             if (e != cudaSuccess) return e;                                                                     \
-            smem_set = a.L.total;                                                                               \
+            smem_set = a.Lf.total;                                                                              \
         }                                                                                                       \
-        kern<<<ctas, threads, a.L.total, stream>>>(a);                                                          \
-        return cudaGetLastError();                                                                              \
+        cudaLaunchConfig_t lc = {};                                                                             \
+        lc.gridDim = dim3(ctas); lc.blockDim = dim3(threads); lc.dynamicSmemBytes = a.Lf.total; lc.stream = stream; \
+        cudaLaunchAttribute at[1];                                                                              \
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                          \
+        at[0].val.programmaticStreamSerializationAllowed = 1;                                                   \
+        lc.attrs = at; lc.numAttrs = a.dep_wait ? 1 : 0;                                                        \
+        return cudaLaunchKernelEx(&lc, kern, a);                                                                \
     } while (0)
     switch (a.V) {
         case 11: SSD_LAUNCH_FAST(11);
@@ -1349,7 +1370,7 @@ static cudaError_t launch_general(const StepArgs& a, int threads, cudaStream_t s
     }
 }
 
-cudaError_t launch_step(const StepArgs& a, int threads, cudaStream_t stream) {
+cudaError_t launch_step(const StepArgs& a, int threads, cudaStream_t stream, ChainState* chain) {
     // the packed row renderers need every warp's slab of 32/G envs to start 4-byte aligned
     const bool fast_rows = (((32 / a.G) * a.obs_env) % 4 == 0) && (reinterpret_cast<uintptr_t>(a.obs) % 4 == 0);
     const bool tape = a.tape_u != nullptr || a.tape_move != nullptr;
@@ -1358,9 +1379,25 @@ cudaError_t launch_step(const StepArgs& a, int threads, cudaStream_t stream) {
     const bool full = !no_fast && a.phases == SSD_PHASE_ALL && a.mask == nullptr && a.order == nullptr && !a.use_beam_buf &&
                       !a.rew_accumulate && a.obs != nullptr && a.rew != nullptr && a.actions != nullptr && a.G == 8 && fast_rows &&
                       (a.V == 11 || a.V == 15 || a.V == 21) && a.env_begin % 4 == 0;
-    if (!full) return launch_general(a, threads, stream, fast_rows);
+    if (!full) {
+        if (chain) chain->valid = false;
+        return launch_general(a, threads, stream, fast_rows);
+    }
     StepArgs f = a;
     f.env_end = a.env_begin + (a.env_end - a.env_begin) / 4 * 4;  // whole warps
+    const bool has_tail = f.env_end != a.env_end;
+    if (chain && chain->enabled && chain->done != nullptr) {
+        // Chained steps (SSD_OPT_CHAIN_STEPS): this launch may overlap the previous step's kernel when that was the
+        // same kind of launch on the same stream; either way it publishes per-task completion words for the next one.
+        f.done = chain->done;
+        f.epoch = ++chain->epoch;
+        f.publish = 1;
+        f.dep_wait = chain->valid && chain->stream == stream && chain->env_begin == f.env_begin && chain->env_end == f.env_end;
+        chain->valid = !has_tail;
+        chain->stream = stream; chain->env_begin = f.env_begin; chain->env_end = f.env_end;
+    } else if (chain) {
+        chain->valid = false;
+    }
     cudaError_t e = cudaSuccess;
     switch (a.kind) {
         case SSD_KIND_HARVEST:
@@ -1373,7 +1410,7 @@ cudaError_t launch_step(const StepArgs& a, int threads, cudaStream_t stream) {
             e = tape ? launch_fast<SSD_KIND_PLAIN, true>(f, threads, stream) : launch_fast<SSD_KIND_PLAIN, false>(f, threads, stream);
             break;
     }
-    if (e != cudaSuccess || f.env_end == a.env_end) return e;
+    if (e != cudaSuccess || !has_tail) return e;
     StepArgs tail = a;  // the last 1..3 envs
     tail.env_begin = f.env_end;
     return launch_general(tail, threads, stream, fast_rows);

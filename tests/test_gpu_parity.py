@@ -134,6 +134,36 @@ def test_philox_vs_oracle(game, B, steps, N, amap):
         assert st["waste_spawned"] > 0 and st["cleaned"] > 0
 
 
+@pytest.mark.parametrize("game", ["harvest", "cleanup"])
+def test_chained_steps(game):
+    """SSD_OPT_CHAIN_STEPS: kernels of consecutive steps overlap (programmatic dependent launch, per-warp
+    completion words).  Same trajectories, observations, rewards and statistics as stream-ordered steps."""
+    from sequential_social_dilemma_games_b200.batched import make_config
+    cfg = make_config(game)
+    B, T = 32768, 120
+    envs = [_env(cfg, B, seed=99, env_id_offset=5), _env(cfg, B, seed=99, env_id_offset=5).chain_steps(True)]
+    g = torch.Generator(device="cuda").manual_seed(3)
+    ring = torch.randint(0, cfg.num_actions, (8, B, cfg.num_agents), generator=g, device="cuda", dtype=torch.int8)
+    outs = []
+    for env in envs:
+        obs = env.reset().clone()
+        rew_sum = torch.zeros((B, cfg.num_agents), dtype=torch.int64, device="cuda")
+        snaps = []
+        for t in range(T):
+            o, r = env.step(ring[t % 8])
+            if t % 40 == 39:  # reading results is ordinary stream-ordered work: it must see the finished step
+                rew_sum += r
+                snaps.append((o.clone(), r.clone()))
+        torch.cuda.synchronize()
+        outs.append((snaps, [x.cpu().numpy() for x in env.get_state()], env.stats()))
+    (s0, st0, k0), (s1, st1, k1) = outs
+    for (o0, r0), (o1, r1) in zip(s0, s1):
+        assert torch.equal(o0, o1) and torch.equal(r0, r1)
+    for x, y in zip(st0, st1):
+        assert np.array_equal(x, y)
+    assert k0 == k1 and k0["env_steps"] == B * T
+
+
 def test_full_size_properties():
     """BASELINE.json configs[2] size (65536 Harvest envs): properties that need no oracle.
     (a) shard invariance: two handles of 32768 envs with env_id_offset reproduce the single
