@@ -30,8 +30,8 @@ HORIZON = 1000  # RLlib "horizon" of the reference's training configs (train_bas
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=3000)
+    ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs-per-gpu", type=int, default=65536)
     ap.add_argument("--game", default="harvest", choices=["harvest", "cleanup"])
@@ -41,6 +41,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-envs", type=int, default=8192)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-chain", action="store_true", help="stream-ordered steps only (no programmatic dependent launch)")
     return ap.parse_args()
 
 
@@ -179,24 +180,36 @@ def run_ours(args, rank, world, local_rank):
         env.step(ring[step_no[0] % 16], out=obs, reward_out=rew)
         step_no[0] += 1
 
-    for _ in range(args.warmup):
-        one_step()
-    barrier()
-    launches0 = env.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clk:
+    def timed(n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
         e0.record()
-        for _ in range(args.steps):
+        for _ in range(n):
             one_step()
         e1.record()
         barrier()
-    ms = e0.elapsed_time(e1)
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return e0.elapsed_time(e1), float(t.item())
+
+    for _ in range(args.warmup):
+        one_step()
+    # stream-ordered steps first (every kernel waits for the previous one to drain) ...
+    _, ms_plain = timed(args.steps)
+    # ... then the headline: consecutive steps chained with programmatic dependent launch (SSD_OPT_CHAIN_STEPS).
+    # The actions are pre-generated, which is the option's precondition; results are identical (tests/test_gpu_parity.py).
+    chained = not args.no_chain
+    if chained:
+        env.chain_steps(True)
+        for _ in range(args.warmup):
+            one_step()
+    launches0 = env.launch_count
+    with ClockSampler(local_rank) as clk:
+        ms, ms_max = timed(args.steps)
     launches = env.launch_count - launches0
-    tms = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms_max = float(tms.item())
     value = world * B * N * args.steps / (ms_max * 1e-3)
+    env.chain_steps(False)
 
     # end to end through the C-ABI with HOST buffers (ssd_step_host): H2D actions, step, D2H obs + rewards
     e2e = None
@@ -249,9 +262,13 @@ def run_ours(args, rank, world, local_rank):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u8", "data": "synthetic", "config": dict(workload(args), parallelism="env-sharded x%d" % world,
-                                                                    envs_per_cta=env.envs_per_cta),
+                                                                    envs_per_cta=env.envs_per_cta,
+                                                                    step_launch="chained: programmatic dependent launch, per-warp "
+                                                                    "completion words (SSD_OPT_CHAIN_STEPS)" if chained else "stream-ordered"),
+                "stream_ordered": {"value": world * B * N * args.steps / (ms_plain * 1e-3), "ms_per_step": ms_plain / args.steps,
+                                   "note": "same K steps without chaining: every step kernel drains before the next starts"},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": traffic, "kernel": "ssd_step_kernel<HARVEST,philox,V=15>", "peak_source": peak_src,
+                             "traffic": traffic, "kernel": "ssd_step_fast_kernel<%s,philox,V=%d>" % (args.game.upper(), 2 * args.view + 1), "peak_source": peak_src,
                              "algorithmic_bytes_per_env_step": alg, "units_per_launch": B},
                 "clocks": clocks, "gpu_launches": launches, "e2e": e2e,
                 "totals": {"env_steps": int(tot[0]), "reward_sum": int(tot[1]), "apples_eaten": int(tot[2]), "hits": int(tot[3])}}
