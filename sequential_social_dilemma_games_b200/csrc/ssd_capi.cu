@@ -45,6 +45,7 @@ struct SsdEnv {
     int HW = 0, Ws = 0, env_bytes = 0, pad_bytes = 0, V = 0, obs_env = 0, n_apple = 0, n_waste = 0, n_spawn = 0;
     uint64_t seed = 0;
     int harvest_nz = 0;
+    int distinct_spawn = 0;
     uint32_t t = 0;
     int64_t launches = 0;
     ssd::SmemLayout L{}, Lf{};
@@ -164,7 +165,7 @@ int ssd_create(const SsdConfig* cfg, ssd_handle* out) {
             if ((r == 0 || c == 0 || r == H - 1 || c == W - 1) && ch != '@')
                 return fail(SSD_ERR_INVALID, "the map must be enclosed by '@' walls (cell %d,%d): the reference indexes grid[new_row, new_col] unchecked (agent.py:111)", r, c);
         }
-    // "There are not enough spawn points!" (map_env.py:661)
+    int distinct_spawn = 0;
     {
         std::vector<int> seen;
         for (int s = 0; s < cfg->num_spawn_points; ++s) {
@@ -175,8 +176,7 @@ int ssd_create(const SsdConfig* cfg, ssd_handle* out) {
             for (int k : seen) dup |= (k == key);
             if (!dup) seen.push_back(key);
         }
-        if (cfg->num_spawn_points > 0 && static_cast<int>(seen.size()) < N)
-            return fail(SSD_ERR_INVALID, "There are not enough spawn points! Check your map? (%d distinct, %d agents; map_env.py:661)", static_cast<int>(seen.size()), N);
+        distinct_spawn = static_cast<int>(seen.size());  // checked by ssd_reset: agents may also be placed with ssd_set_state
     }
     CUDA_TRY(cudaSetDevice(cfg->device));
     cudaDeviceProp prop;
@@ -186,6 +186,7 @@ int ssd_create(const SsdConfig* cfg, ssd_handle* out) {
     SsdEnv* h = new (std::nothrow) SsdEnv();
     if (!h) return fail(SSD_ERR_INVALID, "out of host memory");
     h->cfg = *cfg;
+    h->distinct_spawn = distinct_spawn;
     h->B = cfg->num_envs; h->HW = H * W;
     h->Ws = W + cfg->view_radius;  // r zero bytes after the W cells of every row
     h->env_bytes = static_cast<int>(up16(H * h->Ws));
@@ -391,6 +392,8 @@ int ssd_reset(ssd_handle h, const uint8_t* mask, uint8_t* obs_out, void* stream)
     if (check_handle(h)) return SSD_ERR_INVALID;
     h->chain.valid = false;
     if (h->n_spawn == 0) return fail(SSD_ERR_INVALID, "the map has no 'P' spawn points");
+    if (h->distinct_spawn < h->cfg.num_agents)  // map_env.py:661
+        return fail(SSD_ERR_INVALID, "There are not enough spawn points! Check your map? (%d distinct, %d agents; map_env.py:661)", h->distinct_spawn, h->cfg.num_agents);
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     ssd::ResetArgs r{};

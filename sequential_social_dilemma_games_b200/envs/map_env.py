@@ -101,12 +101,12 @@ class MapEnv(MultiAgentEnv):
             return int(a.row_size)
         return int(self.VIEW_SIZE)
 
-    def _engine(self):
-        """BatchedSSDEnv of one env for the current number of agents (a ghost agent parked on a wall
-        cell stands in when the env has none: it never acts, blocks nothing and is never observed)."""
+    def _engine(self, view=None):
+        """BatchedSSDEnv of one env for the current number of agents and a view size (a ghost agent parked on
+        a wall cell stands in when the env has none: it never acts, blocks nothing and is never observed)."""
         from ..batched import BatchedSSDEnv
         n = max(1, len(self.agents))
-        key = (n, self._view_size())
+        key = (n, self._view_size() if view is None else int(view))
         if key not in self._engines:
             cfg = EnvConfig(self.KIND, self._ascii_map, n, view_size=key[1],
                             colour_map={k: v for k, v in self.color_map.items() if len(k) == 1},
@@ -139,10 +139,10 @@ class MapEnv(MultiAgentEnv):
                 a.reward_this_turn += int(rewards[i])
 
     def _run_phases(self, phases, actions=None, order=None, move_order=None, uniforms=None, waste_order=None,
-                    render=False, rotate=True):
+                    render=False, rotate=True, view=None):
         """Upload host state, run `phases` on the device with a replay tape, download the results."""
         import torch
-        eng = self._engine()
+        eng = self._engine(view)
         n = eng.cfg.num_agents
         self._upload(eng)
         act = np.full((1, n), -1, dtype=np.int8) if actions is None else actions
@@ -213,17 +213,25 @@ class MapEnv(MultiAgentEnv):
         return observations
 
     def _render_obs(self, rotate):
+        """uint8 observations of all agents, as a list (agents may have different view sizes: the reference renders
+        every agent with its own row_size, agent.py:76-78)."""
         if not self.agents:
-            return np.zeros((0,), dtype=np.uint8)
-        if self._beams_from_device:
-            obs, _ = self._run_phases(_lib.PHASE_RENDER, render=True, rotate=rotate,
-                                      order=self._step_order if rotate else None)
-        else:  # beams came from an overridden custom_action: render without, then paint them on the host
-            eng = self._engine()
-            self._upload(eng)
-            obs = eng.render(rotate=rotate).cpu().numpy()[0]
-            self._paint_beams_host(obs, rotate)
-        return obs
+            return []
+        agents = list(self.agents.values())
+        out = [None] * len(agents)
+        for view in sorted({int(a.row_size) for a in agents}):
+            if self._beams_from_device and view == self._view_size():  # the engine that ran the beam phase holds the beams
+                obs, _ = self._run_phases(_lib.PHASE_RENDER, render=True, rotate=rotate, view=view,
+                                          order=self._step_order if rotate else None)
+            else:  # beams from an overridden custom_action, or another view size: render without, paint beam_pos on the host
+                eng = self._engine(view)
+                self._upload(eng)
+                obs = eng.render(rotate=rotate).cpu().numpy()[0]
+                self._paint_beams_host(obs, rotate, view)
+            for i, a in enumerate(agents):
+                if int(a.row_size) == view:
+                    out[i] = obs[i]
+        return out
 
     _beams_from_device = True
     _step_act = None
@@ -253,7 +261,13 @@ class MapEnv(MultiAgentEnv):
             np.random.shuffle(movers)
             mo[0, :len(movers)] = movers
         self._step_act, self._step_order = act, order
-        self._run_phases(_lib.PHASE_MOVES | _lib.PHASE_CONSUME, actions=act, order=order, move_order=mo)
+        from .agent import _SSDAgent
+        stock = all(type(a).consume is _SSDAgent.consume for a in self.agents.values())
+        self._run_phases(_lib.PHASE_MOVES | (_lib.PHASE_CONSUME if stock else 0), actions=act, order=order, move_order=mo)
+        if not stock:  # agents with their own consume(): the reference's loop, map_env.py:178-181
+            for agent in self.agents.values():
+                pos = agent.get_pos()
+                self.world_map[pos[0], pos[1]] = agent.consume(self.world_map[pos[0], pos[1]])
 
     def _custom_action_overridden(self):
         return type(self).custom_action is not getattr(type(self), "_device_custom_action", None)
@@ -294,8 +308,7 @@ class MapEnv(MultiAgentEnv):
                     self.beam_pos.append((int(cell[0]), int(cell[1]), chr(ch)))
                     cell = cell + d
 
-    def _paint_beams_host(self, obs, rotate):
-        view = self._view_size()
+    def _paint_beams_host(self, obs, rotate, view):
         V = 2 * view + 1
         for i, agent in enumerate(self.agents.values()):
             k = {'UP': 0, 'LEFT': 1, 'DOWN': 2, 'RIGHT': 3}[agent.orientation] if rotate else 0

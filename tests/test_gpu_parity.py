@@ -164,6 +164,23 @@ def test_chained_steps(game):
     assert k0 == k1 and k0["env_steps"] == B * T
 
 
+def test_reset_needs_spawn_points():
+    """'There are not enough spawn points! Check your map?' (map_env.py:661) is raised by reset, not by construction:
+    the adapters place hand-made agents with ssd_set_state on maps with fewer 'P' cells than agents."""
+    from sequential_social_dilemma_games_b200 import _lib
+    from sequential_social_dilemma_games_b200.config import EnvConfig, KIND_HARVEST
+    env = _env(EnvConfig(KIND_HARVEST, ["@@@@@@", "@P AA@", "@    @", "@@@@@@"], 3), 4)
+    with pytest.raises(_lib.SsdError, match="not enough spawn points"):
+        env.reset()
+    grid = np.tile(np.vectorize(ord)(np.array([list(r) for r in ["@@@@@@", "@  AA@", "@    @", "@@@@@@"]])).astype(np.uint8), (4, 1, 1))
+    pos = np.tile(np.array([[1, 1], [2, 1], [2, 4]], np.int16), (4, 1, 1))
+    env.set_state(grid, pos, np.zeros((4, 3), np.uint8))
+    obs, rew = env.step(np.full((4, 3), 3, np.int8))  # MOVE_DOWN facing UP = one column to the right
+    assert rew.cpu().numpy().tolist() == [[0, 0, 0]] * 4
+    obs, rew = env.step(np.full((4, 3), 3, np.int8))
+    assert rew.cpu().numpy().tolist() == [[1, 0, 0]] * 4
+
+
 def test_full_size_properties():
     """BASELINE.json configs[2] size (65536 Harvest envs): properties that need no oracle.
     (a) shard invariance: two handles of 32768 envs with env_id_offset reproduce the single
