@@ -166,7 +166,9 @@ int ssd_step_host(ssd_handle h, const int8_t* actions_host, uint8_t* obs_host, i
  * completion word written by step t).  Results are unchanged.  Precondition: the `actions` of a
  * chained step must already be complete when the previous ssd_step was enqueued (a rollout with
  * pre-generated or scripted actions); work enqueued between two chained steps is NOT waited for.
- * Any other call on the handle (reset, set_state, phases, render, ...) breaks the chain safely. */
+ * Any other call on the handle (reset, set_state, phases, render, ...) breaks the chain safely.  The library
+ * only chains launches of 1.5 to 12 waves of CTAs (about 28K to 230K Harvest envs on a B200): smaller grids
+ * have no tail to hide, larger ones amortise it. */
 #define SSD_OPT_CHAIN_STEPS 1
 int ssd_set_option(ssd_handle h, int option, int64_t value);
 

@@ -14,7 +14,7 @@ def curve(game="harvest", B=65536, window=100, total=1000, view=7, agents=5):
     dev = torch.device("cuda", 0)
     cfg = make_config(game, num_agents=agents, view_size=view)
     env = BatchedSSDEnv(cfg, B, device=dev, seed=0)
-    if os.environ.get('SSD_CHAIN'):
+    if os.environ.get('SSD_CHAIN', '0') not in ('', '0'):
         env.chain_steps(True)
     g = torch.Generator(device=dev).manual_seed(1234)
     ring = torch.randint(0, cfg.num_actions, (16, B, cfg.num_agents), generator=g, device=dev, dtype=torch.int8)

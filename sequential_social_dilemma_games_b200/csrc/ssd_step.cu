@@ -1386,7 +1386,23 @@ cudaError_t launch_step(const StepArgs& a, int threads, cudaStream_t stream, Cha
     StepArgs f = a;
     f.env_end = a.env_begin + (a.env_end - a.env_begin) / 4 * 4;  // whole warps
     const bool has_tail = f.env_end != a.env_end;
+    // Chaining pays when a step is a few waves of CTAs (it hides launch, ramp and the half-empty last wave); a single
+    // wave has no tail to hide and very long grids amortise it anyway, while the completion words cost a little
+    // (profiles/r01h_sweep.md): chain between 1.5 and 12 waves.
+    bool chain_here = false;
     if (chain && chain->enabled && chain->done != nullptr) {
+        static int slots = 0;  // resident CTAs of the whole GPU at this CTA shape (8 per SM on B200)
+        if (slots == 0) {
+            int dev = 0, sms = 148;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            slots = sms * 8;
+        }
+        const int ctas = (f.env_end - f.env_begin + (threads / 32) * 4 - 1) / ((threads / 32) * 4);
+        chain_here = 2 * ctas >= 3 * slots && ctas <= 12 * slots;
+        if (getenv("SSD_CHAIN_ALWAYS")) chain_here = true;
+    }
+    if (chain_here) {
         // Chained steps (SSD_OPT_CHAIN_STEPS): this launch may overlap the previous step's kernel when that was the
         // same kind of launch on the same stream; either way it publishes per-task completion words for the next one.
         f.done = chain->done;
