@@ -153,6 +153,11 @@ int ssd_get_beams(ssd_handle h, uint8_t* out, void* stream);
  * MapEnv.map_to_colors for the adapters. */
 int ssd_render(ssd_handle h, int rotate, uint8_t* obs_out, void* stream);
 
+/* Full-map frames for video / visualisation: MapEnv.map_to_colors(get_map_with_agents()) (map_env.py:280-339,
+ * rollout.py:48-82) of every env.  rgb_out dev u8[B][H][W][3].  Beams live for one step only
+ * (map_env.py:169) and are not drawn. */
+int ssd_render_map(ssd_handle h, uint8_t* rgb_out, void* stream);
+
 /* End-to-end step with HOST buffers: H2D actions, fused step, D2H observations and rewards,
  * pipelined in chunks over two internal streams; returns after everything landed.
  * actions_host i8[B][N], obs_host u8[B][N][V][V][3] (NULL to skip), reward_host i32[B][N].

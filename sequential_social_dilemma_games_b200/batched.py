@@ -152,6 +152,16 @@ class BatchedSSDEnv(object):
         _lib.check(_lib.lib.ssd_render(self._h, int(bool(rotate)), _ptr(obs), self._stream()))
         return obs
 
+    def render_map(self, out=None):
+        """uint8 [B, H, W, 3] frames of the whole map with the agents painted (map_to_colors of
+        get_map_with_agents, map_env.py:280-339): what rollout.py / visuallizer_rllib.py turn into videos."""
+        shape = (self.num_envs, self.cfg.height, self.cfg.width, 3)
+        if out is None:
+            out = torch.empty(shape, dtype=torch.uint8, device=self.device)
+        assert out.is_cuda and out.dtype == torch.uint8 and out.is_contiguous() and tuple(out.shape) == shape
+        _lib.check(_lib.lib.ssd_render_map(self._h, _ptr(out), self._stream()))
+        return out
+
     def step_host(self, actions_host, obs_host=None, reward_host=None):
         """End-to-end step with host (ideally pinned) numpy buffers: H2D actions, fused step,
         D2H observations + rewards, all inside libssd_b200 (ssd_step_host)."""

@@ -468,6 +468,17 @@ int ssd_render(ssd_handle h, int rotate, uint8_t* obs_out, void* stream) {
     return SSD_OK;
 }
 
+int ssd_render_map(ssd_handle h, uint8_t* rgb_out, void* stream) {
+    if (check_handle(h)) return SSD_ERR_INVALID;
+    if (!rgb_out) return fail(SSD_ERR_INVALID, "rgb_out is required");
+    h->chain.valid = false;
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(ssd::launch_render_map(h->B, h->cfg.num_agents, h->cfg.height, h->cfg.width, h->Ws, h->env_bytes, h->d_grid, h->d_agents,
+                                    h->d_color, rgb_out, static_cast<cudaStream_t>(stream)));
+    h->launches++;
+    return SSD_OK;
+}
+
 int ssd_step_host(ssd_handle h, const int8_t* actions_host, uint8_t* obs_host, int32_t* reward_host) {
     if (check_handle(h)) return SSD_ERR_INVALID;
     h->chain.valid = false;

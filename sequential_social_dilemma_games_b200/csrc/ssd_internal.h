@@ -169,6 +169,8 @@ cudaError_t launch_pack_state(int kind, int B, int N, int H, int W, int Ws, int 
                               const uint8_t* ori_in, uint8_t* grid, uint32_t* agents, cudaStream_t stream);
 cudaError_t launch_unpack_state(int B, int N, int H, int W, int Ws, int env_bytes, const uint8_t* grid, const uint32_t* agents,
                                 uint8_t* grid_out, int16_t* pos_out, uint8_t* ori_out, cudaStream_t stream);
+cudaError_t launch_render_map(int B, int N, int H, int W, int Ws, int env_bytes, const uint8_t* grid, const uint32_t* agents,
+                              const uint32_t* color, uint8_t* out, cudaStream_t stream);
 cudaError_t launch_philox_selftest(const uint32_t* ctr_key, uint32_t* out, cudaStream_t stream);
 
 // ASCII <-> device cell byte (host helpers shared with ssd_capi.cu)

@@ -1292,6 +1292,25 @@ __global__ void unpack_state_kernel(int B, int N, int H, int W, int Ws, int env_
         if (ori_out != nullptr) ori_out[i] = (w >> 16) & 3;
     }
 }
+// Full-map frames: map_to_colors(get_map_with_agents()) (map_env.py:280-339) for every env, uint8 [B][H][W][3].
+// One thread per output pixel triple; the agents of the env are painted in agent order (the last one on a cell wins).
+// Beams are not part of the persistent state (map_env.py:169 clears them every step) and are not drawn.
+__global__ void render_map_kernel(int B, int N, int H, int W, int Ws, int env_bytes, const uint8_t* grid, const uint32_t* agents,
+                                  const uint32_t* color, uint8_t* out) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const size_t HW = static_cast<size_t>(H) * W;
+    if (i >= static_cast<size_t>(B) * HW) return;
+    const size_t b = i / HW, q = i % HW;
+    const uint32_t r = static_cast<uint32_t>(q / W), c = static_cast<uint32_t>(q % W);
+    uint8_t cell = grid[b * env_bytes + r * Ws + c] & 0x7F;
+    for (int ag = 0; ag < N; ++ag) {
+        const uint32_t w = agents[b * N + ag];
+        if ((w & 255u) == r && ((w >> 8) & 255u) == c) cell = agent_cell(ag);
+    }
+    const uint32_t rgb = color[cell];
+    out[3 * i] = rgb & 255; out[3 * i + 1] = (rgb >> 8) & 255; out[3 * i + 2] = (rgb >> 16) & 255;
+}
+
 __global__ void philox_selftest_kernel(const uint32_t* ck, uint32_t* out) {
     const uint4 v = philox4x32_10(ck[0], ck[1], ck[2], ck[3], ck[4], ck[5]);
     out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
@@ -1449,6 +1468,12 @@ cudaError_t launch_unpack_state(int B, int N, int H, int W, int Ws, int env_byte
     const size_t hw = static_cast<size_t>(H) * W;
     const size_t n = static_cast<size_t>(B) * (hw > static_cast<size_t>(N) ? hw : N);
     unpack_state_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(B, N, H, W, Ws, env_bytes, grid, agents, grid_out, pos_out, ori_out);
+    return cudaGetLastError();
+}
+cudaError_t launch_render_map(int B, int N, int H, int W, int Ws, int env_bytes, const uint8_t* grid, const uint32_t* agents,
+                              const uint32_t* color, uint8_t* out, cudaStream_t stream) {
+    const size_t n = static_cast<size_t>(B) * H * W;
+    render_map_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(B, N, H, W, Ws, env_bytes, grid, agents, color, out);
     return cudaGetLastError();
 }
 cudaError_t launch_philox_selftest(const uint32_t* ctr_key, uint32_t* out, cudaStream_t stream) {

@@ -164,6 +164,26 @@ def test_chained_steps(game):
     assert k0 == k1 and k0["env_steps"] == B * T
 
 
+@pytest.mark.parametrize("game", ["harvest", "cleanup"])
+def test_render_map(game):
+    """ssd_render_map == map_to_colors(get_map_with_agents()) (map_env.py:280-339) computed on the host from the state."""
+    from sequential_social_dilemma_games_b200.batched import make_config
+    cfg = make_config(game, num_agents=10)
+    env = _env(cfg, 37, seed=4)
+    env.reset()
+    rng = np.random.RandomState(1)
+    for _ in range(5):
+        env.step(_random_actions(rng, cfg, 37))
+    frames = env.render_map().cpu().numpy()
+    g, p, o = _state(env)
+    lut = np.asarray(cfg.colour_lut).reshape(128, 3)
+    for b in range(37):
+        chars = g[b].copy()
+        for ag in range(cfg.num_agents):  # str(int(agent_id[-1]) + 1) in a <U1 array: agent-9 shows as '1'
+            chars[p[b, ag, 0], p[b, ag, 1]] = ord(str((ag % 10) + 1)[0])
+        assert np.array_equal(frames[b], lut[chars]), (game, b)
+
+
 def test_reset_needs_spawn_points():
     """'There are not enough spawn points! Check your map?' (map_env.py:661) is raised by reset, not by construction:
     the adapters place hand-made agents with ssd_set_state on maps with fewer 'P' cells than agents."""
