@@ -861,13 +861,15 @@ __device__ __forceinline__ void render_rows_tma(const uint2* s_view, const uint8
     const int n_chunks = (total_rows + 31) >> 5;  // >= 2: a warp renders at least 4 * VT rows
     const int end_last = mis + (total_rows - (n_chunks - 1) * 32) * RB;  // valid image bytes of the last chunk (multiple of 4)
     const int hi_last = min(CH, end_last & ~15);
-    uint8_t* out = dst - mis;  // 16-byte aligned image of chunk 0
+    uint8_t* const img0 = dst - mis;  // 16-byte aligned image of chunk 0
     const uint32_t stage32 = smem_u32(stage);
     // where lane 31 parks the words that spill over a chunk: the head of the next image, or a dummy slot
     uint32_t* const k1 = stage + (mis4 >= 1 ? mis4 - 1 : CH / 4 + 5);
     uint32_t* const k2 = stage + (mis4 >= 2 ? mis4 - 2 : CH / 4 + 6);
     uint32_t* const k3 = stage + (mis4 >= 3 ? mis4 - 3 : CH / 4 + 7);
-    int lo = mis != 0 ? 16 : 0;  // the first 16 - mis bytes of the slab leave with plain stores
+    const int lo0 = mis != 0 ? 16 : 0;  // the first 16 - mis bytes of the slab leave with plain stores
+    uint8_t* gp = img0 + lo0;           // destination, source and size of the next bulk store
+    uint32_t sp = stage32 + lo0, nb = CH - lo0;
     uint32_t c0 = 0, c1 = 0, c2 = 0;
 #pragma unroll 1
     for (int c = 0; c < n_chunks; ++c) {
@@ -902,19 +904,18 @@ __device__ __forceinline__ void render_rows_tma(const uint2* s_view, const uint8
         c0 = Q[M31 - 3]; c1 = Q[M31 - 2]; c2 = Q[M31 - 1];
         fence_async_smem();
         __syncwarp();
-        const int hi = (c == n_chunks - 1) ? hi_last : CH;
+        if (c == n_chunks - 1) nb = hi_last;  // n_chunks >= 2: the last chunk starts at the head of the buffer
         if (lane == 0 && !(debug & 1)) {
-            bulk_s2g_u32(out + lo, stage32 + lo, static_cast<uint32_t>(hi - lo));
+            bulk_s2g_u32(gp, sp, nb);
             bulk_commit();
         }
         if (c == 0 && lane >= mis4 && lane < 4 && mis != 0)  // first bytes of the slab
-            *reinterpret_cast<uint32_t*>(out + 4 * lane) = stage[lane];
-        lo = 0;
-        out += CH;
+            *reinterpret_cast<uint32_t*>(img0 + 4 * lane) = stage[lane];
+        gp += nb; sp = stage32; nb = CH;
     }
-    {   // last bytes of the slab (out was advanced once past the last chunk)
+    {   // last bytes of the slab
         const int off = hi_last + 4 * lane;
-        if (off < end_last) *reinterpret_cast<uint32_t*>(out - CH + off) = stage[off >> 2];
+        if (off < end_last) *reinterpret_cast<uint32_t*>(img0 + static_cast<size_t>(n_chunks - 1) * CH + off) = stage[off >> 2];
     }
     bulk_wait_read();  // shared memory must outlive the last bulk read
 }
