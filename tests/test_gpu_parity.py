@@ -201,6 +201,36 @@ def test_reset_needs_spawn_points():
     assert rew.cpu().numpy().tolist() == [[1, 0, 0]] * 4
 
 
+def test_full_size_episode_vs_oracle():
+    """BASELINE.json configs[2] at full size against the CPU oracle: 65536 Harvest envs, chained steps, 300 steps of one
+    episode.  Rewards are compared every step, the full state and the observations every 50 steps, the counters at
+    the end -- bit for bit."""
+    import os
+    from oracle.oracle import OracleEnv
+    from sequential_social_dilemma_games_b200.batched import make_config
+    cfg = make_config("harvest")
+    B, T = 65536, 300
+    env = _env(cfg, B, seed=2026).chain_steps(True)
+    orc = OracleEnv(cfg, B, seed=2026, n_threads=min(os.cpu_count() or 1, 64))
+    assert np.array_equal(env.reset().cpu().numpy(), orc.reset())
+    g = torch.Generator(device="cuda").manual_seed(11)
+    ring = torch.randint(0, cfg.num_actions, (16, B, cfg.num_agents), generator=g, device="cuda", dtype=torch.int8)
+    ring_h = ring.cpu().numpy()
+    rews = []
+    for t0 in range(0, T, 50):
+        for t in range(t0, t0 + 50):  # 50 chained launches back to back, then ordinary stream-ordered reads
+            obs, rew = env.step(ring[t % 16])
+            rews.append(rew.clone())
+        for t in range(t0, t0 + 50):
+            oobs, orew = orc.step(ring_h[t % 16])
+            assert np.array_equal(rews[t].cpu().numpy(), orew), t
+        _assert_state(env, orc.grid, orc.pos, orc.ori, ("full", t0))
+        assert np.array_equal(obs.cpu().numpy(), oobs), t0
+    st = env.stats()
+    for i, k in enumerate(("env_steps", "reward_sum", "apples_eaten", "fires", "hits", "cleaned", "apples_spawned", "waste_spawned")):
+        assert st[k] == int(orc.stats[i]), (k, st, orc.stats)
+
+
 def test_full_size_properties():
     """BASELINE.json configs[2] size (65536 Harvest envs): properties that need no oracle.
     (a) shard invariance: two handles of 32768 envs with env_id_offset reproduce the single
