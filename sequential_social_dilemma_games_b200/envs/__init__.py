@@ -4,3 +4,4 @@ from .agent import (Agent, BASE_ACTIONS, CLEANUP_ACTIONS, CleanupAgent, HARVEST_
 from .cleanup import CleanupEnv  # noqa: F401
 from .harvest import HarvestEnv  # noqa: F401
 from .map_env import ACTIONS, DEFAULT_COLOURS, MapEnv, ORIENTATIONS  # noqa: F401
+from .vector_env import SSDVectorEnv  # noqa: F401

@@ -60,3 +60,55 @@ def test_fixture_replay_through_the_dict_api():
             assert np.array_equal(np.vectorize(ord)(env.world_map), fx["grid"][t, b]), (b, t)
             for a in range(fx.N):
                 assert np.array_equal(obs['agent-%d' % a], lut[fx["obs"][t, b, a]]), (b, t, a)
+
+
+@pytest.mark.parametrize("game", ["harvest", "cleanup"])
+def test_vector_env_against_oracle(game):
+    """SSDVectorEnv (RLlib VectorEnv surface over one batched device state, production Philox streams): list-of-dicts
+    in, list-of-dicts out, against the CPU oracle on the same seeds -- partial action dicts, dict iteration order as the
+    action order, reset_at of single rows, horizon, return_agent_actions extras."""
+    from oracle.oracle import OracleEnv
+    from sequential_social_dilemma_games_b200.envs import SSDVectorEnv
+    B, N, T = 6, 4, 40
+    venv = SSDVectorEnv(game, B, num_agents=N, seed=77, horizon=25, return_agent_actions=True, env_id_offset=3)
+    orc = OracleEnv(venv.cfg, B, seed=77, env_id_offset=3, n_threads=2)
+    lut = (np.arange(256) - 128.0) / 255.0
+    obs = venv.vector_reset()
+    oobs = orc.reset()
+    for b in range(B):
+        for i in range(N):
+            o = obs[b]['agent-%d' % i]
+            assert np.array_equal(o["curr_obs"], lut[oobs[b, i]])
+            assert np.array_equal(o["other_agent_actions"], np.zeros(N - 1, np.int64)) and o["visible_agents"].tolist() == [1] * (N - 1)
+    rng = np.random.RandomState(0)
+    n_act = venv.action_space.n
+    for t in range(T):
+        acts, a8, order = [], np.full((B, N), -1, np.int8), np.zeros((B, N), np.uint8)
+        for b in range(B):
+            perm = rng.permutation(N) if b % 2 else np.arange(N)
+            present = [int(i) for i in perm if rng.rand() < 0.85]
+            d = {}
+            for i in present:
+                d['agent-%d' % i] = int(rng.randint(n_act))
+                a8[b, i] = d['agent-%d' % i]
+            acts.append(d)
+            order[b] = present + [i for i in range(N) if i not in present]
+        obs, rew, dones, infos = venv.vector_step(acts)
+        oobs, orew = orc.step(a8, action_order=order)
+        for b in range(B):
+            assert infos[b] == {} and dones[b]["__all__"] == (venv._t[b] >= 25)
+            assert [rew[b]['agent-%d' % i] for i in range(N)] == orew[b].tolist(), (t, b)
+            for i in range(N):
+                o = obs[b]['agent-%d' % i]
+                assert np.array_equal(o["curr_obs"], lut[oobs[b, i]]), (t, b, i)
+                others = [acts[b][k] for k in sorted(acts[b]) if k != 'agent-%d' % i]
+                assert o["other_agent_actions"].tolist() == others
+    # reset_at: only that row changes, its counter restarts, and the returned (un-rotated) views match a fresh render
+    before = [x.cpu().numpy().copy() for x in venv.engine.get_state()]
+    o2 = venv.reset_at(2)
+    after = [x.cpu().numpy() for x in venv.engine.get_state()]
+    keep = [b for b in range(B) if b != 2]
+    assert all(np.array_equal(x[keep], y[keep]) for x, y in zip(before, after)) and venv._t[2] == 0 and venv._t[1] == T
+    fresh = venv.engine.render(rotate=False).cpu().numpy()
+    assert all(np.array_equal(o2['agent-%d' % i]["curr_obs"], lut[fresh[2, i]]) for i in range(N))
+    venv.close()
