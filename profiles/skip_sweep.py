@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """Marginal time of the phases of the fused step: SSD_DEBUG_SKIP bits (1 no bulk stores, 2 no render,
-4 no spawn, 8 no beams) at two batch sizes.  Results with a skip bit set are WRONG by construction."""
+4 no spawn, 8 no beams, 16 no literal move emulation, 32 no stats, 64 no grid write-back) at two batch sizes.
+Needs a library built with SSD_PROFILING_KNOBS=1 python -m sequential_social_dilemma_games_b200.build --force (a
+production build compiles the knobs out).  Results with a skip bit set are WRONG by construction."""
 import os
 import subprocess
 import sys

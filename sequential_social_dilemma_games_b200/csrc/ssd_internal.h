@@ -46,6 +46,14 @@ enum : uint8_t {
     kLutEntries = 4 * kNumCodes  // colour table indexed by the grid byte
 };
 __host__ __device__ constexpr uint8_t CB(uint8_t code) { return static_cast<uint8_t>(code * 4); }
+// Phase-skip knobs for timing experiments (profiles/skip_sweep.py).  A production build compiles them out:
+// SSD_SKIP(a, bit) is the constant false unless the library is built with -DSSD_PROFILING_KNOBS.
+#ifdef SSD_PROFILING_KNOBS
+#define SSD_SKIP(dbg, bit) (((dbg) & (bit)) != 0)
+#else
+#define SSD_SKIP(dbg, bit) false
+#endif
+
 constexpr uint8_t kFlag = 0x80;
 constexpr uint8_t kCodeMask = 0x7C;  // cell code without the neighbour count and the agent flag
 
@@ -105,7 +113,7 @@ struct StepArgs {
     int pad_bytes;        // zero bytes between / around the tiles in shared memory
     int n_apple, n_waste, area;
     int harvest_nz;       // bit n: SPAWN_PROB[n] != 0 (harvest.py:13)
-    int debug;            // SSD_DEBUG_SKIP bits (profiling experiments only; 0 in production)
+    int debug;            // SSD_DEBUG_SKIP bits; only read by builds with -DSSD_PROFILING_KNOBS (profiles/skip_sweep.py)
     int obs_env;          // N*V*V*3 bytes
     // ---- launch description
     int G;                // lanes per env in phase A: 8 (N <= 8) or 16

@@ -217,7 +217,7 @@ __device__ __forceinline__ void moves_group(const StepArgs& a, ES& S, MoveScratc
     if (conf_all != 0) {  // warp-uniform branch: groups without a conflict just keep the barriers company
         if (conf != 0 && valid) { S.pos[al] = static_cast<uint16_t>(me.key); M.tgt[al] = static_cast<uint16_t>(tgt); }
         __syncwarp();
-        if (conf != 0 && al == 0 && !(a.debug & 16)) moves_slow<TAPE, ES>(a, S, M, movers, local_env, pk);
+        if (conf != 0 && al == 0 && !SSD_SKIP(a.debug, 16)) moves_slow<TAPE, ES>(a, S, M, movers, local_env, pk);
         __syncwarp();
         if (conf != 0 && valid) me.key = S.pos[al];
     }
@@ -905,7 +905,7 @@ __device__ __forceinline__ void render_rows_tma(const uint2* s_view, const uint8
         fence_async_smem();
         __syncwarp();
         if (c == n_chunks - 1) nb = hi_last;  // n_chunks >= 2: the last chunk starts at the head of the buffer
-        if (lane == 0 && !(debug & 1)) {
+        if (lane == 0 && !SSD_SKIP(debug, 1)) {
             bulk_s2g_u32(gp, sp, nb);
             bulk_commit();
         }
@@ -1012,7 +1012,7 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
         uint32_t* const fire_list = reinterpret_cast<uint32_t*>(wbase + a.Lf.w_union);
         const int ray_f = lane / 3, ray_s = lane - 3 * ray_f;  // Harvest: ray lane -> (firing agent of the round, ray)
         uint32_t fire_ent = 0;
-        if (KIND == SSD_KIND_HARVEST && !(a.debug & 8)) {
+        if (KIND == SSD_KIND_HARVEST && !SSD_SKIP(a.debug, 8)) {
             // update_custom_moves map_env.py:545-552.  Harvest has only 'F' beams: they change no cell, so the
             // firing order is irrelevant and the rays of ALL firing agents of the warp walk at once, 3 lanes each.
             const bool fire_me = me.act == 7;
@@ -1037,7 +1037,7 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
                 __syncwarp();
             }
         }
-        if (KIND == SSD_KIND_CLEANUP && !(a.debug & 8)) {  // firing order matters: a CLEAN beam turns 'H' into 'R' for the next one
+        if (KIND == SSD_KIND_CLEANUP && !SSD_SKIP(a.debug, 8)) {  // firing order matters: a CLEAN beam turns 'H' into 'R' for the next one
             fmask = __ballot_sync(0xffffffffu, me.act == 7 || me.act == 8);
             for (int k = 0; k < N; ++k) {
                 if (!((fmask >> k) & 0x01010101u)) continue;  // nobody in this warp fires in slot k
@@ -1065,7 +1065,7 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
         }
 
         // ---- phase B: the whole warp per env
-        if (KIND != SSD_KIND_PLAIN && !(a.debug & 4)) {
+        if (KIND != SSD_KIND_PLAIN && !SSD_SKIP(a.debug, 4)) {
             void* scratch = wbase + a.Lf.w_union;
             if (KIND == SSD_KIND_HARVEST) {
                 harvest_spawn_warp<TAPE>(a, tiles, tile_pitch, s_apple, static_cast<uint32_t*>(scratch), a.Lf.u_words, we, pk, lane, cnt);
@@ -1082,7 +1082,7 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
         }
 
         // ---- store: grid tiles back to HBM
-        if (!(a.debug & 64)) {
+        if (!SSD_SKIP(a.debug, 64)) {
             const int n16 = a.env_bytes >> 4;
 #pragma unroll
             for (int q = 0; q < EPW; ++q) {
@@ -1153,7 +1153,7 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
                                                 (static_cast<uint32_t>(si) & 0xffffu) | static_cast<uint32_t>(sj) << 16);
             }
             __syncwarp();
-            if (!(a.debug & 2))
+            if (!SSD_SKIP(a.debug, 2))
             render_rows_tma<VT>(s_view, tiles, s_color, reinterpret_cast<uint32_t*>(wbase + a.Lf.w_union + a.Lf.u_stage),
                                 a.obs + static_cast<size_t>(we) * a.obs_env, EPW * N * VT, a.debug);
         }
@@ -1168,7 +1168,7 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
     }
 
     // ---- stats: warp -> CTA -> one set of global atomics per CTA (issued by the last warp to finish)
-    if (a.stats != nullptr && !(a.debug & 32)) {
+    if (a.stats != nullptr && !SSD_SKIP(a.debug, 32)) {
         // per-warp totals are small (4 envs): two packed reductions carry all seven counters
         const uint32_t r0 = __reduce_add_sync(0xffffffffu, static_cast<uint32_t>(cnt.steps | cnt.eaten << 8 | cnt.fires << 16 | cnt.hits << 24));
         const uint32_t r1 = __reduce_add_sync(0xffffffffu, static_cast<uint32_t>(cnt.cleaned | cnt.apples << 10 | cnt.waste << 20));
@@ -1318,6 +1318,7 @@ __global__ void philox_selftest_kernel(const uint32_t* ck, uint32_t* out) {
 }
 
 // ====================================================================== launchers
+constexpr int kMaxDevices = 64;
 template <int KIND, bool TAPE>
 static cudaError_t launch_v(const StepArgs& a, int threads, cudaStream_t stream, bool fast_rows) {
     const int envs_per_cta = (threads / 32) * (32 / a.G);
@@ -1327,11 +1328,14 @@ static cudaError_t launch_v(const StepArgs& a, int threads, cudaStream_t stream,
 #define SSD_LAUNCH(VT_)                                                                                         \
     do {                                                                                                        \
         auto kern = ssd_step_kernel<KIND, TAPE, VT_>;                                                           \
-        static uint32_t smem_set = 0;                                                                           \
-        if (a.L.total > smem_set) {                                                                             \
+        static uint32_t smem_set[kMaxDevices] = {};  /* the attribute is per device */                          \
+        int dev_ = 0;                                                                                           \
+        cudaGetDevice(&dev_);                                                                                   \
+        dev_ = dev_ < kMaxDevices ? dev_ : kMaxDevices - 1;                                                     \
+        if (a.L.total > smem_set[dev_] || dev_ == kMaxDevices - 1) {                                            \
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, a.L.total); \
             if (e != cudaSuccess) return e;                                                                     \
-            smem_set = a.L.total;                                                                               \
+            smem_set[dev_] = a.L.total;                                                                         \
         }                                                                                                       \
         kern<<<ctas, threads, a.L.total, stream>>>(a);                                                          \
         return cudaGetLastError();                                                                              \
@@ -1353,11 +1357,14 @@ static cudaError_t launch_fast(const StepArgs& a, int threads, cudaStream_t stre
 #define SSD_LAUNCH_FAST(VT_)                                                                                    \
     do {                                                                                                        \
         auto kern = ssd_step_fast_kernel<KIND, TAPE, VT_>;                                                      \
-        static uint32_t smem_set = 0;                                                                           \
-        if (a.Lf.total > smem_set) {                                                                            \
+        static uint32_t smem_set[kMaxDevices] = {};  /* the attribute is per device */                          \
+        int dev_ = 0;                                                                                           \
+        cudaGetDevice(&dev_);                                                                                   \
+        dev_ = dev_ < kMaxDevices ? dev_ : kMaxDevices - 1;                                                     \
+        if (a.Lf.total > smem_set[dev_] || dev_ == kMaxDevices - 1) {                                           \
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, a.Lf.total); \
             if (e != cudaSuccess) return e;                                                                     \
-            smem_set = a.Lf.total;                                                                              \
+            smem_set[dev_] = a.Lf.total;                                                                        \
         }                                                                                                       \
         cudaLaunchConfig_t lc = {};                                                                             \
         lc.gridDim = dim3(ctas); lc.blockDim = dim3(threads); lc.dynamicSmemBytes = a.Lf.total; lc.stream = stream; \
@@ -1420,7 +1427,8 @@ cudaError_t launch_step(const StepArgs& a, int threads, cudaStream_t stream, Cha
         }
         const int ctas = (f.env_end - f.env_begin + (threads / 32) * 4 - 1) / ((threads / 32) * 4);
         chain_here = 2 * ctas >= 3 * slots && ctas <= 12 * slots;
-        if (getenv("SSD_CHAIN_ALWAYS")) chain_here = true;
+        static const bool chain_always = getenv("SSD_CHAIN_ALWAYS") != nullptr;  // experiments
+        if (chain_always) chain_here = true;
     }
     if (chain_here) {
         // Chained steps (SSD_OPT_CHAIN_STEPS): this launch may overlap the previous step's kernel when that was the
