@@ -98,7 +98,7 @@ ssd::SmemLayout make_layout(const SsdEnv& h, int threads, bool fast = false) {
     uint32_t w = 0;
     L.w_mbar = w; w += 16;
     L.w_tiles = w; w += epw * (h.env_bytes + h.pad_bytes) + h.pad_bytes;
-    L.w_env = w; w += epw * (fast ? sizeof(ssd::FastScratch) : sizeof(ssd::EnvScratch));
+    L.w_env = w; w += epw * (fast ? 10u * G : sizeof(ssd::EnvScratch));  // FastScratchT<G> is 10 bytes per lane
     L.w_union = w;
     L.u_stage = up16(epw * h.cfg.num_agents * 8);                          // view params first
     const uint32_t u_render = L.u_stage + up16(32u * 3u * h.V) + 32;       // + staging of 32 view rows, spill and dummy words
@@ -282,7 +282,7 @@ int ssd_create(const SsdConfig* cfg, ssd_handle* out) {
     bad |= h->alloc(&h->d_agents, static_cast<size_t>(h->B_pad) * N);
     bad |= h->alloc(&h->d_beam_buf, static_cast<size_t>(h->B_pad) * 64);
     bad |= h->alloc(&h->d_stats, static_cast<size_t>(SSD_NUM_STATS));
-    bad |= h->alloc(&h->chain.done, static_cast<size_t>(h->B_pad / 4 + 1));
+    bad |= h->alloc(&h->chain.done, static_cast<size_t>(h->B_pad / 2 + 1));  // one word per task (4 or 2 envs)
     if (bad) { const char* m = cudaGetErrorString(cudaGetLastError()); ssd_destroy(h); return fail(SSD_ERR_CUDA, "device allocation failed: %s", m); }
     // initial state: post-reset_map grid, agents parked on the first spawn point (or cell 1,1)
     {
@@ -294,7 +294,7 @@ int ssd_create(const SsdConfig* cfg, ssd_handle* out) {
         cudaError_t e2 = cudaMemcpy(h->d_agents, ag.data(), ag.size() * 4, cudaMemcpyHostToDevice);
         cudaError_t e3 = cudaMemset(h->d_stats, 0, SSD_NUM_STATS * sizeof(unsigned long long));
         cudaError_t e4 = cudaMemset(h->d_beam_buf, 0, static_cast<size_t>(h->B_pad) * 64);
-        if (e4 == cudaSuccess) e4 = cudaMemset(h->chain.done, 0, (static_cast<size_t>(h->B_pad) / 4 + 1) * sizeof(uint32_t));
+        if (e4 == cudaSuccess) e4 = cudaMemset(h->chain.done, 0, (static_cast<size_t>(h->B_pad) / 2 + 1) * sizeof(uint32_t));
         if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess) {
             ssd_destroy(h);
             return fail(SSD_ERR_CUDA, "state initialisation failed");

@@ -75,14 +75,15 @@ struct EnvScratch {
 };
 static_assert(sizeof(EnvScratch) % 16 == 0, "EnvScratch must stay 16-byte sized");
 
-// The same for the specialised full-step kernel (N <= 8, actions in agent order).
-struct FastScratch {
-    uint16_t pos[8];
-    int32_t rew[8];   // 32-bit: rays of different shooters add their -50 with shared-memory atomics
-    uint8_t raylen[24];
-    uint8_t order[8];
+// The same for the specialised full-step kernel (G = 8 or 16 lanes per env, actions in agent order).
+template <int G>
+struct FastScratchT {
+    uint16_t pos[G];
+    int32_t rew[G];   // 32-bit: rays of different shooters add their -50 with shared-memory atomics
+    uint8_t raylen[3 * G];
+    uint8_t order[G];
 };
-static_assert(sizeof(FastScratch) % 16 == 0, "FastScratch must stay 16-byte sized");
+static_assert(sizeof(FastScratchT<8>) == 80 && sizeof(FastScratchT<16>) == 160, "FastScratchT is 10 bytes per lane");
 
 // Scratch of the literal update_moves emulation (moves_slow); lives in the per-warp phase union.
 struct MoveScratch {

@@ -349,7 +349,7 @@ __device__ __forceinline__ void harvest_drain(const StepArgs& a, uint8_t* tiles,
     __syncwarp();
 }
 
-template <bool TAPE>
+template <bool TAPE, int EPW>
 __device__ __forceinline__ void harvest_spawn_warp(const StepArgs& a, uint8_t* tiles, int tile_pitch, const uint16_t* __restrict__ s_apple,
                                                    uint32_t* __restrict__ list, int cap, int we, const PhiloxKey& pk, int lane, Counters& cnt) {
     const int n_apple = a.n_apple;
@@ -357,7 +357,7 @@ __device__ __forceinline__ void harvest_spawn_warp(const StepArgs& a, uint8_t* t
     const uint32_t lt = lanemask_lt();
     int n_list = 0;
 #pragma unroll 1
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < EPW; ++q) {
         if (n_list + n_apple > cap) { harvest_drain<TAPE>(a, tiles, tile_pitch, list, n_list, we, pk, lane, cnt); n_list = 0; }
         const uint8_t* __restrict__ g = tiles + a.pad_bytes + q * tile_pitch;
         int base = 0;
@@ -920,9 +920,11 @@ __device__ __forceinline__ void render_rows_tma(const uint2* s_view, const uint8
     bulk_wait_read();  // shared memory must outlive the last bulk read
 }
 
-template <int KIND, bool TAPE, int VT>
+template <int KIND, bool TAPE, int VT, int G>
 __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid_constant__ StepArgs a) {
-    constexpr int G = 8, EPW = 4;
+    constexpr int EPW = 32 / G;                                       // envs per warp: 4 (N <= 8) or 2 (N <= 16)
+    constexpr uint32_t kSlotLsb = G == 8 ? 0x01010101u : 0x00010001u;  // bit 0 of every env's lane group
+    using FastScratch = FastScratchT<G>;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint32_t s_color[kLutEntries];
     __shared__ int s_cta_stats[SSD_NUM_STATS];
@@ -954,7 +956,7 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
             mbar_init(mbar, 1);
             mbar_expect_tx(mbar, static_cast<uint32_t>(EPW) * a.env_bytes);
             if (a.dep_wait) {  // chained step: the previous step's kernel may still be running; wait for OUR four envs only
-                while (ld_acquire_u32(a.done + (we >> 2)) != a.epoch - 1) __nanosleep(64);
+                while (ld_acquire_u32(a.done + we / EPW) != a.epoch - 1) __nanosleep(64);
                 fence_async_all();  // its ordinary stores -> our TMA loads
             }
         }
@@ -969,7 +971,7 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
                 for (int i = lane * 16; i < a.pad_bytes; i += 512) *reinterpret_cast<uint4*>(tiles + q * tile_pitch + i) = z;
         }
         // agent words and actions travel while the tiles do
-        const int al = lane & (G - 1), gbase = lane & ~(G - 1), j = lane >> 3;
+        const int al = lane & (G - 1), gbase = lane & ~(G - 1), j = lane / G;
         FastScratch& S = envs[j];
         uint8_t* g = tiles + a.pad_bytes + j * tile_pitch;
         const int e = we + j;
@@ -1040,7 +1042,7 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
         if (KIND == SSD_KIND_CLEANUP && !SSD_SKIP(a.debug, 8)) {  // firing order matters: a CLEAN beam turns 'H' into 'R' for the next one
             fmask = __ballot_sync(0xffffffffu, me.act == 7 || me.act == 8);
             for (int k = 0; k < N; ++k) {
-                if (!((fmask >> k) & 0x01010101u)) continue;  // nobody in this warp fires in slot k
+                if (!((fmask >> k) & kSlotLsb)) continue;  // nobody in this warp fires in slot k
                 const bool fire = (fmask >> (gbase + k)) & 1u;
                 const int act_k = __shfl_sync(0xffffffffu, me.act, k, G);
                 const uint32_t key_k = __shfl_sync(0xffffffffu, me.key, k, G);
@@ -1068,7 +1070,7 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
         if (KIND != SSD_KIND_PLAIN && !SSD_SKIP(a.debug, 4)) {
             void* scratch = wbase + a.Lf.w_union;
             if (KIND == SSD_KIND_HARVEST) {
-                harvest_spawn_warp<TAPE>(a, tiles, tile_pitch, s_apple, static_cast<uint32_t*>(scratch), a.Lf.u_words, we, pk, lane, cnt);
+                harvest_spawn_warp<TAPE, EPW>(a, tiles, tile_pitch, s_apple, static_cast<uint32_t*>(scratch), a.Lf.u_words, we, pk, lane, cnt);
             } else {
 #pragma unroll 1
                 for (int q = 0; q < EPW; ++q) {
@@ -1122,7 +1124,7 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
             }
             if (KIND == SSD_KIND_CLEANUP) {  // beams in firing order: a later beam overwrites an earlier one
                 for (int k = 0; k < N; ++k) {
-                    if (!((fmask >> k) & 0x01010101u)) continue;
+                    if (!((fmask >> k) & kSlotLsb)) continue;
                     const uint32_t key_k = __shfl_sync(0xffffffffu, me.key, k, G);
                     const int ori_k = __shfl_sync(0xffffffffu, me.ori, k, G);
                     const int act_k = __shfl_sync(0xffffffffu, me.act, k, G);
@@ -1162,18 +1164,19 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
             if (lane == 0) {
                 bulk_wait_all();
                 __threadfence();
-                st_release_u32(a.done + (we >> 2), a.epoch);
+                st_release_u32(a.done + we / EPW, a.epoch);
             }
         }
     }
 
     // ---- stats: warp -> CTA -> one set of global atomics per CTA (issued by the last warp to finish)
     if (a.stats != nullptr && !SSD_SKIP(a.debug, 32)) {
-        // per-warp totals are small (4 envs): two packed reductions carry all seven counters
+        // per-warp totals are small (<= 32 agents): two packed reductions carry all seven counters
+        //   r0: steps | eaten << 8 | fires << 16 | hits << 24 (hits <= 3 per shooter)     r1: cleaned | waste << 8 | apples << 12
         const uint32_t r0 = __reduce_add_sync(0xffffffffu, static_cast<uint32_t>(cnt.steps | cnt.eaten << 8 | cnt.fires << 16 | cnt.hits << 24));
-        const uint32_t r1 = __reduce_add_sync(0xffffffffu, static_cast<uint32_t>(cnt.cleaned | cnt.apples << 10 | cnt.waste << 20));
+        const uint32_t r1 = __reduce_add_sync(0xffffffffu, static_cast<uint32_t>(cnt.cleaned | cnt.waste << 8 | cnt.apples << 12));
         if (lane < 7) {
-            const uint32_t v = lane < 4 ? (r0 >> (8 * lane)) & 255u : (lane == 6 ? r1 >> 20 : (r1 >> (10 * (lane - 4))) & 1023u);
+            const uint32_t v = lane < 4 ? (r0 >> (8 * lane)) & 255u : (lane == 4 ? r1 & 255u : (lane == 5 ? r1 >> 12 : (r1 >> 8) & 15u));
             if (v) atomicAdd(&s_cta_stats[lane == 0 ? 0 : lane + 1], static_cast<int>(v));
         }
         __syncwarp();
@@ -1349,14 +1352,14 @@ static cudaError_t launch_v(const StepArgs& a, int threads, cudaStream_t stream,
 #undef SSD_LAUNCH
 }
 
-template <int KIND, bool TAPE>
+template <int KIND, bool TAPE, int G>
 static cudaError_t launch_fast(const StepArgs& a, int threads, cudaStream_t stream) {
-    const int envs_per_cta = (threads / 32) * 4;
+    const int envs_per_cta = (threads / 32) * (32 / G);
     const int ctas = (a.env_end - a.env_begin + envs_per_cta - 1) / envs_per_cta;
     if (ctas <= 0) return cudaSuccess;
 #define SSD_LAUNCH_FAST(VT_)                                                                                    \
     do {                                                                                                        \
-        auto kern = ssd_step_fast_kernel<KIND, TAPE, VT_>;                                                      \
+        auto kern = ssd_step_fast_kernel<KIND, TAPE, VT_, G>;                                                      \
         static uint32_t smem_set[kMaxDevices] = {};  /* the attribute is per device */                          \
         int dev_ = 0;                                                                                           \
         cudaGetDevice(&dev_);                                                                                   \
@@ -1404,14 +1407,15 @@ cudaError_t launch_step(const StepArgs& a, int threads, cudaStream_t stream, Cha
     // a production step: everything the specialised kernel assumes (see ssd_step_fast_kernel)
     static const bool no_fast = getenv("SSD_NO_FAST") != nullptr;
     const bool full = !no_fast && a.phases == SSD_PHASE_ALL && a.mask == nullptr && a.order == nullptr && !a.use_beam_buf &&
-                      !a.rew_accumulate && a.obs != nullptr && a.rew != nullptr && a.actions != nullptr && a.G == 8 && fast_rows &&
-                      (a.V == 11 || a.V == 15 || a.V == 21) && a.env_begin % 4 == 0;
+                      !a.rew_accumulate && a.obs != nullptr && a.rew != nullptr && a.actions != nullptr && fast_rows &&
+                      (a.V == 11 || a.V == 15 || a.V == 21) && a.env_begin % (32 / a.G) == 0;
     if (!full) {
         if (chain) chain->valid = false;
         return launch_general(a, threads, stream, fast_rows);
     }
     StepArgs f = a;
-    f.env_end = a.env_begin + (a.env_end - a.env_begin) / 4 * 4;  // whole warps
+    const int epw = 32 / a.G;
+    f.env_end = a.env_begin + (a.env_end - a.env_begin) / epw * epw;  // whole warps
     const bool has_tail = f.env_end != a.env_end;
     // Chaining pays when a step is a few waves of CTAs (it hides launch, ramp and the half-empty last wave); a single
     // wave has no tail to hide and very long grids amortise it anyway, while the completion words cost a little
@@ -1425,7 +1429,7 @@ cudaError_t launch_step(const StepArgs& a, int threads, cudaStream_t stream, Cha
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
             slots = sms * 8;
         }
-        const int ctas = (f.env_end - f.env_begin + (threads / 32) * 4 - 1) / ((threads / 32) * 4);
+        const int ctas = (f.env_end - f.env_begin + (threads / 32) * epw - 1) / ((threads / 32) * epw);
         chain_here = 2 * ctas >= 3 * slots && ctas <= 12 * slots;
         static const bool chain_always = getenv("SSD_CHAIN_ALWAYS") != nullptr;  // experiments
         if (chain_always) chain_here = true;
@@ -1443,19 +1447,17 @@ cudaError_t launch_step(const StepArgs& a, int threads, cudaStream_t stream, Cha
         chain->valid = false;
     }
     cudaError_t e = cudaSuccess;
+#define SSD_FAST(KIND_)                                                                                                     \
+    e = a.G == 8 ? (tape ? launch_fast<KIND_, true, 8>(f, threads, stream) : launch_fast<KIND_, false, 8>(f, threads, stream)) \
+                 : (tape ? launch_fast<KIND_, true, 16>(f, threads, stream) : launch_fast<KIND_, false, 16>(f, threads, stream))
     switch (a.kind) {
-        case SSD_KIND_HARVEST:
-            e = tape ? launch_fast<SSD_KIND_HARVEST, true>(f, threads, stream) : launch_fast<SSD_KIND_HARVEST, false>(f, threads, stream);
-            break;
-        case SSD_KIND_CLEANUP:
-            e = tape ? launch_fast<SSD_KIND_CLEANUP, true>(f, threads, stream) : launch_fast<SSD_KIND_CLEANUP, false>(f, threads, stream);
-            break;
-        default:
-            e = tape ? launch_fast<SSD_KIND_PLAIN, true>(f, threads, stream) : launch_fast<SSD_KIND_PLAIN, false>(f, threads, stream);
-            break;
+        case SSD_KIND_HARVEST: SSD_FAST(SSD_KIND_HARVEST); break;
+        case SSD_KIND_CLEANUP: SSD_FAST(SSD_KIND_CLEANUP); break;
+        default: SSD_FAST(SSD_KIND_PLAIN); break;
     }
+#undef SSD_FAST
     if (e != cudaSuccess || !has_tail) return e;
-    StepArgs tail = a;  // the last 1..3 envs
+    StepArgs tail = a;  // the envs that do not fill a warp
     tail.env_begin = f.env_end;
     return launch_general(tail, threads, stream, fast_rows);
 }
