@@ -201,6 +201,42 @@ def test_reset_needs_spawn_points():
     assert rew.cpu().numpy().tolist() == [[1, 0, 0]] * 4
 
 
+@pytest.mark.parametrize("B", [32768, 32770])
+def test_chain_is_broken_safely(B):
+    """Chained stepping interleaved with everything else a caller may do (masked reset, state download / upload,
+    render, a step with an explicit action order, a batch that leaves a tail for the general kernel): same results
+    as an unchained handle."""
+    from sequential_social_dilemma_games_b200.batched import make_config
+    cfg = make_config("harvest")
+    g = torch.Generator(device="cuda").manual_seed(5)
+    ring = torch.randint(0, cfg.num_actions, (8, B, cfg.num_agents), generator=g, device="cuda", dtype=torch.int8)
+    mask = (torch.arange(B, device="cuda") % 3 == 0).to(torch.uint8)
+    order = torch.argsort(torch.rand((B, cfg.num_agents), generator=g, device="cuda"), dim=1).to(torch.uint8)
+    finals = []
+    for chained in (False, True):
+        env = _env(cfg, B, seed=31).chain_steps(chained)
+        env.reset()
+        log = []
+        for t in range(30):
+            env.step(ring[t % 8])
+        env.reset(mask=mask)
+        for t in range(30, 45):
+            env.step(ring[t % 8])
+        st = [x.clone() for x in env.get_state()]
+        env.set_state(*st)
+        for t in range(45, 60):
+            env.step(ring[t % 8])
+        log.append(env.render(rotate=True).clone())
+        env.step(ring[3], action_order=order)
+        for t in range(61, 75):
+            obs, rew = env.step(ring[t % 8])
+        torch.cuda.synchronize()
+        finals.append((log[0], obs.clone(), rew.clone(), [x.cpu().numpy() for x in env.get_state()], env.stats()))
+    a, b = finals
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+    assert all(np.array_equal(x, y) for x, y in zip(a[3], b[3])) and a[4] == b[4]
+
+
 def test_full_size_episode_vs_oracle():
     """BASELINE.json configs[2] at full size against the CPU oracle: 65536 Harvest envs, chained steps, 300 steps of one
     episode.  Rewards are compared every step, the full state and the observations every 50 steps, the counters at
