@@ -7,7 +7,7 @@ import sys
 from collections import Counter, defaultdict
 
 
-def main(path, lo, hi, nenv=65536.0, fname="ssd_step.cu"):
+def main(path, lo, hi, nenv=65536.0, fname="ssd_step_fast.cu"):
     cur_file, cur_line, hdr = None, None, None
     byline, src, total = defaultdict(Counter), {}, Counter()
     for r in csv.reader(open(path)):
@@ -41,4 +41,4 @@ def main(path, lo, hi, nenv=65536.0, fname="ssd_step.cu"):
 
 if __name__ == "__main__":
     main(sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), float(sys.argv[4]) if len(sys.argv) > 4 else 65536.0,
-         sys.argv[5] if len(sys.argv) > 5 else "ssd_step.cu")
+         sys.argv[5] if len(sys.argv) > 5 else "ssd_step_fast.cu")

@@ -1,20 +1,24 @@
 #!/usr/bin/env python
 """Per-function-region and per-stall-reason totals of an `ncu --page source --csv --print-source cuda,sass`
-dump of ssd_step_kernel.  Regions are found from the `__device__`/`__global__` function headers of
-csrc/ssd_step.cu, so the script follows the source as it changes.
+dump of the step kernels.  Regions are found from the `__device__`/`__global__` function headers of
+csrc/ssd_phases.cuh, ssd_step_fast.cu and ssd_step_general.cu, so the script follows the source as it changes.
+(ncu attributes an inlined instruction to the call site AND the callee line: the per-region sums overlap a little.)
 Usage: python profiles/ncu_regions.py both.csv <num_envs_per_launch> [num_launches_in_dump]"""
 import csv
 import os
 import re
 import sys
 
-SRC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
-                   "sequential_social_dilemma_games_b200", "csrc", "ssd_step.cu")
+CSRC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "sequential_social_dilemma_games_b200", "csrc")
+FILES = ("ssd_phases.cuh", "ssd_step_fast.cu", "ssd_step_general.cu")  # older dumps: one file, ssd_step.cu
 
 
-def regions():
+def regions(fname):
     out, cur = [], None
-    for ln, line in enumerate(open(SRC), 1):
+    path = os.path.join(CSRC, fname)
+    if not os.path.exists(path):
+        return out
+    for ln, line in enumerate(open(path), 1):
         m = re.match(r"^(?:template.*\n)?(?:static\s+)?(?:__device__|__global__)[^(]*?\b(\w+)\s*\(", line)
         if m:
             cur = m.group(1)
@@ -22,7 +26,7 @@ def regions():
             if len(out) > 1:
                 out[-2][2] = ln - 1
         m2 = re.match(r"^\s*// ---- (.*)$", line)
-        if m2 and cur == "ssd_step_kernel":
+        if m2 and cur in ("ssd_step_kernel", "ssd_step_fast_kernel"):
             out.append(["kernel: " + m2.group(1)[:40], ln, 10 ** 9])
             out[-2][2] = ln - 1
     return out
@@ -56,13 +60,14 @@ def main(path, n_envs, n_launch=1):
     print("warp instructions per env-step: %.1f   (total %d over %d launch(es) of %d envs)" % (ti / n_launch / n_envs, ti, n_launch, n_envs))
     print("%-44s %7s %7s %12s" % ("region", "inst%", "stall%", "inst/env"))
     acc_i = acc_s = 0
-    for name, a, b in regions():
-        i = sum(v for (f, l), v in inst.items() if f == "ssd_step.cu" and a <= l <= b)
-        s = sum(v for (f, l), v in stall.items() if f == "ssd_step.cu" and a <= l <= b)
-        acc_i += i
-        acc_s += s
-        if i:
-            print("%-44s %6.2f%% %6.2f%% %12.1f" % (name, 100.0 * i / ti, 100.0 * s / max(ts, 1), i / n_launch / n_envs))
+    for fname in FILES:
+        for name, a, b in regions(fname):
+            i = sum(v for (f, l), v in inst.items() if f == fname and a <= l <= b)
+            s = sum(v for (f, l), v in stall.items() if f == fname and a <= l <= b)
+            acc_i += i
+            acc_s += s
+            if i:
+                print("%-44s %6.2f%% %6.2f%% %12.1f" % (name, 100.0 * i / ti, 100.0 * s / max(ts, 1), i / n_launch / n_envs))
     print("%-44s %6.2f%% %6.2f%% %12.1f" % ("other files (philox, intrinsics, atomics)", 100.0 * (ti - acc_i) / ti, 100.0 * (ts - acc_s) / max(ts, 1), (ti - acc_i) / n_launch / n_envs))
     print()
     tot = sum(stalls_by.values())

@@ -171,7 +171,10 @@ struct ResetArgs {
     uint8_t* grid; uint32_t* agents;
 };
 
-// Launchers implemented in ssd_step.cu.
+// Launchers.  launch_step (ssd_step_fast.cu) decides which kernel steps what; launch_general (ssd_step_general.cu) is
+// the kernel with all the runtime flags; the rest live in ssd_aux.cu.
+constexpr int kMaxDevices = 64;
+cudaError_t launch_general(const StepArgs& a, int threads, cudaStream_t stream, bool fast_rows);
 cudaError_t launch_step(const StepArgs& a, int threads, cudaStream_t stream, ChainState* chain = nullptr);
 cudaError_t launch_reset(const ResetArgs& a, cudaStream_t stream);
 cudaError_t launch_pack_state(int kind, int B, int N, int H, int W, int Ws, int env_bytes, const uint8_t* grid_in, const int16_t* pos_in,

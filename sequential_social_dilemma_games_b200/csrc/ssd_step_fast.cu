@@ -1,0 +1,476 @@
+// The specialised full-step kernel for sm_100a and the dispatcher launch_step (which kernel steps what, and when
+// consecutive steps are chained with programmatic dependent launch).
+// Reference citations are relative to the reference root (social_dilemmas/envs/...).
+#include "ssd_phases.cuh"
+
+namespace ssd {
+
+// ====================================================================== the fast path of a full step
+// Same algorithm as ssd_step_kernel, specialised for what a production step is: all phases, every env
+// stepped (no mask), actions in agent order, N <= 8 (8 lanes per env, 4 envs per warp), a packed
+// row renderer for this view size and only whole warps (the launcher sends any tail envs through the
+// general kernel).  What the specialisation buys: no per-env / per-phase flag tests, fire flags from
+// one ballot, view geometry straight from the agent registers, and observation rows that leave
+// shared memory as TMA bulk stores instead of LDS.128 / STG.128 pairs.
+
+// Packed rows with TMA copy-out.  As render_rows, but every chunk of 32 rows (32 * 3V bytes, a multiple
+// of 16) is written by ONE cp.async.bulk from the staging buffer.  The warp's slab starts at `dst`
+// = 16-byte aligned base + mis; the buffer holds the aligned image [base + c*CH, base + (c+1)*CH) of
+// chunk c: the mis/4 words that spill over the end of a chunk are kept in registers by lane 31
+// (they are its last words) and stored at the head of the next chunk's image.  Only the first
+// 16 - mis and the last mis bytes of the slab are written with plain 4-byte stores.
+__host__ __device__ constexpr int row_words(int o, int RB) { return ((o + RB - 1) >> 2) - ((o + 3) >> 2) + 1; }
+__host__ __device__ constexpr int row_words_min(int RB) {
+    int m = row_words(0, RB);
+    for (int r = 1; r < 4; ++r) m = row_words(r, RB) < m ? row_words(r, RB) : m;
+    return m;
+}
+
+template <int VT>
+__device__ __forceinline__ void render_rows_tma(const uint2* s_view, const uint8_t* tiles, const uint32_t* s_color,
+                                                uint32_t* stage, uint8_t* dst, int total_rows, int debug) {
+    constexpr int RB = 3 * VT;            // bytes per view row
+    constexpr int CH = 32 * RB;           // bytes per chunk
+    constexpr int NP = (RB + 3 + 3) / 4;  // words covering the row plus the next row's first pixel
+    constexpr int O31 = 31 * RB, M31 = ((O31 + RB - 1) >> 2) - ((O31 + 3) >> 2) + 1;  // lane 31 owns the chunk's last words
+    constexpr int MMIN = row_words_min(RB);  // every lane owns at least this many words of a chunk
+    static_assert(M31 >= 3 && M31 <= NP, "carry words must all live in lane 31");
+    const int lane = threadIdx.x & 31;
+    const int mis = static_cast<int>(reinterpret_cast<uintptr_t>(dst) & 15);  // multiple of 4
+    const int mis4 = mis >> 2;
+    const uint32_t o = static_cast<uint32_t>(lane) * RB;
+    const uint32_t d8 = 8u * ((4u - (o & 3u)) & 3u);
+    const uint32_t w0 = (o + 3) >> 2, w1 = (o + RB - 1) >> 2;
+    const bool extra = static_cast<int>(w1 - w0) + 1 > MMIN;  // this lane owns MMIN + 1 words of every chunk
+    uint32_t* st = stage + mis4 + w0;
+    const int n_chunks = (total_rows + 31) >> 5;  // >= 2: a warp renders at least 4 * VT rows
+    const int end_last = mis + (total_rows - (n_chunks - 1) * 32) * RB;  // valid image bytes of the last chunk (multiple of 4)
+    const int hi_last = min(CH, end_last & ~15);
+    uint8_t* const img0 = dst - mis;  // 16-byte aligned image of chunk 0
+    const uint32_t stage32 = smem_u32(stage);
+    // where lane 31 parks the words that spill over a chunk: the head of the next image, or a dummy slot
+    uint32_t* const k1 = stage + (mis4 >= 1 ? mis4 - 1 : CH / 4 + 5);
+    uint32_t* const k2 = stage + (mis4 >= 2 ? mis4 - 2 : CH / 4 + 6);
+    uint32_t* const k3 = stage + (mis4 >= 3 ? mis4 - 3 : CH / 4 + 7);
+    const int lo0 = mis != 0 ? 16 : 0;  // the first 16 - mis bytes of the slab leave with plain stores
+    uint8_t* gp = img0 + lo0;           // destination, source and size of the next bulk store
+    uint32_t sp = stage32 + lo0, nb = CH - lo0;
+    uint32_t c0 = 0, c1 = 0, c2 = 0;
+#pragma unroll 1
+    for (int c = 0; c < n_chunks; ++c) {
+        const int R = min(c * 32 + lane, total_rows - 1);  // lanes past the end redo the last row; their words are never copied out
+        const int ga = R / VT, i = R - ga * VT;            // rows are ordered (env, agent, i)
+        uint32_t X[VT + 2];
+        {
+            const uint2 vp = s_view[ga];
+            const int si = static_cast<int16_t>(vp.y & 0xffffu), sj = static_cast<int32_t>(vp.y) >> 16;
+            const uint8_t* g = tiles + static_cast<int32_t>(vp.x) + i * si;
+#pragma unroll
+            for (int j = 0; j < VT; ++j) X[j] = cell_color(s_color, g[j * sj]);
+        }
+        X[VT] = __shfl_down_sync(0xffffffffu, X[0], 1);
+        X[VT + 1] = 0;
+        uint32_t P[NP + 1];
+#pragma unroll
+        for (int w = 0; w < NP; ++w) {
+            const int p = (4 * w) / 3, ph = (4 * w) % 3;
+            P[w] = __byte_perm(X[p], X[p + 1], ph == 0 ? 0x4210u : (ph == 1 ? 0x5421u : 0x6542u));
+        }
+        P[NP] = 0;
+        uint32_t Q[MMIN + 1];
+#pragma unroll
+        for (int m = 0; m <= MMIN; ++m) Q[m] = __funnelshift_r(P[m], P[m + 1], d8);
+        bulk_wait_read();  // the previous chunk's bulk store (issued by lane 0) must have finished READING the buffer
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < MMIN; ++m) st[m] = Q[m];
+        if (extra) st[MMIN] = Q[MMIN];
+        if (lane == 31) { *k1 = c2; *k2 = c1; *k3 = c0; }  // head of this image = spill of the previous chunk (unused for c == 0)
+        c0 = Q[M31 - 3]; c1 = Q[M31 - 2]; c2 = Q[M31 - 1];
+        fence_async_smem();
+        __syncwarp();
+        if (c == n_chunks - 1) nb = hi_last;  // n_chunks >= 2: the last chunk starts at the head of the buffer
+        if (lane == 0 && !SSD_SKIP(debug, 1)) {
+            bulk_s2g_u32(gp, sp, nb);
+            bulk_commit();
+        }
+        if (c == 0 && lane >= mis4 && lane < 4 && mis != 0)  // first bytes of the slab
+            *reinterpret_cast<uint32_t*>(img0 + 4 * lane) = stage[lane];
+        gp += nb; sp = stage32; nb = CH;
+    }
+    {   // last bytes of the slab
+        const int off = hi_last + 4 * lane;
+        if (off < end_last) *reinterpret_cast<uint32_t*>(img0 + static_cast<size_t>(n_chunks - 1) * CH + off) = stage[off >> 2];
+    }
+    bulk_wait_read();  // shared memory must outlive the last bulk read
+}
+
+template <int KIND, bool TAPE, int VT, int G>
+__global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid_constant__ StepArgs a) {
+    constexpr int EPW = 32 / G;                                       // envs per warp: 4 (N <= 8) or 2 (N <= 16)
+    constexpr uint32_t kSlotLsb = G == 8 ? 0x01010101u : 0x00010001u;  // bit 0 of every env's lane group
+    using FastScratch = FastScratchT<G>;
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint32_t s_color[kLutEntries];
+    __shared__ int s_cta_stats[SSD_NUM_STATS];
+    __shared__ int s_done;
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
+    const int N = a.N;
+    uint16_t* s_apple = reinterpret_cast<uint16_t*>(smem + a.Lf.apple);
+    pdl_launch_dependents();  // a chained next step may start launching (it waits per task, see below)
+
+    for (int i = tid; i < kLutEntries; i += nthr) s_color[i] = a.color[i];
+    if (tid < SSD_NUM_STATS) s_cta_stats[tid] = 0;
+    if (tid == 0) s_done = 0;
+    if (KIND != SSD_KIND_PLAIN)
+#pragma unroll 1
+        for (int i = tid; i < ((a.n_apple + 63) & ~63); i += nthr) s_apple[i] = i < a.n_apple ? a.apple_cell[i] : static_cast<uint16_t>(a.Ws + 1);
+    __syncthreads();
+
+    uint8_t* wbase = smem + a.Lf.warp0 + warp * a.Lf.warp_stride;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(wbase + a.Lf.w_mbar);
+    uint8_t* tiles = wbase + a.Lf.w_tiles;
+    FastScratch* envs = reinterpret_cast<FastScratch*>(wbase + a.Lf.w_env);
+    const int tile_pitch = a.env_bytes + a.pad_bytes;
+    const int we = a.env_begin + (blockIdx.x * nwarps + warp) * EPW;  // the launcher only sends whole warps
+    Counters cnt = {0, 0, 0, 0, 0, 0, 0};
+
+    if (we < a.env_end) {
+        // ---- load: one TMA bulk copy per env tile; zero the frames while they are in flight
+        if (lane == 0) {
+            mbar_init(mbar, 1);
+            mbar_expect_tx(mbar, static_cast<uint32_t>(EPW) * a.env_bytes);
+            if (a.dep_wait) {  // chained step: the previous step's kernel may still be running; wait for OUR four envs only
+                while (ld_acquire_u32(a.done + we / EPW) != a.epoch - 1) __nanosleep(64);
+                fence_async_all();  // its ordinary stores -> our TMA loads
+            }
+        }
+        __syncwarp();
+        if (lane < EPW)
+            bulk_g2s(tiles + a.pad_bytes + lane * tile_pitch, a.grid + static_cast<size_t>(we + lane) * a.env_bytes, a.env_bytes, mbar);
+        {
+            const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int q = 0; q <= EPW; ++q)
+#pragma unroll 1
+                for (int i = lane * 16; i < a.pad_bytes; i += 512) *reinterpret_cast<uint4*>(tiles + q * tile_pitch + i) = z;
+        }
+        // agent words and actions travel while the tiles do
+        const int al = lane & (G - 1), gbase = lane & ~(G - 1), j = lane / G;
+        FastScratch& S = envs[j];
+        uint8_t* g = tiles + a.pad_bytes + j * tile_pitch;
+        const int e = we + j;
+        const bool valid = al < N;
+        const size_t gi = static_cast<size_t>(e) * N + (valid ? al : 0);
+        PhiloxKey pk;
+        pk.k0 = a.key0; pk.k1 = a.key1; pk.t = a.t;
+        pk.env = static_cast<uint32_t>(a.env_id0 + static_cast<uint64_t>(e));
+        AgentLane me;
+        me.key = 0x0101; me.ori = 0; me.act = -1; me.rew = 0;
+        if (valid) {
+            const uint32_t w = __ldcg(a.agents + gi);  // L2: a chained predecessor may just have written it
+            me.act = a.actions[gi];
+            me.key = (w & 255) << 8 | ((w >> 8) & 255);
+            me.ori = (w >> 16) & 3;
+            S.order[al] = static_cast<uint8_t>(al);
+            S.rew[al] = 0;
+        }
+        mbar_wait(mbar, 0);  // tiles landed
+        __syncwarp();
+
+        // ---- phase A: one lane per agent
+        moves_group<TAPE>(a, S, reinterpret_cast<MoveScratch*>(wbase + a.Lf.w_union)[j], g, me, valid, al, G, e, pk);
+        cnt.steps += (al == 0);
+        if (valid) S.pos[al] = static_cast<uint16_t>(me.key);
+        const int my_idx = tile_idx(a, me.key);
+        {   // consume, map_env.py:178-181: of agents sharing a cell (appendix A.2 quirk) the first in agent order eats
+            const uint8_t under = g[my_idx];
+            const bool on_apple = valid && is_apple(under);
+            const uint32_t same = __match_any_sync(0xffffffffu, on_apple ? (me.key | static_cast<uint32_t>(gbase) << 16) : (0x80000000u | lane));
+            const bool ate = on_apple && (__ffs(same) - 1) == lane;
+            if (ate) { g[my_idx] = CB(C_EMPTY) | (under & 3); me.rew += 1; ++cnt.eaten; }
+            __syncwarp();
+            if (KIND == SSD_KIND_HARVEST) recount_events(__ballot_sync(0xffffffffu, ate), static_cast<int>(g - tiles) + my_idx, tiles, a.Ws);
+        }
+        __syncwarp();
+        if (KIND != SSD_KIND_PLAIN && valid) g[my_idx] |= kFlag;  // "an agent stands here"
+        __syncwarp();
+        uint32_t fmask = 0;  // bit (8 * env slot + agent): that agent fires
+        uint32_t* const fire_list = reinterpret_cast<uint32_t*>(wbase + a.Lf.w_union);
+        const int ray_f = lane / 3, ray_s = lane - 3 * ray_f;  // Harvest: ray lane -> (firing agent of the round, ray)
+        uint32_t fire_ent = 0;
+        if (KIND == SSD_KIND_HARVEST && !SSD_SKIP(a.debug, 8)) {
+            // update_custom_moves map_env.py:545-552.  Harvest has only 'F' beams: they change no cell, so the
+            // firing order is irrelevant and the rays of ALL firing agents of the warp walk at once, 3 lanes each.
+            const bool fire_me = me.act == 7;
+            fmask = __ballot_sync(0xffffffffu, fire_me);
+            if (fmask) {
+                fire_ent = me.key | static_cast<uint32_t>(me.ori) << 16 | static_cast<uint32_t>(j) << 18 | static_cast<uint32_t>(al) << 21;
+                if (fire_me) { fire_list[__popc(fmask & lanemask_lt())] = fire_ent; me.rew -= 1; ++cnt.fires; }  // fire_beam agent.py:170-172
+                __syncwarp();
+                const int nf = __popc(fmask);
+#pragma unroll 1
+                for (int f0 = 0; f0 < nf; f0 += 10) {
+                    if (lane < 30 && f0 + ray_f < nf) {
+                        const uint32_t en = fire_list[f0 + ray_f];
+                        const int slot = (en >> 18) & 3, ag = en >> 21;
+                        int upd = -1, hits = 0;
+                        const int n = ray_walk<FastScratch, true>(a, envs[slot], tiles + a.pad_bytes + slot * tile_pitch, en & 0xffffu,
+                                                                  (en >> 16) & 3, ray_s, false, upd, hits);
+                        envs[slot].raylen[ag * 3 + ray_s] = static_cast<uint8_t>(n);
+                        cnt.hits += hits;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        if (KIND == SSD_KIND_CLEANUP && !SSD_SKIP(a.debug, 8)) {  // firing order matters: a CLEAN beam turns 'H' into 'R' for the next one
+            fmask = __ballot_sync(0xffffffffu, me.act == 7 || me.act == 8);
+            for (int k = 0; k < N; ++k) {
+                if (!((fmask >> k) & kSlotLsb)) continue;  // nobody in this warp fires in slot k
+                const bool fire = (fmask >> (gbase + k)) & 1u;
+                const int act_k = __shfl_sync(0xffffffffu, me.act, k, G);
+                const uint32_t key_k = __shfl_sync(0xffffffffu, me.key, k, G);
+                const int ori_k = __shfl_sync(0xffffffffu, me.ori, k, G);
+                const bool clean = act_k == 8;
+                int upd = -1, hits = 0, n = 0;
+                if (fire && al < 3) n = ray_walk(a, S, g, key_k, ori_k, al, clean, upd, hits);
+                if (fire && al == k && !clean) { me.rew -= 1; ++cnt.fires; }  // fire_beam agent.py:170-172
+                __syncwarp();
+                if (fire && al < 3) {
+                    S.raylen[k * 3 + al] = static_cast<uint8_t>(n);
+                    if (upd >= 0) { g[upd] = CB(C_RIVER) | (g[upd] & kFlag); ++cnt.cleaned; }  // update_map :551-558, before the next agent fires
+                    cnt.hits += hits;
+                }
+                __syncwarp();
+            }
+        }
+        if (valid) {
+            me.rew += S.rew[al];  // -50 per hit taken
+            a.agents[gi] = (me.key >> 8) | (me.key & 255) << 8 | static_cast<uint32_t>(me.ori) << 16;
+            a.rew[gi] = me.rew;
+        }
+
+        // ---- phase B: the whole warp per env
+        if (KIND != SSD_KIND_PLAIN && !SSD_SKIP(a.debug, 4)) {
+            void* scratch = wbase + a.Lf.w_union;
+            if (KIND == SSD_KIND_HARVEST) {
+                harvest_spawn_warp<TAPE, EPW>(a, tiles, tile_pitch, s_apple, static_cast<uint32_t*>(scratch), a.Lf.u_words, we, pk, lane, cnt);
+            } else {
+#pragma unroll 1
+                for (int q = 0; q < EPW; ++q) {
+                    pk.env = static_cast<uint32_t>(a.env_id0 + static_cast<uint64_t>(we + q));
+                    cleanup_spawn<TAPE>(a, tiles + a.pad_bytes + q * tile_pitch, s_apple, static_cast<uint32_t*>(scratch), we + q, pk, lane, cnt);
+                    __syncwarp();
+                }
+            }
+            if (valid) g[my_idx] &= 0x7F;  // agents sharing a cell all write the same byte
+            __syncwarp();
+        }
+
+        // ---- store: grid tiles back to HBM
+        if (!SSD_SKIP(a.debug, 64)) {
+            const int n16 = a.env_bytes >> 4;
+#pragma unroll
+            for (int q = 0; q < EPW; ++q) {
+                uint4* gdst = reinterpret_cast<uint4*>(a.grid + static_cast<size_t>(we + q) * a.env_bytes);
+                const uint4* gsrc = reinterpret_cast<const uint4*>(tiles + a.pad_bytes + q * tile_pitch);
+#pragma unroll 1
+                for (int i = lane; i < n16; i += 32) gdst[i] = gsrc[i];
+            }
+        }
+        __syncwarp();  // the write-back above has read the tiles
+
+        // ---- phase C: overlay (get_map_with_agents map_env.py:280-302), view geometry, packed rows
+        {
+            const uint32_t same = __match_any_sync(0xffffffffu, valid ? (me.key | static_cast<uint32_t>(gbase) << 16) : (0x80000000u | lane));
+            if (valid && (31 - __clz(same)) == lane) g[my_idx] = agent_cell(al);  // the last agent on a cell wins
+            __syncwarp();
+            if (KIND == SSD_KIND_HARVEST && fmask) {  // all beams are 'F': the painting order is irrelevant
+                if ((fmask >> lane) & 1u) fire_list[__popc(fmask & lanemask_lt())] = fire_ent;  // the union was reused by the spawn pass
+                __syncwarp();
+                const int nf = __popc(fmask);
+#pragma unroll 1
+                for (int f0 = 0; f0 < nf; f0 += 10) {
+                    if (lane < 30 && f0 + ray_f < nf) {
+                        const uint32_t en = fire_list[f0 + ray_f];
+                        const int slot = (en >> 18) & 3, ag = en >> 21, ori = (en >> 16) & 3;
+                        const int d0 = (ori == 1) - (ori == 3), d1 = (ori == 2) - (ori == 0);
+                        int r = static_cast<int>((en >> 8) & 255) + d0, c = static_cast<int>(en & 255) + d1;
+                        if (ray_s == 1) { r += -d1 - d0; c += d0 - d1; }
+                        if (ray_s == 2) { r -= -d1 + d0; c -= d0 + d1; }
+                        const int n = envs[slot].raylen[ag * 3 + ray_s], dp = d0 * a.Ws + d1;
+                        uint8_t* p = tiles + a.pad_bytes + slot * tile_pitch + r * a.Ws + c;
+#pragma unroll 1
+                        for (int i = 0; i < n; ++i) { *p = CB(C_FIRE); p += dp; }
+                    }
+                }
+                __syncwarp();
+            }
+            if (KIND == SSD_KIND_CLEANUP) {  // beams in firing order: a later beam overwrites an earlier one
+                for (int k = 0; k < N; ++k) {
+                    if (!((fmask >> k) & kSlotLsb)) continue;
+                    const uint32_t key_k = __shfl_sync(0xffffffffu, me.key, k, G);
+                    const int ori_k = __shfl_sync(0xffffffffu, me.ori, k, G);
+                    const int act_k = __shfl_sync(0xffffffffu, me.act, k, G);
+                    if (((fmask >> (gbase + k)) & 1u) && al < 3) {
+                        const int d0 = (ori_k == 1) - (ori_k == 3), d1 = (ori_k == 2) - (ori_k == 0);
+                        int r = static_cast<int>(key_k >> 8) + d0, c = static_cast<int>(key_k & 255) + d1;
+                        if (al == 1) { r += -d1 - d0; c += d0 - d1; }
+                        if (al == 2) { r -= -d1 + d0; c -= d0 + d1; }
+                        const int n = S.raylen[k * 3 + al], dp = d0 * a.Ws + d1;
+                        const uint8_t ch = act_k == 8 ? CB(C_CLEAN) : CB(C_FIRE);
+                        int p = r * a.Ws + c;
+#pragma unroll 1
+                        for (int i = 0; i < n; ++i) { g[p] = ch; p += dp; }
+                    }
+                    __syncwarp();
+                }
+            }
+            uint2* s_view = reinterpret_cast<uint2*>(wbase + a.Lf.w_union);
+            if (valid) {  // rot90 folded into strides, see view_param
+                const int pr = me.key >> 8, pc = me.key & 255, r = a.r, Ws = a.Ws;
+                const int k = (4 - me.ori) & 3;
+                int a0, si, sj;
+                if (k == 0)      { a0 = (pr - r) * Ws + pc - r; si = Ws;  sj = 1; }
+                else if (k == 2) { a0 = (pr + r) * Ws + pc + r; si = -Ws; sj = -1; }
+                else if (k == 1) { a0 = (pr - r) * Ws + pc + r; si = -1;  sj = Ws; }
+                else             { a0 = (pr + r) * Ws + pc - r; si = 1;   sj = -Ws; }
+                s_view[j * N + al] = make_uint2(static_cast<uint32_t>(a0 + a.pad_bytes + j * tile_pitch),
+                                                (static_cast<uint32_t>(si) & 0xffffu) | static_cast<uint32_t>(sj) << 16);
+            }
+            __syncwarp();
+            if (!SSD_SKIP(a.debug, 2))
+            render_rows_tma<VT>(s_view, tiles, s_color, reinterpret_cast<uint32_t*>(wbase + a.Lf.w_union + a.Lf.u_stage),
+                                a.obs + static_cast<size_t>(we) * a.obs_env, EPW * N * VT, a.debug);
+        }
+        if (a.publish) {  // everything this task wrote (grid, agent words, rewards, observation rows) is visible before the word is
+            __syncwarp();
+            if (lane == 0) {
+                bulk_wait_all();
+                __threadfence();
+                st_release_u32(a.done + we / EPW, a.epoch);
+            }
+        }
+    }
+
+    // ---- stats: warp -> CTA -> one set of global atomics per CTA (issued by the last warp to finish)
+    if (a.stats != nullptr && !SSD_SKIP(a.debug, 32)) {
+        // per-warp totals are small (<= 32 agents): two packed reductions carry all seven counters
+        //   r0: steps | eaten << 8 | fires << 16 | hits << 24 (hits <= 3 per shooter)     r1: cleaned | waste << 8 | apples << 12
+        const uint32_t r0 = __reduce_add_sync(0xffffffffu, static_cast<uint32_t>(cnt.steps | cnt.eaten << 8 | cnt.fires << 16 | cnt.hits << 24));
+        const uint32_t r1 = __reduce_add_sync(0xffffffffu, static_cast<uint32_t>(cnt.cleaned | cnt.waste << 8 | cnt.apples << 12));
+        if (lane < 7) {
+            const uint32_t v = lane < 4 ? (r0 >> (8 * lane)) & 255u : (lane == 4 ? r1 & 255u : (lane == 5 ? r1 >> 12 : (r1 >> 8) & 15u));
+            if (v) atomicAdd(&s_cta_stats[lane == 0 ? 0 : lane + 1], static_cast<int>(v));
+        }
+        __syncwarp();
+        int last = 0;
+        if (lane == 0) { __threadfence_block(); last = (atomicAdd(&s_done, 1) == nwarps - 1); }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last && lane < SSD_NUM_STATS) {
+            const int tot = *reinterpret_cast<volatile int*>(&s_cta_stats[lane]);
+            if (tot) atomicAdd(&a.stats[lane], static_cast<unsigned long long>(tot));
+        }
+    }
+}
+
+// ====================================================================== launchers
+template <int KIND, bool TAPE, int G>
+static cudaError_t launch_fast(const StepArgs& a, int threads, cudaStream_t stream) {
+    const int envs_per_cta = (threads / 32) * (32 / G);
+    const int ctas = (a.env_end - a.env_begin + envs_per_cta - 1) / envs_per_cta;
+    if (ctas <= 0) return cudaSuccess;
+#define SSD_LAUNCH_FAST(VT_)                                                                                    \
+    do {                                                                                                        \
+        auto kern = ssd_step_fast_kernel<KIND, TAPE, VT_, G>;                                                      \
+        static uint32_t smem_set[kMaxDevices] = {};  /* the attribute is per device */                          \
+        int dev_ = 0;                                                                                           \
+        cudaGetDevice(&dev_);                                                                                   \
+        dev_ = dev_ < kMaxDevices ? dev_ : kMaxDevices - 1;                                                     \
+        if (a.Lf.total > smem_set[dev_] || dev_ == kMaxDevices - 1) {                                           \
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, a.Lf.total); \
+            if (e != cudaSuccess) return e;                                                                     \
+            smem_set[dev_] = a.Lf.total;                                                                        \
+        }                                                                                                       \
+        cudaLaunchConfig_t lc = {};                                                                             \
+        lc.gridDim = dim3(ctas); lc.blockDim = dim3(threads); lc.dynamicSmemBytes = a.Lf.total; lc.stream = stream; \
+        cudaLaunchAttribute at[1];                                                                              \
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                          \
+        at[0].val.programmaticStreamSerializationAllowed = 1;                                                   \
+        lc.attrs = at; lc.numAttrs = a.dep_wait ? 1 : 0;                                                        \
+        return cudaLaunchKernelEx(&lc, kern, a);                                                                \
+    } while (0)
+    switch (a.V) {
+        case 11: SSD_LAUNCH_FAST(11);
+        case 15: SSD_LAUNCH_FAST(15);
+        default: SSD_LAUNCH_FAST(21);
+    }
+#undef SSD_LAUNCH_FAST
+}
+
+
+cudaError_t launch_step(const StepArgs& a, int threads, cudaStream_t stream, ChainState* chain) {
+    // the packed row renderers need every warp's slab of 32/G envs to start 4-byte aligned
+    const bool fast_rows = (((32 / a.G) * a.obs_env) % 4 == 0) && (reinterpret_cast<uintptr_t>(a.obs) % 4 == 0);
+    const bool tape = a.tape_u != nullptr || a.tape_move != nullptr;
+    // a production step: everything the specialised kernel assumes (see ssd_step_fast_kernel)
+    static const bool no_fast = getenv("SSD_NO_FAST") != nullptr;
+    const bool full = !no_fast && a.phases == SSD_PHASE_ALL && a.mask == nullptr && a.order == nullptr && !a.use_beam_buf &&
+                      !a.rew_accumulate && a.obs != nullptr && a.rew != nullptr && a.actions != nullptr && fast_rows &&
+                      (a.V == 11 || a.V == 15 || a.V == 21) && a.env_begin % (32 / a.G) == 0;
+    if (!full) {
+        if (chain) chain->valid = false;
+        return launch_general(a, threads, stream, fast_rows);
+    }
+    StepArgs f = a;
+    const int epw = 32 / a.G;
+    f.env_end = a.env_begin + (a.env_end - a.env_begin) / epw * epw;  // whole warps
+    const bool has_tail = f.env_end != a.env_end;
+    // Chaining pays when a step is a few waves of CTAs (it hides launch, ramp and the half-empty last wave); a single
+    // wave has no tail to hide and very long grids amortise it anyway, while the completion words cost a little
+    // (profiles/r01h_sweep.md): chain between 1.5 and 12 waves.
+    bool chain_here = false;
+    if (chain && chain->enabled && chain->done != nullptr) {
+        static int slots = 0;  // resident CTAs of the whole GPU at this CTA shape (8 per SM on B200)
+        if (slots == 0) {
+            int dev = 0, sms = 148;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            slots = sms * 8;
+        }
+        const int ctas = (f.env_end - f.env_begin + (threads / 32) * epw - 1) / ((threads / 32) * epw);
+        chain_here = 2 * ctas >= 3 * slots && ctas <= 12 * slots;
+        static const bool chain_always = getenv("SSD_CHAIN_ALWAYS") != nullptr;  // experiments
+        if (chain_always) chain_here = true;
+    }
+    if (chain_here) {
+        // Chained steps (SSD_OPT_CHAIN_STEPS): this launch may overlap the previous step's kernel when that was the
+        // same kind of launch on the same stream; either way it publishes per-task completion words for the next one.
+        f.done = chain->done;
+        f.epoch = ++chain->epoch;
+        f.publish = 1;
+        f.dep_wait = chain->valid && chain->stream == stream && chain->env_begin == f.env_begin && chain->env_end == f.env_end;
+        chain->valid = !has_tail;
+        chain->stream = stream; chain->env_begin = f.env_begin; chain->env_end = f.env_end;
+    } else if (chain) {
+        chain->valid = false;
+    }
+    cudaError_t e = cudaSuccess;
+#define SSD_FAST(KIND_)                                                                                                     \
+    e = a.G == 8 ? (tape ? launch_fast<KIND_, true, 8>(f, threads, stream) : launch_fast<KIND_, false, 8>(f, threads, stream)) \
+                 : (tape ? launch_fast<KIND_, true, 16>(f, threads, stream) : launch_fast<KIND_, false, 16>(f, threads, stream))
+    switch (a.kind) {
+        case SSD_KIND_HARVEST: SSD_FAST(SSD_KIND_HARVEST); break;
+        case SSD_KIND_CLEANUP: SSD_FAST(SSD_KIND_CLEANUP); break;
+        default: SSD_FAST(SSD_KIND_PLAIN); break;
+    }
+#undef SSD_FAST
+    if (e != cudaSuccess || !has_tail) return e;
+    StepArgs tail = a;  // the envs that do not fill a warp
+    tail.env_begin = f.env_end;
+    return launch_general(tail, threads, stream, fast_rows);
+}
+
+
+}  // namespace ssd
