@@ -98,6 +98,20 @@ __device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// One leader lane per (converged) warp.  ptxas knows that code guarded by an elect.sync predicate runs on a single
+// lane, so bulk-copy operands reach the uniform registers with plain R2URs instead of a waterfall loop.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t is_leader;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(is_leader));
+    return is_leader != 0;
+}
+
 __device__ __forceinline__ uint32_t lanemask_lt() {
     uint32_t m;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));

@@ -90,7 +90,7 @@ __device__ __forceinline__ void render_rows_tma(const uint2* s_view, const uint8
         fence_async_smem();
         __syncwarp();
         if (c == n_chunks - 1) nb = hi_last;  // n_chunks >= 2: the last chunk starts at the head of the buffer
-        if (lane == 0 && !SSD_SKIP(debug, 1)) {
+        if (elect_one() && !SSD_SKIP(debug, 1)) {  // the elected lane is lane 0 of the converged warp: it owns all bulk groups
             bulk_s2g_u32(gp, sp, nb);
             bulk_commit();
         }
@@ -142,12 +142,15 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
             mbar_expect_tx(mbar, static_cast<uint32_t>(EPW) * a.env_bytes);
             if (a.dep_wait) {  // chained step: the previous step's kernel may still be running; wait for OUR four envs only
                 while (ld_acquire_u32(a.done + we / EPW) != a.epoch - 1) __nanosleep(64);
-                fence_async_all();  // its ordinary stores -> our TMA loads
             }
         }
         __syncwarp();
-        if (lane < EPW)
-            bulk_g2s(tiles + a.pad_bytes + lane * tile_pitch, a.grid + static_cast<size_t>(we + lane) * a.env_bytes, a.env_bytes, mbar);
+        if (elect_one()) {  // one lane issues all tile loads: uniform operands, no per-lane replay
+            if (a.dep_wait) fence_async_all();  // the predecessor's ordinary stores (acquired above) -> our TMA loads
+#pragma unroll
+            for (int q = 0; q < EPW; ++q)
+                bulk_g2s(tiles + a.pad_bytes + q * tile_pitch, a.grid + static_cast<size_t>(we + q) * a.env_bytes, a.env_bytes, mbar);
+        }
         {
             const uint4 z = make_uint4(0, 0, 0, 0);
 #pragma unroll
@@ -345,9 +348,9 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
                                 a.obs + static_cast<size_t>(we) * a.obs_env, EPW * N * VT, a.debug);
         }
         if (a.publish) {  // everything this task wrote (grid, agent words, rewards, observation rows) is visible before the word is
+            bulk_wait_all();  // all lanes: only the lane that committed the bulk stores actually waits
             __syncwarp();
             if (lane == 0) {
-                bulk_wait_all();
                 __threadfence();
                 st_release_u32(a.done + we / EPW, a.epoch);
             }
