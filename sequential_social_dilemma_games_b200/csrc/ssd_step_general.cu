@@ -42,8 +42,9 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_kernel(const __grid_cons
         // ---- load: one TMA bulk copy per env tile; zero frames while they are in flight
         if (lane == 0) { mbar_init(mbar, 1); mbar_expect_tx(mbar, static_cast<uint32_t>(EPW) * a.env_bytes); }
         __syncwarp();
-        if (lane < EPW)
-            bulk_g2s(tiles + a.pad_bytes + lane * tile_pitch, a.grid + static_cast<size_t>(we + lane) * a.env_bytes, a.env_bytes, mbar);
+        if (elect_one())  // one lane issues all tile loads: uniform operands, no per-lane replay
+            for (int q = 0; q < EPW; ++q)
+                bulk_g2s(tiles + a.pad_bytes + q * tile_pitch, a.grid + static_cast<size_t>(we + q) * a.env_bytes, a.env_bytes, mbar);
         {
             const uint4 z = make_uint4(0, 0, 0, 0);
             for (int q = 0; q <= EPW; ++q)
