@@ -11,7 +11,7 @@ if len(sys.argv) > 1:
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     from tune_step import time_cfg
     for B in [int(x) for x in os.environ.get('BS', '65536,262144').split(',')]:
-        ms = time_cfg("harvest", B, steps=200, warm=100)
+        ms = time_cfg(os.environ.get("GAME", "harvest"), B, steps=200, warm=100)
         print("skip=%2s B=%6d %.4f ms/step" % (os.environ.get("SSD_DEBUG_SKIP", "0"), B, ms), flush=True)
 else:
     for skip in [int(x) for x in os.environ.get('SKIPS', '0,1,2,4,8,6,14').split(',')]:

@@ -102,7 +102,7 @@ ssd::SmemLayout make_layout(const SsdEnv& h, int threads, bool fast = false) {
     L.w_union = w;
     L.u_stage = up16(epw * h.cfg.num_agents * 8);                          // view params first
     const uint32_t u_render = L.u_stage + up16(32u * 3u * h.V) + 32;       // + staging of 32 view rows, spill and dummy words
-    const uint32_t u_spawn = up16(std::max(h.n_apple * 4, h.n_waste * 4)); // need-list / waste keys
+    const uint32_t u_spawn = up16(std::max(std::max(h.n_apple * 4, h.n_waste * 4), h.cfg.kind == SSD_KIND_CLEANUP ? 512 : 0)); // need-list / waste keys / 32 Philox blocks
     const uint32_t u_moves = epw * sizeof(ssd::MoveScratch);
     L.u_words = std::max(u_render, std::max(u_spawn, u_moves)) / 4;
     w += 4 * L.u_words;

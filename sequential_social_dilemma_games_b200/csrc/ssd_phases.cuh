@@ -403,21 +403,57 @@ __device__ __forceinline__ void cleanup_spawn(const StepArgs& a, uint8_t* g, con
     const double apple_p = a.apple_p[h], waste_p = a.waste_p[h];
     const uint64_t apple_thr = a.apple_thr[h], waste_thr = a.waste_thr[h];
 
+    // Nothing can spawn above the depletion threshold (both probabilities are 0, cleanup.py:160-162): without a tape
+    // to account draws for, the scans below have no effect.  Under random play this is the common case.
+    if (!TAPE && apple_thr == 0 && (waste_thr == 0 || n_waste == 0)) return;
+
     int base = 0;
-    for (int i0 = 0; i0 < n_apple; i0 += 32) {  // apple pass, cleanup.py:135-141 (a draw per eligible point)
-        const int i = i0 + lane;
-        bool el = false;
-        int idx = 0;
-        if (i < n_apple) { idx = s_apple[i]; const uint8_t c = g[idx]; el = (c != CB(C_APPLE)) && !(c & kFlag); }
-        const uint32_t m = __ballot_sync(0xffffffffu, el);
-        if (el) {
-            const int rank = base + __popc(m & lanemask_lt());
-            bool spawn;
-            if (TAPE) spawn = a.tape_u[static_cast<size_t>(local_env) * a.u_stride + rank] < apple_p;
-            else spawn = apple_thr != 0 && philox_u53(pk, a.spawn_stream, rank) < apple_thr;
-            if (spawn) { g[idx] = CB(C_APPLE); ++cnt.apples; }  // apple cells are never read again in this pass
+    if (TAPE) {
+        for (int i0 = 0; i0 < n_apple; i0 += 32) {  // apple pass, cleanup.py:135-141 (a draw per eligible point)
+            const int i = i0 + lane;
+            bool el = false;
+            int idx = 0;
+            if (i < n_apple) { idx = s_apple[i]; const uint8_t c = g[idx]; el = (c != CB(C_APPLE)) && !(c & kFlag); }
+            const uint32_t m = __ballot_sync(0xffffffffu, el);
+            if (el) {
+                const int rank = base + __popc(m & lanemask_lt());
+                if (a.tape_u[static_cast<size_t>(local_env) * a.u_stride + rank] < apple_p) { g[idx] = CB(C_APPLE); ++cnt.apples; }
+            }
+            base += __popc(m);
         }
-        base += __popc(m);
+    } else {
+        // Two groups of 32 points per trip (the table is padded to 64).  Their <= 64 draws are the words of <= 33 Philox
+        // blocks: lane L evaluates block (base >> 1) + L ONCE and parks it in `keys` (free until the waste pass), every
+        // eligible lane picks its half -- half the Philox evaluations of one per group.
+        uint4* const blocks = reinterpret_cast<uint4*>(keys);
+        const uint32_t lt = lanemask_lt();
+#pragma unroll 1
+        for (int i0 = 0; i0 < n_apple; i0 += 64) {
+            const int i = i0 + lane;
+            const int idx0 = s_apple[i], idx1 = s_apple[i + 32];
+            const uint8_t c0 = g[idx0], c1 = g[idx1];
+            const bool el0 = (i < n_apple) & (c0 != CB(C_APPLE)) & (c0 < kFlag);  // no apple, no agent (cleanup.py:138)
+            const bool el1 = (i + 32 < n_apple) & (c1 != CB(C_APPLE)) & (c1 < kFlag);
+            const uint32_t m0 = __ballot_sync(0xffffffffu, el0), m1 = __ballot_sync(0xffffffffu, el1);
+            const int cnt0 = __popc(m0), total = cnt0 + __popc(m1);
+            if (apple_thr != 0 && total != 0) {
+                const uint32_t first = static_cast<uint32_t>(base) >> 1;
+                blocks[lane] = philox4x32_10(pk.env, pk.t, a.spawn_stream, first + lane, pk.k0, pk.k1);
+                __syncwarp();
+                const uint32_t r0 = base + __popc(m0 & lt), r1 = base + cnt0 + __popc(m1 & lt);
+                auto draw = [&](uint32_t r) -> uint64_t {  // k-th 53-bit uniform = words (2k, 2k+1) of the stream
+                    if ((r >> 1) - first < 32u) {
+                        const uint2 w = reinterpret_cast<const uint2*>(blocks)[r - 2 * first];
+                        return (static_cast<uint64_t>(w.x >> 5) << 26) | (w.y >> 6);
+                    }
+                    return philox_u53(pk, a.spawn_stream, r);  // draw 64 of a trip that started on an odd index
+                };
+                if (el0 && draw(r0) < apple_thr) { g[idx0] = CB(C_APPLE); ++cnt.apples; }  // apple cells are never read again
+                if (el1 && draw(r1) < apple_thr) { g[idx1] = CB(C_APPLE); ++cnt.apples; }
+                __syncwarp();
+            }
+            base += total;
+        }
     }
 
     if (TAPE && a.n_draws_out != nullptr && lane == 0) a.n_draws_out[local_env] = base;  // apple pass; the waste pass adds its own
@@ -447,7 +483,7 @@ __device__ __forceinline__ void cleanup_spawn(const StepArgs& a, uint8_t* g, con
             if (a.n_draws_out != nullptr && lane == 0) a.n_draws_out[local_env] = base;
         } else {
             // random.shuffle replacement: canonical waste points ordered by (32-bit key, index).
-            int n_el = 0;
+            __syncwarp();
             for (int i0 = 0; i0 < n_waste; i0 += 128) {  // one Philox block = keys of 4 consecutive points
                 const int i = i0 + lane * 4;
                 if (i < n_waste) {
@@ -458,21 +494,40 @@ __device__ __forceinline__ void cleanup_spawn(const StepArgs& a, uint8_t* g, con
                     if (i + 3 < n_waste) keys[i + 3] = k4.w;
                 }
             }
-            for (int i = lane; i < n_waste; i += 32) n_el += (g[a.waste_cell[i]] & 0x7F) != CB(C_WASTE);
-            n_el = __reduce_add_sync(0xffffffffu, n_el);
+            // eligibility (not 'H', cleanup.py:149) of the points lane, lane + 32, ... as a bit mask per lane
+            uint32_t el_bits = 0;
+            int el_cnt = 0;
+            for (int i = lane, k = 0; i < n_waste; i += 32, ++k) {
+                const bool el = (g[a.waste_cell[i]] & 0x7F) != CB(C_WASTE);
+                el_bits |= static_cast<uint32_t>(el) << (k & 31);
+                el_cnt += el;
+            }
+            const int n_el = __reduce_add_sync(0xffffffffu, el_cnt);
             __syncwarp();
-            // the k-th scanned non-'H' cell draws uniform #(base + k); the first success wins
-            int kstar = 0;
-            while (kstar < n_el && !(philox_u53(pk, a.spawn_stream, base + kstar) < waste_thr)) ++kstar;
+            // the k-th scanned non-'H' cell draws uniform #(base + k); the first success wins.  32 candidates k at a time.
+            int kstar = n_el;
+            for (int k0 = 0; k0 < n_el; k0 += 32) {
+                const bool ok = k0 + lane < n_el && philox_u53(pk, a.spawn_stream, base + k0 + lane) < waste_thr;
+                const uint32_t sm = __ballot_sync(0xffffffffu, ok);
+                if (sm) { kstar = k0 + __ffs(sm) - 1; break; }
+            }
             if (kstar < n_el) {
                 uint64_t prev = 0;  // select the (kstar+1)-th smallest (key, index) among the eligible cells
                 bool first = true;
                 for (int it = 0; it <= kstar; ++it) {
                     uint64_t best = ~0ull;
-                    for (int i = lane; i < n_waste; i += 32) {
-                        if ((g[a.waste_cell[i]] & 0x7F) == CB(C_WASTE)) continue;
-                        const uint64_t kx = static_cast<uint64_t>(keys[i]) << 32 | static_cast<uint32_t>(i);
-                        if ((first || kx > prev) && kx < best) best = kx;
+                    if (n_waste <= 1024) {
+                        for (uint32_t bits = el_bits; bits; bits &= bits - 1) {
+                            const int i = lane + 32 * (__ffs(bits) - 1);
+                            const uint64_t kx = static_cast<uint64_t>(keys[i]) << 32 | static_cast<uint32_t>(i);
+                            if ((first || kx > prev) && kx < best) best = kx;
+                        }
+                    } else {  // more than 32 points per lane: the mask wrapped, test the cells again
+                        for (int i = lane; i < n_waste; i += 32) {
+                            if ((g[a.waste_cell[i]] & 0x7F) == CB(C_WASTE)) continue;
+                            const uint64_t kx = static_cast<uint64_t>(keys[i]) << 32 | static_cast<uint32_t>(i);
+                            if ((first || kx > prev) && kx < best) best = kx;
+                        }
                     }
                     prev = warp_min_u64(best);
                     first = false;
