@@ -28,6 +28,13 @@ def _assert_state(env, grid, pos, ori, tag):
     assert np.array_equal(g, grid), (tag, "grid")
 
 
+def _assert_env0(env, grid, pos, ori, tag):
+    g, p, o = _state(env)
+    assert np.array_equal(p[0], pos), (tag, "pos")
+    assert np.array_equal(o[0], ori), (tag, "ori")
+    assert np.array_equal(g[0], grid), (tag, "grid")
+
+
 def test_philox_on_device():
     from sequential_social_dilemma_games_b200.batched import philox_selftest
     kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
@@ -38,41 +45,60 @@ def test_philox_on_device():
         assert tuple(int(x) for x in philox_selftest(ctr, key)) == want
 
 
+def _order(fx, t, sel=slice(None), explicit=False):
+    """The action order of step t, or None when it is the agent order and the caller does not insist: None lets the
+    step take the specialised full-step kernel, an explicit order always takes the general kernel."""
+    o = fx["order"][t][sel]
+    if not explicit and np.array_equal(o, np.broadcast_to(np.arange(o.shape[-1], dtype=o.dtype), o.shape)):
+        return None
+    return o
+
+
+@pytest.mark.parametrize("explicit_order", [False, True], ids=["fast", "general"])
 @pytest.mark.parametrize("name", TAPE_FIXTURES)
-def test_tape_golden(name):
-    """Reference trajectories replayed on the device from the recorded RNG tape."""
+def test_tape_golden(name, explicit_order):
+    """Reference trajectories replayed on the device from the recorded RNG tape, through the specialised kernel
+    (agent-order steps of whole warps) and through the general kernel (explicit action order)."""
     fx = Fixture(name)
-    env = _env(fx.cfg, fx.B)
-    env.set_state(fx["init_grid"], fx["init_pos"], fx["init_ori"])
-    assert np.array_equal(env.render(rotate=False).cpu().numpy(), fx["init_obs"])  # reset() view, map_env.py:239
+    rep = 1 if explicit_order else -(-4 // fx.B)  # the specialised kernel steps whole warps of 4 (2) envs
+    sel = np.arange(fx.B * rep) % fx.B
+    env = _env(fx.cfg, len(sel))
+    env.set_state(fx["init_grid"][sel], fx["init_pos"][sel], fx["init_ori"][sel])
+    assert np.array_equal(env.render(rotate=False).cpu().numpy(), fx["init_obs"][sel])  # reset() view, map_env.py:239
     for t in range(fx.T):
-        obs, rew = env.step(fx["actions"][t], action_order=fx["order"][t], tape=fx.tape(t))
-        _assert_state(env, fx["grid"][t], fx["pos"][t], fx["ori"][t], (name, t))
-        assert np.array_equal(rew.cpu().numpy(), fx["reward"][t]), (name, t, "reward")
-        assert np.array_equal(obs.cpu().numpy(), fx["obs"][t]), (name, t, "obs")
+        obs, rew = env.step(fx["actions"][t][sel], action_order=_order(fx, t, sel, explicit_order), tape=fx.tape(t, sel))
+        _assert_state(env, fx["grid"][t][sel], fx["pos"][t][sel], fx["ori"][t][sel], (name, t))
+        assert np.array_equal(rew.cpu().numpy(), fx["reward"][t][sel]), (name, t, "reward")
+        assert np.array_equal(obs.cpu().numpy(), fx["obs"][t][sel]), (name, t, "obs")
     st = env.stats()
-    assert st["env_steps"] == fx.T * fx.B and st["reward_sum"] == int(fx["reward"].sum())
+    assert st["env_steps"] == fx.T * len(sel) and st["reward_sum"] == int(fx["reward"][:, sel].sum())
 
 
+@pytest.mark.parametrize("explicit_order", [False, True], ids=["fast", "general"])
 @pytest.mark.parametrize("name", PHILOX_FIXTURES)
-def test_philox_golden(name):
-    """Reference driven by the production Philox streams: on-device reset + step, no tape."""
+def test_philox_golden(name, explicit_order):
+    """Reference driven by the production Philox streams: on-device reset + step, no tape.  Every fixture env has its
+    own seed, so it runs as env 0 of its own handle -- of 4 envs for the specialised kernel (whole warps; the other
+    three are bystanders with neighbouring env ids), of 1 env for the general kernel."""
     fx = Fixture(name)
     reset_at = list(fx["reset_at"])
+    nb = 1 if explicit_order else 4
     for b in range(fx.B):
-        env = _env(fx.cfg, 1, seed=int(fx["seeds"][b]), env_id_offset=int(fx["env_ids"][b]))
+        env = _env(fx.cfg, nb, seed=int(fx["seeds"][b]), env_id_offset=int(fx["env_ids"][b]))
         obs = env.reset()
-        _assert_state(env, fx["init_grid"][b:b + 1], fx["init_pos"][b:b + 1], fx["init_ori"][b:b + 1], (name, b, "reset"))
+        _assert_env0(env, fx["init_grid"][b], fx["init_pos"][b], fx["init_ori"][b], (name, b, "reset"))
         assert np.array_equal(obs.cpu().numpy()[0], fx["init_obs"][b])
         for t in range(fx.T):
             if t in reset_at:
                 ri = reset_at.index(t)
                 obs = env.reset()
-                _assert_state(env, fx["reset_grid"][ri, b:b + 1], fx["reset_pos"][ri, b:b + 1], fx["reset_ori"][ri, b:b + 1], (name, b, t, "reset"))
+                _assert_env0(env, fx["reset_grid"][ri, b], fx["reset_pos"][ri, b], fx["reset_ori"][ri, b], (name, b, t, "reset"))
                 assert np.array_equal(obs.cpu().numpy()[0], fx["reset_obs"][ri, b])
             assert env.t == t
-            obs, rew = env.step(fx["actions"][t, b:b + 1], action_order=fx["order"][t, b:b + 1])
-            _assert_state(env, fx["grid"][t, b:b + 1], fx["pos"][t, b:b + 1], fx["ori"][t, b:b + 1], (name, b, t))
+            order = _order(fx, t, slice(b, b + 1), explicit_order)
+            obs, rew = env.step(np.repeat(fx["actions"][t, b:b + 1], nb, axis=0),
+                                action_order=None if order is None else np.repeat(order, nb, axis=0))
+            _assert_env0(env, fx["grid"][t, b], fx["pos"][t, b], fx["ori"][t, b], (name, b, t))
             assert np.array_equal(rew.cpu().numpy()[0], fx["reward"][t, b]), (name, b, t)
             assert np.array_equal(obs.cpu().numpy()[0], fx["obs"][t, b]), (name, b, t)
 
@@ -86,7 +112,7 @@ def test_config2_cleanup_4096_tape():
     env = _env(fx.cfg, B)
     env.set_state(fx["init_grid"][sel], fx["init_pos"][sel], fx["init_ori"][sel])
     for t in range(fx.T):
-        obs, rew = env.step(fx["actions"][t][sel], action_order=fx["order"][t][sel], tape=fx.tape(t, sel))
+        obs, rew = env.step(fx["actions"][t][sel], action_order=_order(fx, t, sel), tape=fx.tape(t, sel))  # agent order: specialised kernel
         if t % 10 == 0 or t == fx.T - 1:
             _assert_state(env, fx["grid"][t][sel], fx["pos"][t][sel], fx["ori"][t][sel], ("cfg2", t))
             assert np.array_equal(obs.cpu().numpy(), fx["obs"][t][sel]), ("cfg2", t)
