@@ -210,6 +210,55 @@ def test_render_map(game):
         assert np.array_equal(frames[b], lut[chars]), (game, b)
 
 
+def _random_map(rng, game, n_agents):
+    H, W = int(rng.randint(5, 25)), int(rng.randint(6, 41))
+    m = np.full((H, W), ' ', dtype='<U1')
+    m[0, :] = m[-1, :] = m[:, 0] = m[:, -1] = '@'
+    inner = [(r, c) for r in range(1, H - 1) for c in range(1, W - 1)]
+    rng.shuffle(inner)
+    n_wall = len(inner) // 10
+    for r, c in inner[:n_wall]:
+        m[r, c] = '@'
+    rest = inner[n_wall:]
+    n_spawn = min(len(rest) // 3, n_agents + int(rng.randint(0, 6)))
+    for r, c in rest[:n_spawn]:
+        m[r, c] = 'P'
+    pool = rest[n_spawn:]
+    for r, c in pool[:len(pool) * 2 // 3]:
+        m[r, c] = rng.choice(['A', ' ']) if game == "harvest" else rng.choice(['B', 'H', 'R', 'S', ' '])
+    return [''.join(row) for row in m], n_spawn
+
+
+@pytest.mark.parametrize("case", range(14))
+def test_random_maps_vs_oracle(case):
+    """Random wall-enclosed maps (interior walls, scattered spawn / apple / waste / river cells), 1..16 agents, view radius
+    2..10 (5, 7 and 10 take the specialised kernel when the batch fills whole warps), both games, against the oracle."""
+    from oracle.oracle import OracleEnv
+    from sequential_social_dilemma_games_b200.batched import make_config
+    rng = np.random.RandomState(1000 + case)
+    game = "harvest" if case % 2 == 0 else "cleanup"
+    N = int(rng.randint(1, 17))
+    while True:
+        amap, n_spawn = _random_map(rng, game, N)
+        if n_spawn >= N:
+            break
+    view = int(rng.choice([2, 3, 5, 5, 7, 7, 10, 10]))
+    B = int(rng.choice([8, 24, 37, 64]))
+    cfg = make_config(game, num_agents=N, view_size=view, ascii_map=amap)
+    env = _env(cfg, B, seed=case, env_id_offset=case * 7)
+    orc = OracleEnv(cfg, B, seed=case, env_id_offset=case * 7, n_threads=4)
+    assert np.array_equal(env.reset().cpu().numpy(), orc.reset()), (case, "reset")
+    _assert_state(env, orc.grid, orc.pos, orc.ori, (case, "reset"))
+    for t in range(50):
+        a = _random_actions(rng, cfg, B, p_clean=0.3 if game == "cleanup" else 0.0)
+        a[rng.rand(B, N) < 0.05] = -1
+        obs, rew = env.step(a)
+        oobs, orew = orc.step(a)
+        assert np.array_equal(rew.cpu().numpy(), orew), (case, t, "reward", amap)
+        _assert_state(env, orc.grid, orc.pos, orc.ori, (case, t, amap))
+        assert np.array_equal(obs.cpu().numpy(), oobs), (case, t, "obs")
+
+
 def test_reset_needs_spawn_points():
     """'There are not enough spawn points! Check your map?' (map_env.py:661) is raised by reset, not by construction:
     the adapters place hand-made agents with ssd_set_state on maps with fewer 'P' cells than agents."""
