@@ -175,6 +175,7 @@ int ssd_step_host(ssd_handle h, const int8_t* actions_host, uint8_t* obs_host, i
  * only chains launches of 1.5 to 12 waves of CTAs (about 28K to 230K Harvest envs on a B200): smaller grids
  * have no tail to hide, larger ones amortise it. */
 #define SSD_OPT_CHAIN_STEPS 1
+#define SSD_OPT_GENERAL_KERNEL 2 /* 1: step everything with the general kernel (tests compare the two kernels) */
 int ssd_set_option(ssd_handle h, int option, int64_t value);
 
 /* Running counters since creation (host i64[SSD_NUM_STATS]); synchronises `stream`. */

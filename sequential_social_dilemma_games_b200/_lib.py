@@ -12,6 +12,7 @@ ABI_VERSION = 1
 MAX_AGENTS = 16
 NUM_STATS = 8
 OPT_CHAIN_STEPS = 1
+OPT_GENERAL_KERNEL = 2
 PHASE_MOVES, PHASE_CONSUME, PHASE_BEAMS, PHASE_SPAWN, PHASE_RENDER, PHASE_ALL = 1, 2, 4, 8, 16, 31
 
 # every symbol include/ssd_b200.h declares (tests/test_cabi.py checks the list against the header)

@@ -208,6 +208,11 @@ class BatchedSSDEnv(object):
         _lib.check(_lib.lib.ssd_set_option(self._h, _lib.OPT_CHAIN_STEPS, int(bool(on))))
         return self
 
+    def general_kernel_only(self, on=True):
+        """SSD_OPT_GENERAL_KERNEL: step with the general kernel even where the specialised one applies (tests)."""
+        _lib.check(_lib.lib.ssd_set_option(self._h, _lib.OPT_GENERAL_KERNEL, int(bool(on))))
+        return self
+
     def stats(self):
         out = np.zeros(_lib.NUM_STATS, dtype=np.int64)
         _lib.check(_lib.lib.ssd_stats(self._h, out.ctypes.data, self._stream()))

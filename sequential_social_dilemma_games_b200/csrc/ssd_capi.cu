@@ -526,6 +526,10 @@ int ssd_set_option(ssd_handle h, int option, int64_t value) {
             h->chain.enabled = value != 0;
             h->chain.valid = false;
             return SSD_OK;
+        case SSD_OPT_GENERAL_KERNEL:
+            h->chain.general_only = value != 0;
+            h->chain.valid = false;
+            return SSD_OK;
         default:
             return fail(SSD_ERR_INVALID, "unknown option %d", option);
     }

@@ -155,6 +155,7 @@ struct StepArgs {
 // Host-side bookkeeping of the step chain (one per handle).
 struct ChainState {
     bool enabled = false, valid = false;
+    bool general_only = false;  // SSD_OPT_GENERAL_KERNEL
     cudaStream_t stream = nullptr;
     int env_begin = 0, env_end = 0;
     uint32_t epoch = 0;

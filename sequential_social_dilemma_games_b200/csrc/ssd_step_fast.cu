@@ -7,7 +7,7 @@ namespace ssd {
 
 // ====================================================================== the fast path of a full step
 // Same algorithm as ssd_step_kernel, specialised for what a production step is: all phases, every env
-// stepped (no mask), actions in agent order, N <= 8 (8 lanes per env, 4 envs per warp), a packed
+// stepped (no mask), N <= 8 (8 lanes per env, 4 envs per warp) or N <= 16 (16 lanes, 2 envs), a packed
 // row renderer for this view size and only whole warps (the launcher sends any tail envs through the
 // general kernel).  What the specialisation buys: no per-env / per-phase flag tests, fire flags from
 // one ballot, view geometry straight from the agent registers, and observation rows that leave
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
             me.act = a.actions[gi];
             me.key = (w & 255) << 8 | ((w >> 8) & 255);
             me.ori = (w >> 16) & 3;
-            S.order[al] = static_cast<uint8_t>(al);
+            S.order[al] = a.order != nullptr ? a.order[gi] : static_cast<uint8_t>(al);  // action-dict order (NULL: agent order)
             S.rew[al] = 0;
         }
         mbar_wait(mbar, 0);  // tiles landed
@@ -229,16 +229,18 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
         }
         if (KIND == SSD_KIND_CLEANUP && !SSD_SKIP(a.debug, 8)) {  // firing order matters: a CLEAN beam turns 'H' into 'R' for the next one
             fmask = __ballot_sync(0xffffffffu, me.act == 7 || me.act == 8);
+            const bool in_order = a.order != nullptr;  // the k-th entry of the action dict is agent S.order[k]
             for (int k = 0; k < N; ++k) {
-                if (!((fmask >> k) & kSlotLsb)) continue;  // nobody in this warp fires in slot k
-                const bool fire = (fmask >> (gbase + k)) & 1u;
-                const int act_k = __shfl_sync(0xffffffffu, me.act, k, G);
-                const uint32_t key_k = __shfl_sync(0xffffffffu, me.key, k, G);
-                const int ori_k = __shfl_sync(0xffffffffu, me.ori, k, G);
+                const int ag = in_order ? S.order[k] : k;
+                const bool fire = (fmask >> (gbase + ag)) & 1u;
+                if (in_order ? !__any_sync(0xffffffffu, fire) : !((fmask >> k) & kSlotLsb)) continue;  // nobody in this warp fires in slot k
+                const int act_k = __shfl_sync(0xffffffffu, me.act, ag, G);
+                const uint32_t key_k = __shfl_sync(0xffffffffu, me.key, ag, G);
+                const int ori_k = __shfl_sync(0xffffffffu, me.ori, ag, G);
                 const bool clean = act_k == 8;
                 int upd = -1, hits = 0, n = 0;
                 if (fire && al < 3) n = ray_walk(a, S, g, key_k, ori_k, al, clean, upd, hits);
-                if (fire && al == k && !clean) { me.rew -= 1; ++cnt.fires; }  // fire_beam agent.py:170-172
+                if (fire && al == ag && !clean) { me.rew -= 1; ++cnt.fires; }  // fire_beam agent.py:170-172
                 __syncwarp();
                 if (fire && al < 3) {
                     S.raylen[k * 3 + al] = static_cast<uint8_t>(n);
@@ -311,12 +313,15 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
                 __syncwarp();
             }
             if (KIND == SSD_KIND_CLEANUP) {  // beams in firing order: a later beam overwrites an earlier one
+                const bool in_order = a.order != nullptr;
                 for (int k = 0; k < N; ++k) {
-                    if (!((fmask >> k) & kSlotLsb)) continue;
-                    const uint32_t key_k = __shfl_sync(0xffffffffu, me.key, k, G);
-                    const int ori_k = __shfl_sync(0xffffffffu, me.ori, k, G);
-                    const int act_k = __shfl_sync(0xffffffffu, me.act, k, G);
-                    if (((fmask >> (gbase + k)) & 1u) && al < 3) {
+                    const int ag = in_order ? S.order[k] : k;
+                    const bool fired = (fmask >> (gbase + ag)) & 1u;
+                    if (in_order ? !__any_sync(0xffffffffu, fired) : !((fmask >> k) & kSlotLsb)) continue;
+                    const uint32_t key_k = __shfl_sync(0xffffffffu, me.key, ag, G);
+                    const int ori_k = __shfl_sync(0xffffffffu, me.ori, ag, G);
+                    const int act_k = __shfl_sync(0xffffffffu, me.act, ag, G);
+                    if (fired && al < 3) {
                         const int d0 = (ori_k == 1) - (ori_k == 3), d1 = (ori_k == 2) - (ori_k == 0);
                         int r = static_cast<int>(key_k >> 8) + d0, c = static_cast<int>(key_k & 255) + d1;
                         if (al == 1) { r += -d1 - d0; c += d0 - d1; }
@@ -419,7 +424,7 @@ cudaError_t launch_step(const StepArgs& a, int threads, cudaStream_t stream, Cha
     const bool tape = a.tape_u != nullptr || a.tape_move != nullptr;
     // a production step: everything the specialised kernel assumes (see ssd_step_fast_kernel)
     static const bool no_fast = getenv("SSD_NO_FAST") != nullptr;
-    const bool full = !no_fast && a.phases == SSD_PHASE_ALL && a.mask == nullptr && a.order == nullptr && !a.use_beam_buf &&
+    const bool full = !no_fast && !(chain && chain->general_only) && a.phases == SSD_PHASE_ALL && a.mask == nullptr && !a.use_beam_buf &&
                       !a.rew_accumulate && a.obs != nullptr && a.rew != nullptr && a.actions != nullptr && fast_rows &&
                       (a.V == 11 || a.V == 15 || a.V == 21) && a.env_begin % (32 / a.G) == 0;
     if (!full) {

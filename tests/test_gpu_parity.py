@@ -46,8 +46,7 @@ def test_philox_on_device():
 
 
 def _order(fx, t, sel=slice(None), explicit=False):
-    """The action order of step t, or None when it is the agent order and the caller does not insist: None lets the
-    step take the specialised full-step kernel, an explicit order always takes the general kernel."""
+    """The action order of step t, or None when it is the agent order and the caller does not insist."""
     o = fx["order"][t][sel]
     if not explicit and np.array_equal(o, np.broadcast_to(np.arange(o.shape[-1], dtype=o.dtype), o.shape)):
         return None
@@ -57,12 +56,12 @@ def _order(fx, t, sel=slice(None), explicit=False):
 @pytest.mark.parametrize("explicit_order", [False, True], ids=["fast", "general"])
 @pytest.mark.parametrize("name", TAPE_FIXTURES)
 def test_tape_golden(name, explicit_order):
-    """Reference trajectories replayed on the device from the recorded RNG tape, through the specialised kernel
-    (agent-order steps of whole warps) and through the general kernel (explicit action order)."""
+    """Reference trajectories replayed on the device from the recorded RNG tape, through the specialised kernel (whole
+    warps; the order array is dropped where it is the agent order) and through the general kernel (explicit order)."""
     fx = Fixture(name)
     rep = 1 if explicit_order else -(-4 // fx.B)  # the specialised kernel steps whole warps of 4 (2) envs
     sel = np.arange(fx.B * rep) % fx.B
-    env = _env(fx.cfg, len(sel))
+    env = _env(fx.cfg, len(sel)).general_kernel_only(explicit_order)
     env.set_state(fx["init_grid"][sel], fx["init_pos"][sel], fx["init_ori"][sel])
     assert np.array_equal(env.render(rotate=False).cpu().numpy(), fx["init_obs"][sel])  # reset() view, map_env.py:239
     for t in range(fx.T):
@@ -84,7 +83,7 @@ def test_philox_golden(name, explicit_order):
     reset_at = list(fx["reset_at"])
     nb = 1 if explicit_order else 4
     for b in range(fx.B):
-        env = _env(fx.cfg, nb, seed=int(fx["seeds"][b]), env_id_offset=int(fx["env_ids"][b]))
+        env = _env(fx.cfg, nb, seed=int(fx["seeds"][b]), env_id_offset=int(fx["env_ids"][b])).general_kernel_only(explicit_order)
         obs = env.reset()
         _assert_env0(env, fx["init_grid"][b], fx["init_pos"][b], fx["init_ori"][b], (name, b, "reset"))
         assert np.array_equal(obs.cpu().numpy()[0], fx["init_obs"][b])
