@@ -273,16 +273,18 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
             __syncwarp();
         }
 
-        // ---- store: grid tiles back to HBM
+        // ---- store: grid tiles back to HBM, one TMA bulk store per tile.  The overlay below repaints the tiles, so the
+        // warp waits until the copy engine has READ them (not until the writes have landed).
         if (!SSD_SKIP(a.debug, 64)) {
-            const int n16 = a.env_bytes >> 4;
+            fence_async_smem();  // the phases above wrote the tiles with ordinary stores
+            __syncwarp();
+            if (elect_one()) {
 #pragma unroll
-            for (int q = 0; q < EPW; ++q) {
-                uint4* gdst = reinterpret_cast<uint4*>(a.grid + static_cast<size_t>(we + q) * a.env_bytes);
-                const uint4* gsrc = reinterpret_cast<const uint4*>(tiles + a.pad_bytes + q * tile_pitch);
-#pragma unroll 1
-                for (int i = lane; i < n16; i += 32) gdst[i] = gsrc[i];
+                for (int q = 0; q < EPW; ++q)
+                    bulk_s2g(a.grid + static_cast<size_t>(we + q) * a.env_bytes, tiles + a.pad_bytes + q * tile_pitch, a.env_bytes);
+                bulk_commit();
             }
+            bulk_wait_read();
         }
         __syncwarp();  // the write-back above has read the tiles
 
