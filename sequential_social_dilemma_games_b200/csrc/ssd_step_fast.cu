@@ -250,11 +250,7 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
                 __syncwarp();
             }
         }
-        if (valid) {
-            me.rew += S.rew[al];  // -50 per hit taken
-            a.agents[gi] = (me.key >> 8) | (me.key & 255) << 8 | static_cast<uint32_t>(me.ori) << 16;
-            a.rew[gi] = me.rew;
-        }
+        if (valid) me.rew += S.rew[al];  // -50 per hit taken
 
         // ---- phase B: the whole warp per env
         if (KIND != SSD_KIND_PLAIN && !SSD_SKIP(a.debug, 4)) {
@@ -353,6 +349,10 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
             if (!SSD_SKIP(a.debug, 2))
             render_rows_tma<VT>(s_view, tiles, s_color, reinterpret_cast<uint32_t*>(wbase + a.Lf.w_union + a.Lf.u_stage),
                                 a.obs + static_cast<size_t>(we) * a.obs_env, EPW * N * VT, a.debug);
+        }
+        if (valid) {  // agent words and rewards last: no ordinary global store is in flight when the row loop fences
+            a.agents[gi] = (me.key >> 8) | (me.key & 255) << 8 | static_cast<uint32_t>(me.ori) << 16;
+            a.rew[gi] = me.rew;
         }
         if (a.publish) {  // everything this task wrote (grid, agent words, rewards, observation rows) is visible before the word is
             bulk_wait_all();  // all lanes: only the lane that committed the bulk stores actually waits
