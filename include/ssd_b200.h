@@ -134,6 +134,13 @@ int ssd_reset(ssd_handle h, const uint8_t* mask, uint8_t* obs_out, void* stream)
 int ssd_step(ssd_handle h, const int8_t* actions, const uint8_t* action_order, const SsdTape* tape,
              uint8_t* obs_out, int32_t* reward_out, void* stream);
 
+/* A scripted rollout: `num_steps` consecutive ssd_step calls whose actions all exist up front -- actions dev
+ * i8[num_steps][B][N] in agent order, rewards dev i32[num_steps][B][N], observations of step s into slot s % ring_slots of
+ * obs_ring dev u8[ring_slots][B][N][V][V][3].  Because no input of a later step is produced between the launches, the
+ * library chains the step kernels (see SSD_OPT_CHAIN_STEPS) regardless of the option; results equal num_steps calls of
+ * ssd_step.  This is the reference's own benchmark shape (random-action rollouts). */
+int ssd_rollout(ssd_handle h, int num_steps, const int8_t* actions, uint8_t* obs_ring, int ring_slots, int32_t* reward_out, void* stream);
+
 /* A subset of the phases of one step (SSD_PHASE_* mask), for overridden hooks: e.g. run
  * MOVES|CONSUME, apply a Python custom_action through ssd_get_state/ssd_set_state, then
  * SPAWN|RENDER.  Beam cells persist on the device between the phase calls of one step; rewards

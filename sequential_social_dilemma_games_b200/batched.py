@@ -147,6 +147,21 @@ class BatchedSSDEnv(object):
         del keep
         return obs, reward_out
 
+    def rollout(self, actions, obs_ring=None, reward_out=None):
+        """T steps with actions that all exist up front (int8 [T, B, N] on the device): ssd_rollout.  Observations of
+        step s land in obs_ring[s % R] (uint8 [R, B, N, V, V, 3], default R = 1), rewards in reward_out [T, B, N]."""
+        B, N = self.num_envs, self.cfg.num_agents
+        assert actions.is_cuda and actions.dtype == torch.int8 and actions.is_contiguous() and tuple(actions.shape[1:]) == (B, N)
+        T = int(actions.shape[0])
+        if obs_ring is None:
+            obs_ring = torch.empty((1,) + tuple(self.obs_shape), dtype=torch.uint8, device=self.device)
+        assert obs_ring.is_cuda and obs_ring.dtype == torch.uint8 and obs_ring.is_contiguous() and tuple(obs_ring.shape[1:]) == tuple(self.obs_shape)
+        if reward_out is None:
+            reward_out = torch.empty((T, B, N), dtype=torch.int32, device=self.device)
+        assert reward_out.is_cuda and reward_out.dtype == torch.int32 and reward_out.is_contiguous() and tuple(reward_out.shape) == (T, B, N)
+        _lib.check(_lib.lib.ssd_rollout(self._h, T, _ptr(actions), _ptr(obs_ring), int(obs_ring.shape[0]), _ptr(reward_out), self._stream()))
+        return obs_ring, reward_out
+
     def render(self, rotate=True, out=None):
         obs = self._obs_buf(out)
         _lib.check(_lib.lib.ssd_render(self._h, int(bool(rotate)), _ptr(obs), self._stream()))

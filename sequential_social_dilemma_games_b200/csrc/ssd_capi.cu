@@ -438,6 +438,23 @@ int ssd_step(ssd_handle h, const int8_t* actions, const uint8_t* action_order, c
     return ssd_step_phases(h, SSD_PHASE_ALL, actions, action_order, tape, obs_out, reward_out, stream);
 }
 
+int ssd_rollout(ssd_handle h, int num_steps, const int8_t* actions, uint8_t* obs_ring, int ring_slots, int32_t* reward_out, void* stream) {
+    if (check_handle(h)) return SSD_ERR_INVALID;
+    if (num_steps < 0 || ring_slots < 1) return fail(SSD_ERR_INVALID, "num_steps must be >= 0 and ring_slots >= 1");
+    if (!actions || !obs_ring || !reward_out) return fail(SSD_ERR_INVALID, "actions, obs_ring and reward_out are required");
+    // every step's inputs exist before the first launch: exactly the precondition of chained steps
+    const bool was_enabled = h->chain.enabled;
+    h->chain.enabled = true;
+    const size_t bn = static_cast<size_t>(h->B) * h->cfg.num_agents, obs_bytes = static_cast<size_t>(h->B) * h->obs_env;
+    int rc = SSD_OK;
+    for (int s = 0; s < num_steps && rc == SSD_OK; ++s)
+        rc = ssd_step_phases(h, SSD_PHASE_ALL, actions + s * bn, nullptr, nullptr, obs_ring + (s % ring_slots) * obs_bytes,
+                             reward_out + s * bn, stream);
+    h->chain.enabled = was_enabled;
+    h->chain.valid = false;
+    return rc;
+}
+
 int ssd_get_beams(ssd_handle h, uint8_t* out, void* stream) {
     if (check_handle(h) || !out) return SSD_ERR_INVALID;
     h->chain.valid = false;

@@ -275,6 +275,24 @@ def test_reset_needs_spawn_points():
     assert rew.cpu().numpy().tolist() == [[1, 0, 0]] * 4
 
 
+def test_rollout_equals_steps():
+    """ssd_rollout (T chained steps in one call, observation ring) == T calls of ssd_step."""
+    from sequential_social_dilemma_games_b200.batched import make_config
+    cfg = make_config("harvest")
+    B, T, R = 32768, 24, 3
+    g = torch.Generator(device="cuda").manual_seed(8)
+    acts = torch.randint(0, cfg.num_actions, (T, B, cfg.num_agents), generator=g, device="cuda", dtype=torch.int8)
+    a, b = _env(cfg, B, seed=12), _env(cfg, B, seed=12)
+    a.reset(); b.reset()
+    ring, rews = a.rollout(acts, obs_ring=torch.empty((R,) + tuple(a.obs_shape), dtype=torch.uint8, device="cuda"))
+    for t in range(T):
+        obs, rew = b.step(acts[t])
+        assert torch.equal(rew, rews[t]), t
+        if t >= T - R:
+            assert torch.equal(obs, ring[t % R]), t
+    assert all(torch.equal(x, y) for x, y in zip(a.get_state(), b.get_state())) and a.stats() == b.stats() and a.t == b.t
+
+
 @pytest.mark.parametrize("B", [32768, 32770])
 def test_chain_is_broken_safely(B):
     """Chained stepping interleaved with everything else a caller may do (masked reset, state download / upload,
