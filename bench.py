@@ -9,6 +9,11 @@ GPU (one fused kernel launch).  Workload at N=1: BASELINE.json configs[2] -- Har
 default HARVEST_MAP, 65 536 batched envs, 15x15x3 egocentric uint8 observations; with N>1 every GPU
 owns 65 536 envs of its own (weak scaling, no collective on the step path, Philox streams keyed by
 global env id).  Prints ONE JSON line (rank 0).
+
+`value` times K steps of BatchedSSDEnv.step with consecutive steps chained (SSD_OPT_CHAIN_STEPS: programmatic dependent
+launch; the actions are pre-generated, which is the option's precondition); `stream_ordered` is the same K steps
+without chaining; `e2e` goes through ssd_step_host with pinned host buffers (H2D actions, D2H observations + rewards
+inside the timed region); `cpu_baseline` / `--impl reference` time the C port of the reference's step on the host cores.
 """
 import argparse
 import json
