@@ -150,6 +150,7 @@ struct StepArgs {
     uint32_t epoch;
     int dep_wait;         // wait for done[task] == epoch - 1 instead of relying on stream order
     int publish;          // write done[task] = epoch when the task's results are visible
+    int pdl_wait;         // launched early behind the previous kernel of the stream: griddepcontrol.wait after the prologue
 };
 
 // Host-side bookkeeping of the step chain (one per handle).

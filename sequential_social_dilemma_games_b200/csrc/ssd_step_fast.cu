@@ -135,6 +135,11 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
     const int we = a.env_begin + (blockIdx.x * nwarps + warp) * EPW;  // the launcher only sends whole warps
     Counters cnt = {0, 0, 0, 0, 0, 0, 0};
 
+    // Every fast launch carries the programmatic-serialization attribute: the CTAs become resident while the previous
+    // kernel of the stream drains and do everything above (tables, barrier) early.  Unless this step is chained to it
+    // task by task (dep_wait), nothing that kernel wrote is touched before it has completed.
+    if (a.pdl_wait) pdl_wait();
+
     if (we < a.env_end) {
         // ---- load: one TMA bulk copy per env tile; zero the frames while they are in flight
         if (lane == 0) {
@@ -408,7 +413,7 @@ static cudaError_t launch_fast(const StepArgs& a, int threads, cudaStream_t stre
         cudaLaunchAttribute at[1];                                                                              \
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                          \
         at[0].val.programmaticStreamSerializationAllowed = 1;                                                   \
-        lc.attrs = at; lc.numAttrs = a.dep_wait ? 1 : 0;                                                        \
+        lc.attrs = at; lc.numAttrs = (a.dep_wait || a.pdl_wait) ? 1 : 0;                                                        \
         return cudaLaunchKernelEx(&lc, kern, a);                                                                \
     } while (0)
     switch (a.V) {
@@ -466,6 +471,8 @@ cudaError_t launch_step(const StepArgs& a, int threads, cudaStream_t stream, Cha
     } else if (chain) {
         chain->valid = false;
     }
+    static const bool no_pdl = getenv("SSD_NO_PDL") != nullptr;  // experiments
+    f.pdl_wait = !f.dep_wait && !no_pdl;
     cudaError_t e = cudaSuccess;
 #define SSD_FAST(KIND_)                                                                                                     \
     e = a.G == 8 ? (tape ? launch_fast<KIND_, true, 8>(f, threads, stream) : launch_fast<KIND_, false, 8>(f, threads, stream)) \
