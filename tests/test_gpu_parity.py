@@ -275,6 +275,30 @@ def test_reset_needs_spawn_points():
     assert rew.cpu().numpy().tolist() == [[1, 0, 0]] * 4
 
 
+@pytest.mark.parametrize("game", ["harvest", "cleanup"])
+def test_checkpoint_resume(game):
+    """State download + (seed, step counter) is a complete checkpoint: a fresh handle resumed from it continues the
+    trajectory bit for bit (Philox streams are pure functions of seed, global env id and step)."""
+    from sequential_social_dilemma_games_b200.batched import make_config
+    cfg = make_config(game)
+    B = 4096
+    g = torch.Generator(device="cuda").manual_seed(2)
+    acts = torch.randint(0, cfg.num_actions, (60, B, cfg.num_agents), generator=g, device="cuda", dtype=torch.int8)
+    a = _env(cfg, B, seed=777, env_id_offset=10)
+    a.reset()
+    for t in range(30):
+        a.step(acts[t])
+    ckpt = ([x.cpu().numpy().copy() for x in a.get_state()], a.t)
+    b = _env(cfg, B, seed=1, env_id_offset=10)
+    b.set_state(*ckpt[0])
+    b.seed(777, t=ckpt[1])
+    for t in range(30, 60):
+        oa, ra = a.step(acts[t])
+        ob, rb = b.step(acts[t])
+        assert torch.equal(ra, rb) and torch.equal(oa, ob), t
+    assert all(torch.equal(x, y) for x, y in zip(a.get_state(), b.get_state()))
+
+
 def test_rollout_equals_steps():
     """ssd_rollout (T chained steps in one call, observation ring) == T calls of ssd_step."""
     from sequential_social_dilemma_games_b200.batched import make_config
