@@ -59,11 +59,13 @@ struct Counters {  // per-lane event counts, reduced per warp at the end of the 
 // ====================================================================== phase A: moves
 __device__ __forceinline__ bool occupied(const uint16_t* p, int N, uint32_t key) {
     bool f = false;  // `x in self.agent_pos` (map_env.py:251-253)
+#pragma unroll 1
     for (int a = 0; a < N; ++a) f |= (p[a] == key);
     return f;
 }
 __device__ __forceinline__ int by_pos(const uint16_t* p, int N, uint32_t key) {
     int o = -1;  // dict built in agent order: the LAST agent on a cell wins (map_env.py:397)
+#pragma unroll 1
     for (int a = 0; a < N; ++a) o = (p[a] == key) ? a : o;
     return o;
 }
@@ -77,6 +79,7 @@ __device__ __noinline__ void moves_slow(const StepArgs& a, ES& S, MoveScratch& M
     // mover list in action order (agent_moves is an insertion-ordered dict, map_env.py:400-412)
     uint8_t* shuf = M.shuf;
     int n_mov = 0;
+#pragma unroll 1
     for (int k = 0; k < N; ++k) {
         const int ag = S.order[k];
         if (movers >> ag & 1) shuf[n_mov++] = static_cast<uint8_t>(ag);
@@ -84,22 +87,26 @@ __device__ __noinline__ void moves_slow(const StepArgs& a, ES& S, MoveScratch& M
     // np.random.shuffle(shuffle_list), map_env.py:421-423
     if (TAPE) {
         const uint8_t* mo = a.tape_move + static_cast<size_t>(local_env) * N;
+#pragma unroll 1
         for (int i = 0; i < n_mov; ++i) shuf[i] = mo[i] < N ? mo[i] : static_cast<uint8_t>(N - 1);  // malformed tapes must not fault
     } else {
         uint4 blk = make_uint4(0, 0, 0, 0);
         uint32_t w = 0;
+#pragma unroll 1
         for (int i = n_mov - 1; i >= 1; --i, ++w) {
             if ((w & 3) == 0) blk = philox4x32_10(pk.env, pk.t, STREAM_MOVE, w >> 2, pk.k0, pk.k1);
             const uint32_t j = __umulhi(pick_word(blk, w), static_cast<uint32_t>(i + 1));
             const uint8_t tmp = shuf[i]; shuf[i] = shuf[j]; shuf[j] = tmp;
         }
     }
+#pragma unroll 1
     for (int ag = 0; ag < N; ++ag) M.orig[ag] = (movers >> ag & 1) ? M.tgt[ag] : 0xFFFFu;
 
     // contested cells in lexicographic (row, col) order == ascending key (np.unique axis=0, :424)
     int prev = -1;
     while (true) {
         int cell = 0x10000, cnt = 0;
+#pragma unroll 1
         for (int ag = 0; ag < N; ++ag) {
             const int o = M.orig[ag];
             if (o != 0xFFFF && o > prev) {
@@ -111,6 +118,7 @@ __device__ __noinline__ void moves_slow(const StepArgs& a, ES& S, MoveScratch& M
         if (cnt < 2) continue;
         bool cell_free = true;
         int winner = -1;
+#pragma unroll 1
         for (int i = 0; i < n_mov; ++i) {  // conflicting agents in shuffled order (:441-442)
             const int ag = shuf[i];
             if (M.orig[ag] != cell) continue;
@@ -126,6 +134,7 @@ __device__ __noinline__ void moves_slow(const StepArgs& a, ES& S, MoveScratch& M
             }
         }
         if (cell_free) S.pos[winner] = static_cast<uint16_t>(cell);  // :480-483
+#pragma unroll 1
         for (int i = 0; i < n_mov; ++i) {                            // :486-491
             const int ag = shuf[i];
             if (M.orig[ag] == cell) M.tgt[ag] = S.pos[ag];
@@ -135,9 +144,11 @@ __device__ __noinline__ void moves_slow(const StepArgs& a, ES& S, MoveScratch& M
     // remaining moves: fix-point loop, map_env.py:494-543
     uint32_t alive = movers;
     while (alive) {
+#pragma unroll 1
         for (int ag = 0; ag < N; ++ag) M.snap[ag] = S.pos[ag];  // agent_by_pos snapshot (:495)
         const uint32_t in_copy = alive;                         // moves_copy (:498)
         uint32_t deleted = 0;
+#pragma unroll 1
         for (int k = 0; k < N; ++k) {
             const int ag = S.order[k];
             if (!(in_copy >> ag & 1) || (deleted >> ag & 1)) continue;
@@ -158,6 +169,7 @@ __device__ __noinline__ void moves_slow(const StepArgs& a, ES& S, MoveScratch& M
             }
         }
         if (alive == in_copy) {  // nobody could move freely: move them all (:540-543)
+#pragma unroll 1
             for (int ag = 0; ag < N; ++ag) if (alive >> ag & 1) S.pos[ag] = M.tgt[ag];
             break;
         }
