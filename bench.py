@@ -200,17 +200,17 @@ def run_ours(args, rank, world, local_rank):
 
     for _ in range(args.warmup):
         one_step()
-    # stream-ordered steps first (every kernel waits for the previous one to drain) ...
-    _, ms_plain = timed(args.steps)
-    # ... then the headline: consecutive steps chained with programmatic dependent launch (SSD_OPT_CHAIN_STEPS).
-    # The actions are pre-generated, which is the option's precondition; results are identical (tests/test_gpu_parity.py).
-    chained = not args.no_chain
-    if chained:
-        env.chain_steps(True)
-        for _ in range(args.warmup):
-            one_step()
-    launches0 = env.launch_count
-    with ClockSampler(local_rank) as clk:
+    with ClockSampler(local_rank) as clk:  # clocks and throttle reasons over both timed regions
+        # stream-ordered steps first (every kernel waits for the previous one to drain) ...
+        _, ms_plain = timed(args.steps)
+        # ... then the headline: consecutive steps chained with programmatic dependent launch (SSD_OPT_CHAIN_STEPS).
+        # The actions are pre-generated, which is the option's precondition; results are identical (tests/test_gpu_parity.py).
+        chained = not args.no_chain
+        if chained:
+            env.chain_steps(True)
+            for _ in range(args.warmup):
+                one_step()
+        launches0 = env.launch_count
         ms, ms_max = timed(args.steps)
     launches = env.launch_count - launches0
     value = world * B * N * args.steps / (ms_max * 1e-3)
