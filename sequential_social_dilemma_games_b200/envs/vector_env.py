@@ -22,6 +22,7 @@ import torch
 from ..batched import BatchedSSDEnv, make_config
 from .harvest import HarvestEnv
 from .cleanup import CleanupEnv
+from .spaces import Discrete
 
 _OBS_LUT = (np.arange(256) - 128.0) / 255.0   # map_env.py:199 on every possible uint8
 
@@ -40,7 +41,7 @@ class SSDVectorEnv(object):
         self.uint8_obs = bool(uint8_obs)
         self._t = np.zeros(self.num_envs, dtype=np.int64)
         proto = (HarvestEnv if game.lower() == "harvest" else CleanupEnv)
-        self.action_space = proto.action_space.fget(self)
+        self.action_space = Discrete(proto.NUM_ACTIONS)
         self.view_len = view_size
         self.observation_space = proto.observation_space.fget(self)
         self._act = torch.empty((self.num_envs, self.num_agents), dtype=torch.int8, device=self.engine.device)
