@@ -171,6 +171,24 @@ int ssd_render_map(ssd_handle h, uint8_t* rgb_out, void* stream);
  * Pinned host memory gives full PCIe bandwidth; pageable memory works but is slower. */
 int ssd_step_host(ssd_handle h, const int8_t* actions_host, uint8_t* obs_host, int32_t* reward_host);
 
+/* ---- Policy-side consumer of the observation tensor -------------------------------------------------
+ * The feature trunk of the reference's policy network, models/conv_to_fcnet_v2.py:36-66: Conv2D(6, 3x3, stride 1,
+ * 'valid') -> ReLU -> flatten -> Dense(32) -> ReLU -> Dense(32) -> ReLU, applied to (obs - 128) / 255 (map_env.py:199)
+ * of uint8 observations resident in HBM -- what ssd_step / ssd_rollout wrote -- in one fused tensor-core kernel
+ * (fp16 operands, fp32 accumulation; nothing but the features returns to HBM).  The LSTM cell and the two heads that
+ * follow (conv_to_fcnet_v2.py:68-92) are plain GEMMs on [M, 32] / [M, 128] and are left to the caller's BLAS.
+ *
+ * Weights are HOST fp32 arrays in the Keras layouts: conv_w [3][3][3][6] (kh, kw, in, out), conv_b [6],
+ * fc1_w [1014][32] (inputs flattened (row, col, filter) as keras Flatten does), fc1_b [32], fc2_w [32][32], fc2_b [32].
+ * Only view_radius 7 (15x15 observations, the reference's HARVEST_VIEW_SIZE / CLEANUP_VIEW_SIZE) is built. */
+typedef struct SsdPolicy* ssd_policy_t;
+int ssd_policy_create(int view_radius, int device, const float* conv_w, const float* conv_b, const float* fc1_w, const float* fc1_b,
+                      const float* fc2_w, const float* fc2_b, ssd_policy_t* out);
+/* obs dev u8[num_agents][15][15][3] (16-byte aligned; the [B][N][...] tensor of ssd_step with num_agents = B*N),
+ * features dev f32[num_agents][32] (16-byte aligned). */
+int ssd_policy_features(ssd_policy_t p, const uint8_t* obs, int64_t num_agents, float* features, void* stream);
+void ssd_policy_destroy(ssd_policy_t p);
+
 /* Tuning options.
  * SSD_OPT_CHAIN_STEPS (default 0): when 1, consecutive ssd_step calls on the same stream are launched
  * with programmatic dependent launch: the kernel of step t+1 starts filling SMs while the last CTAs of

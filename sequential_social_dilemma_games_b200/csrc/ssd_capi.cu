@@ -39,6 +39,10 @@ uint64_t threshold53(double p) {
 
 }  // namespace
 
+namespace ssd {
+int set_error(int code, const char* msg) { return fail(code, "%s", msg); }
+}  // namespace ssd
+
 struct SsdEnv {
     SsdConfig cfg{};
     int B = 0, B_pad = 0, E = 0, threads = 128;

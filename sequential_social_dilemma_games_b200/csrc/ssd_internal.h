@@ -203,4 +203,7 @@ inline uint8_t ascii_to_cell(uint8_t ch) {
     }
 }
 
+// records the thread-local message behind ssd_last_error() and returns `code` (ssd_capi.cu)
+int set_error(int code, const char* msg);
+
 }  // namespace ssd

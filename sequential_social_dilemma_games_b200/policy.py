@@ -1,0 +1,117 @@
+"""Policy-side consumer of the observation tensor: the network of the reference's
+models/conv_to_fcnet_v2.py (ConvToFCNetv2) evaluated on uint8 observations that never leave the GPU.
+
+    trunk   Conv2D(6, 3x3, stride 1, 'valid') -> ReLU -> flatten -> Dense(32) -> ReLU -> Dense(32) -> ReLU
+            (conv_to_fcnet_v2.py:36-66, filters as train_baseline.py:104 configures them) -- ONE fused tcgen05 kernel
+            behind the C ABI (`ssd_policy_features`, csrc/ssd_policy.cu) that reads the uint8 [B, N, 15, 15, 3] tensor
+            `BatchedSSDEnv.step` wrote and folds the (x - 128) / 255 of map_env.py:199 into the first layer;
+    head    LSTM(cell_size) -> logits / value (conv_to_fcnet_v2.py:68-92): plain GEMMs on [M, 32] and [M, cell] --
+            torch / cuBLAS calls here, library plumbing.
+
+Weights are numpy fp32 arrays in the Keras layouts (conv kernel [kh, kw, in, out], dense kernels [in, out], LSTM kernel
+[in, 4u] / recurrent kernel [u, 4u] / bias [4u] with gates ordered i, f, c, o), so a checkpoint of the reference model
+loads without transposition.  There is no CPU path: the trunk raises without the CUDA library.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+VIEW_RADIUS = 7
+OBS_SIDE = 2 * VIEW_RADIUS + 1
+CONV_FILTERS = 6
+FEATURES = 32
+FLAT = (OBS_SIDE - 2) * (OBS_SIDE - 2) * CONV_FILTERS   # 1014
+
+
+def random_weights(num_outputs, cell_size=128, seed=0):
+    """Random-init weights of the right shapes (normc for the dense layers as conv_to_fcnet_v2.py:63, glorot elsewhere)."""
+    rng = np.random.RandomState(seed)
+
+    def normc(shape, std=1.0):
+        w = rng.randn(*shape).astype(np.float32)
+        return (w * std / np.sqrt(np.square(w).sum(axis=0, keepdims=True))).astype(np.float32)
+
+    def glorot(shape, fan_in, fan_out):
+        lim = np.sqrt(6.0 / (fan_in + fan_out))
+        return rng.uniform(-lim, lim, size=shape).astype(np.float32)
+
+    u = cell_size
+    return {
+        "conv_w": glorot((3, 3, 3, CONV_FILTERS), 27, 9 * CONV_FILTERS), "conv_b": (0.1 * rng.randn(CONV_FILTERS)).astype(np.float32),
+        "fc1_w": normc((FLAT, FEATURES)), "fc1_b": (0.1 * rng.randn(FEATURES)).astype(np.float32),
+        "fc2_w": normc((FEATURES, FEATURES)), "fc2_b": (0.1 * rng.randn(FEATURES)).astype(np.float32),
+        "lstm_w": glorot((FEATURES, 4 * u), FEATURES, 4 * u), "lstm_u": glorot((u, 4 * u), u, 4 * u),
+        "lstm_b": np.concatenate([np.zeros(u), np.ones(u), np.zeros(2 * u)]).astype(np.float32),   # unit forget bias
+        "logits_w": glorot((u, num_outputs), u, num_outputs), "logits_b": np.zeros(num_outputs, np.float32),
+        "value_w": glorot((u, 1), u, 1), "value_b": np.zeros(1, np.float32),
+    }
+
+
+class ConvToFCNet(object):
+    """Forward pass of ConvToFCNetv2 for a batch of agents; `obs` is the uint8 tensor of the step path."""
+
+    def __init__(self, weights, device="cuda:0"):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.SsdError("the policy trunk runs on a CUDA device only")
+        w = {k: np.ascontiguousarray(v, dtype=np.float32) for k, v in weights.items()}
+        for name, shape in (("conv_w", (3, 3, 3, CONV_FILTERS)), ("conv_b", (CONV_FILTERS,)), ("fc1_w", (FLAT, FEATURES)),
+                            ("fc1_b", (FEATURES,)), ("fc2_w", (FEATURES, FEATURES)), ("fc2_b", (FEATURES,))):
+            if w[name].shape != shape:
+                raise ValueError("%s has shape %s, expected %s" % (name, w[name].shape, shape))
+        self.weights = w
+        self._h = C.c_void_p()
+        ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+        _lib.check(_lib.lib.ssd_policy_create(VIEW_RADIUS, self.device.index or 0, ptr(w["conv_w"]), ptr(w["conv_b"]), ptr(w["fc1_w"]),
+                                              ptr(w["fc1_b"]), ptr(w["fc2_w"]), ptr(w["fc2_b"]), C.byref(self._h)))
+        self.cell_size = w["lstm_u"].shape[0] if "lstm_u" in w else 0
+        self._head = {k: torch.from_numpy(w[k]).to(self.device) for k in
+                      ("lstm_w", "lstm_u", "lstm_b", "logits_w", "logits_b", "value_w", "value_b") if k in w}
+
+    def close(self):
+        if self._h:
+            _lib.lib.ssd_policy_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def features(self, obs, out=None):
+        """uint8 [..., 15, 15, 3] on the device -> float32 [M, 32] (M = product of the leading dims)."""
+        if obs.dtype != torch.uint8 or obs.device != self.device or tuple(obs.shape[-3:]) != (OBS_SIDE, OBS_SIDE, 3):
+            raise ValueError("obs must be a uint8 [..., %d, %d, 3] tensor on %s" % (OBS_SIDE, OBS_SIDE, self.device))
+        obs = obs.contiguous()
+        m = obs.numel() // (OBS_SIDE * OBS_SIDE * 3)
+        if out is None:
+            out = torch.empty((m, FEATURES), dtype=torch.float32, device=self.device)
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        _lib.check(_lib.lib.ssd_policy_features(self._h, C.c_void_p(obs.data_ptr()), m, C.c_void_p(out.data_ptr()), stream))
+        return out
+
+    def initial_state(self, m):
+        z = torch.zeros((m, self.cell_size), dtype=torch.float32, device=self.device)
+        return z, z.clone()
+
+    def forward(self, obs, h, c):
+        """-> (logits [M, A], value [M], h', c'): the trunk kernel, then the LSTM cell and the heads as library GEMMs."""
+        x = self.features(obs)
+        hd = self._head
+        gates = torch.addmm(hd["lstm_b"], x, hd["lstm_w"]).addmm_(h, hd["lstm_u"])
+        i, f, g, o = gates.chunk(4, dim=1)   # Keras gate order
+        c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
+        h = torch.sigmoid(o) * torch.tanh(c)
+        logits = torch.addmm(hd["logits_b"], h, hd["logits_w"])
+        value = torch.addmm(hd["value_b"], h, hd["value_w"]).squeeze(1)
+        return logits, value, h, c
+
+    def act(self, obs, h, c, generator=None):
+        """Sample int8 actions [M] on the device for the next `BatchedSSDEnv.step`."""
+        logits, value, h, c = self.forward(obs, h, c)
+        a = torch.multinomial(torch.softmax(logits, dim=1), 1, generator=generator).squeeze(1).to(torch.int8)
+        return a, value, h, c

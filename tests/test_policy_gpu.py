@@ -1,0 +1,64 @@
+"""The fused policy trunk (csrc/ssd_policy.cu) against a plain PyTorch fp32 reference of the same layers
+(models/conv_to_fcnet_v2.py:36-66 on (obs - 128) / 255).  The kernel multiplies fp16 operands (weights and activations
+rounded to 11 significant bits) and accumulates in fp32, so the comparison is to a stated tolerance, not bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ATOL, RTOL = 2e-2, 2e-2   # fp16 operand rounding through three layers; features are O(1)
+
+
+def _reference_features(w, obs):
+    x = (obs.to(torch.float32) - 128.0) / 255.0                      # map_env.py:199
+    x = x.permute(0, 3, 1, 2)                                         # NHWC -> NCHW
+    k = torch.from_numpy(w["conv_w"]).to(obs.device).permute(3, 2, 0, 1)   # [kh, kw, in, out] -> [out, in, kh, kw]
+    y = torch.relu(torch.nn.functional.conv2d(x, k, torch.from_numpy(w["conv_b"]).to(obs.device)))
+    y = y.permute(0, 2, 3, 1).reshape(obs.shape[0], -1)              # keras Flatten of NHWC
+    y = torch.relu(y @ torch.from_numpy(w["fc1_w"]).to(obs.device) + torch.from_numpy(w["fc1_b"]).to(obs.device))
+    return torch.relu(y @ torch.from_numpy(w["fc2_w"]).to(obs.device) + torch.from_numpy(w["fc2_b"]).to(obs.device))
+
+
+@pytest.mark.parametrize("m", [1, 127, 128, 129, 5 * 1024 + 3])
+def test_trunk_matches_fp32_reference_random_pixels(m):
+    from sequential_social_dilemma_games_b200 import policy
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    w = policy.random_weights(num_outputs=8, seed=3)
+    net = policy.ConvToFCNet(w)
+    g = torch.Generator(device="cuda").manual_seed(m)
+    obs = torch.randint(0, 256, (m, 15, 15, 3), dtype=torch.uint8, device="cuda", generator=g)
+    got = net.features(obs)
+    want = _reference_features(w, obs)
+    torch.cuda.synchronize()
+    assert got.shape == (m, 32)
+    assert torch.isfinite(got).all()
+    err = (got - want).abs().max().item()
+    assert torch.allclose(got, want, atol=ATOL, rtol=RTOL), "max abs err %g (ref max %g)" % (err, want.abs().max().item())
+    assert want.abs().max().item() > 0.1   # the comparison is not vacuous
+
+
+def test_trunk_on_env_observations_and_rollout_loop():
+    """Observations straight from the step kernel; a short closed loop env -> policy -> env with no host round trip."""
+    from sequential_social_dilemma_games_b200 import policy
+    from sequential_social_dilemma_games_b200.batched import BatchedSSDEnv, make_config
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    env = BatchedSSDEnv(make_config("harvest", num_agents=5), 300, seed=5)
+    w = policy.random_weights(num_outputs=8, seed=1)
+    net = policy.ConvToFCNet(w)
+    obs = env.reset()
+    h, c = net.initial_state(300 * 5)
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    for _ in range(6):
+        flat = obs.reshape(-1, 15, 15, 3)
+        got = net.features(flat)
+        want = _reference_features(w, flat)
+        assert torch.allclose(got, want, atol=ATOL, rtol=RTOL), (got - want).abs().max().item()
+        a, value, h, c = net.act(flat, h, c, generator=gen)
+        assert a.dtype == torch.int8 and int(a.min()) >= 0 and int(a.max()) < 8
+        obs, rew = env.step(a.reshape(300, 5))
+    torch.cuda.synchronize()
+    env.close()
+    net.close()
