@@ -22,37 +22,44 @@
 #include <vector>
 
 #include "ssd_internal.h"
+#include "ssd_device.cuh"
 
 namespace ssd {
 namespace policy {
 
 constexpr int V = 15, IMG = V * V * 3, ROWB = V * 3, CO = V - 2, NF = 6, FEAT = 32;
 constexpr int GA = 128;                       // agents per group = UMMA M
-constexpr int K1 = 144, N1 = 80;              // 3 * 45 = 135 taps padded to 9 k-steps; 13 * 6 = 78 columns padded
+constexpr int ROWK = 48;                      // one image row: 45 taps padded to 3 k-steps
+constexpr int N1 = 80;                        // 13 * 6 = 78 conv outputs of one output row, padded
 constexpr int K2 = 80, N2 = FEAT;             // one row block of Dense(32)
 constexpr int K3 = FEAT, N3 = FEAT;
-constexpr int kThreads = 128;
-constexpr int kTmemCols = 256;                // D1 at column 0 (80 used), D2 at 128, D3 at 160
-constexpr int kColD1 = 0, kColD2 = 128, kColD3 = 160;
+constexpr int RING = 4;                       // image-row operand blocks in flight
+constexpr int kProducerWarps = 4, kMmaWarp = 4, kThreads = 288;   // warps 0-3 build operands, warp 4 issues MMAs, warps 5-8 drain
+constexpr int kTmemCols = 256;
+constexpr int kColD1a = 0, kColD2 = 96, kColD1b = 128, kColD3 = 224;
 
 // shared-memory carve-up (bytes)
-constexpr int kObsBytes = GA * IMG;                       // 86 400, a multiple of 16
-constexpr int kOffObs = 0;
-constexpr int kOffA = 86528;                              // obs + slack for the padded taps of the last agent
-constexpr int kABytes = (K1 / 8) * GA * 16;               // 36 864; also holds C (20 480) and the fc2 operand (8 192)
-constexpr int kOffW = kOffA + kABytes;                    // the packed weights, in the order of the blob
-constexpr int kB1Bytes = (K1 / 8) * N1 * 16;              // 23 040
-constexpr int kB2Bytes = (K2 / 8) * N2 * 16;              // 5 120 per row block
+constexpr int kRowBytes = (ROWK / 8) * GA * 16;           // 12 288 per image-row block
+constexpr int kCBytes = (K2 / 8) * GA * 16;               // 20 480
+constexpr int kX3Bytes = (K3 / 8) * GA * 16;              // 8 192
+constexpr int kB1Bytes = (3 * ROWK / 8) * N1 * 16;        // 23 040
+constexpr int kB2Bytes = (K2 / 8) * N2 * 16;              // 5 120 per row block of Dense(32)
 constexpr int kB3Bytes = (K3 / 8) * N3 * 16;              // 2 048
 constexpr int kConstFloats = N1 + N2 + N3;                // cb[80], b1[32], b2[32]
-constexpr int kBlobBytes = kB1Bytes + CO * kB2Bytes + kB3Bytes + kConstFloats * 4;   // 92 224
-constexpr int kOffB1 = kOffW, kOffB2 = kOffB1 + kB1Bytes, kOffB3 = kOffB2 + CO * kB2Bytes, kOffConst = kOffB3 + kB3Bytes;
-constexpr int kOffBar = kOffW + ((kBlobBytes + 15) & ~15);
-constexpr int kSmemBytes = kOffBar + 16;
-static_assert(kBlobBytes % 16 == 0 && kOffA % 128 == 0 && kOffW % 128 == 0, "operand tiles must be 16-byte aligned");
+constexpr int kHeadBytes = kB1Bytes + kB3Bytes + kConstFloats * 4;   // resident part of the blob: 25 664
+constexpr int kBlobBytes = kHeadBytes + CO * kB2Bytes;    // + the 13 row blocks of Dense(32), streamed: 92 224
+constexpr int kOffObs = 0;                                // 128 * 675 = 86 400 + slack for the padded taps of the last agent
+constexpr int kOffRing = 86528;
+constexpr int kOffC = kOffRing + RING * kRowBytes;
+constexpr int kOffX3 = kOffC + 2 * kCBytes;
+constexpr int kOffB1 = kOffX3 + kX3Bytes, kOffB3 = kOffB1 + kB1Bytes, kOffConst = kOffB3 + kB3Bytes;
+constexpr int kOffW1 = kOffB1 + kHeadBytes;
+constexpr int kOffBar = kOffW1 + 2 * kB2Bytes;
+enum { BAR_OBS = 0, BAR_ROW_FULL = 1, BAR_ROW_FREE = 5, BAR_D1_FULL = 9, BAR_D1_FREE = 11, BAR_C_FULL = 13, BAR_C_FREE = 15, BAR_D2 = 17, BAR_X3 = 18,
+       BAR_D3 = 19, BAR_COUNT = 20 };
+constexpr int kSmemBytes = kOffBar + BAR_COUNT * 8;
+static_assert(kHeadBytes % 16 == 0 && kOffRing % 128 == 0 && kOffB1 % 128 == 0 && kOffW1 % 16 == 0 && kOffBar % 8 == 0, "alignment");
 static_assert(kSmemBytes <= 227 * 1024, "one CTA per SM");
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
 // UMMA shared-memory descriptor, K-major, no swizzle: LBO = distance of the two 8-element k-halves of one MMA,
 // SBO = distance of consecutive 8-row groups; version 1 (sm_100) in bits 46-47.
@@ -70,182 +77,246 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {  // arrives on `bar` when every MMA issued so far has completed
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done = 0;
-    while (!done) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-    }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// 16 consecutive accumulator columns of this thread's row (TMEM lane = 32 * (warp % 4) + lane)
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-    uint32_t r[16];
+// 16 consecutive accumulator columns of this thread's row (TMEM lane = 32 * (warp % 4) + lane); no wait
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
     asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
-        "tcgen05.wait::ld.sync.aligned;"
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
           "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr)
         : "memory");
-#pragma unroll
-    for (int q = 0; q < 16; ++q) v[q] = __uint_as_float(r[q]);
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint32_t pack_relu_h2(float a, float b) {
     const __half2 h = __floats2half2_rn(fmaxf(a, 0.f), fmaxf(b, 0.f));
     return *reinterpret_cast<const uint32_t*>(&h);
 }
 
+// Three roles, each looping over the same groups g = blockIdx.x, blockIdx.x + gridDim.x, ...:
+//   producers (warps 0-3, thread = agent): image row r of the group -> operand block ring[R % 4] (R counts rows over all
+//       groups of the CTA); thread 0 also streams the Dense(32) row block of output row r - 2 and the next group's bytes;
+//   MMA thread (warp 4): conv(i) = 9 MMAs over ring blocks i..i+2 into D1[T % 2] (T counts output rows), then the
+//       Dense(32) partial of output row i - 1 while the drain warps convert row i;
+//   drain warps (5-8, thread = accumulator row): D1 -> relu -> fp16 -> C[T % 2]; at the end of a group D2 -> fc2 operand,
+//       D3 -> features in HBM.
+// Barrier parities: the n-th use of a full barrier waits parity n & 1; the n-th reuse of a slot waits its free barrier on
+// parity (n & 1) ^ 1 (passes at once for n = 0).
 __global__ void __launch_bounds__(kThreads, 1) policy_features_kernel(const uint8_t* __restrict__ obs, long long M, const uint8_t* __restrict__ blob,
                                                                      float* __restrict__ out) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint32_t s_tmem;
-    const int t = threadIdx.x, warp = t >> 5;
-    const uint32_t sA = smem_u32(smem + kOffA), sB1 = smem_u32(smem + kOffB1), sB2 = smem_u32(smem + kOffB2), sB3 = smem_u32(smem + kOffB3);
-    const uint32_t bar = smem_u32(smem + kOffBar);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
     const float* s_const = reinterpret_cast<const float*>(smem + kOffConst);
+    const long long n_groups = (M + GA - 1) / GA;
 
-    if (warp == 0) {  // tensor memory for the three accumulators
+    if (tid == 0) {
+        for (int b = 0; b < BAR_COUNT; ++b) {
+            const bool by_warps = (b >= BAR_ROW_FULL && b < BAR_ROW_FREE) || (b >= BAR_D1_FREE && b < BAR_C_FREE) || b == BAR_X3;
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bars + b)), "r"(by_warps ? 4 : 1) : "memory");
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kMmaWarp) {  // tensor memory for the accumulators
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (t == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    for (int i = t; i < kBlobBytes / 16; i += kThreads)  // packed weights: once per CTA (the grid is persistent)
-        reinterpret_cast<uint4*>(smem + kOffW)[i] = reinterpret_cast<const uint4*>(blob)[i];
+    for (int i = tid; i < kHeadBytes / 16; i += kThreads)  // conv and fc2 weights, constants: once per CTA (the grid is persistent)
+        reinterpret_cast<uint4*>(smem + kOffB1)[i] = reinterpret_cast<const uint4*>(blob)[i];
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = s_tmem;
-    const uint32_t trow = tmem + (static_cast<uint32_t>(warp * 32) << 16);  // this warp's quarter of the 128 lanes
-    uint32_t parity = 0;
-    constexpr uint32_t kI1 = umma_idesc(GA, N1), kI2 = umma_idesc(GA, N2), kI3 = umma_idesc(GA, N3);
 
-    const long long n_groups = (M + GA - 1) / GA;
-    for (long long g = blockIdx.x; g < n_groups; g += gridDim.x) {
-        const long long a0 = g * GA;
-        const int rem = static_cast<int>(M - a0 < GA ? M - a0 : GA);
-        {   // the group's observations: rem * 675 contiguous bytes (the group starts 16-byte aligned: 128 * 675 = 5400 * 16)
+    if (warp < kProducerWarps) {
+        // ------------------------------------------------------------------ producers
+        const int t = tid;
+        auto load_obs = [&](long long g) {  // thread 0: the group's rem * 675 contiguous bytes (a group starts 16-byte aligned)
+            const long long a0 = g * GA;
+            const int rem = static_cast<int>(M - a0 < GA ? M - a0 : GA);
             const uint8_t* src = obs + a0 * IMG;
-            const int bytes = rem * IMG, vec = bytes >> 4;
-            for (int i = t; i < vec; i += kThreads) reinterpret_cast<uint4*>(smem + kOffObs)[i] = __ldg(reinterpret_cast<const uint4*>(src) + i);
-            for (int i = (vec << 4) + t; i < bytes; i += kThreads) smem[kOffObs + i] = src[i];
-        }
-        __syncthreads();
-
+            const uint32_t bytes = static_cast<uint32_t>(rem) * IMG, b16 = bytes & ~15u;
+            for (uint32_t i = b16; i < bytes; ++i) smem[kOffObs + i] = src[i];
+            mbar_expect_tx(bars + BAR_OBS, b16);
+            bulk_g2s(smem + kOffObs, src, b16, bars + BAR_OBS);
+        };
+        if (t == 0 && blockIdx.x < n_groups) load_obs(blockIdx.x);
+        uint32_t R = 0, T = 0, gi = 0;
+        for (long long g = blockIdx.x; g < n_groups; g += gridDim.x, ++gi) {
+            mbar_wait(bars + BAR_OBS, gi & 1);
 #pragma unroll 1
-        for (int i = 0; i < CO; ++i) {
-            {   // A1: this agent's 144-byte window as fp16(1024 + byte), eight taps per 16-byte store
-                const int base = t * IMG + i * ROWB;
-                const uint32_t* w = reinterpret_cast<const uint32_t*>(smem + kOffObs + (base & ~3));
-                const uint32_t sh = static_cast<uint32_t>(base & 3) * 8;
-                uint4* dst = reinterpret_cast<uint4*>(smem + kOffA + t * 16);
-                uint32_t w0 = w[0];
+            for (int r = 0; r < V; ++r, ++R) {
+                const uint32_t slot = R & (RING - 1);
+                mbar_wait(bars + BAR_ROW_FREE + slot, ((R >> 2) & 1) ^ 1);
+                {   // fp16(1024 + byte) of this agent's 48-byte window, eight taps per 16-byte store
+                    const int base = t * IMG + r * ROWB;
+                    const uint32_t* w = reinterpret_cast<const uint32_t*>(smem + kOffObs + (base & ~3));
+                    const uint32_t sh = static_cast<uint32_t>(base & 3) * 8;
+                    uint4* dst = reinterpret_cast<uint4*>(smem + kOffRing + slot * kRowBytes + t * 16);
+                    uint32_t x[ROWK / 4 + 1];
 #pragma unroll
-                for (int kc = 0; kc < K1 / 8; ++kc) {
-                    const uint32_t w1 = w[2 * kc + 1], w2 = w[2 * kc + 2];
-                    const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
-                    dst[kc * GA] = make_uint4(__byte_perm(lo, 0x64646464u, 0x4140), __byte_perm(lo, 0x64646464u, 0x4342),
-                                              __byte_perm(hi, 0x64646464u, 0x4140), __byte_perm(hi, 0x64646464u, 0x4342));
-                    w0 = w2;
+                    for (int q = 0; q <= ROWK / 4; ++q) x[q] = w[q];
+#pragma unroll
+                    for (int kc = 0; kc < ROWK / 8; ++kc) {
+                        const uint32_t lo = __funnelshift_r(x[2 * kc], x[2 * kc + 1], sh), hi = __funnelshift_r(x[2 * kc + 1], x[2 * kc + 2], sh);
+                        dst[kc * GA] = make_uint4(__byte_perm(lo, 0x64646464u, 0x4140), __byte_perm(lo, 0x64646464u, 0x4342),
+                                                  __byte_perm(hi, 0x64646464u, 0x4140), __byte_perm(hi, 0x64646464u, 0x4342));
+                    }
+                }
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    if (warp == 0 && r >= 2) {  // the Dense(32) row block of output row r - 2 rides on the same barrier
+                        const uint32_t Tt = T + (r - 2), b = Tt & 1;
+                        mbar_wait(bars + BAR_C_FREE + b, ((Tt >> 1) & 1) ^ 1);  // its buffer: read last by the partial of row Tt - 2
+                        mbar_expect_tx(bars + BAR_ROW_FULL + slot, kB2Bytes);
+                        bulk_g2s(smem + kOffW1 + b * kB2Bytes, blob + kHeadBytes + (r - 2) * kB2Bytes, kB2Bytes, bars + BAR_ROW_FULL + slot);
+                    } else {
+                        mbar_arrive(bars + BAR_ROW_FULL + slot);
+                    }
                 }
             }
-            fence_async_smem();
-            tc_fence_before();
-            __syncthreads();
-            if (t == 0) {
-                tc_fence_after();
-#pragma unroll
-                for (int ks = 0; ks < K1 / 16; ++ks)
-                    umma_f16(tmem + kColD1, umma_desc(sA + ks * 2 * GA * 16, GA * 16, 128), umma_desc(sB1 + ks * 2 * N1 * 16, N1 * 16, 128), kI1, ks > 0);
-                umma_commit(bar);
-            }
-            bar_wait(bar, parity);
-            parity ^= 1;
-            tc_fence_after();
-            {   // C = fp16(relu(D1 / 255 + cb)) into the (now free) operand buffer, as the K-major A operand of Dense(32)
-                uint4* dst = reinterpret_cast<uint4*>(smem + kOffA + t * 16);
-#pragma unroll
-                for (int c0 = 0; c0 < N1; c0 += 16) {
-                    float v[16];
-                    tmem_ld16(trow + kColD1 + c0, v);
-#pragma unroll
-                    for (int q = 0; q < 16; ++q) v[q] = v[q] * (1.0f / 255.0f) + s_const[c0 + q];
-                    dst[(c0 / 8) * GA] = make_uint4(pack_relu_h2(v[0], v[1]), pack_relu_h2(v[2], v[3]), pack_relu_h2(v[4], v[5]), pack_relu_h2(v[6], v[7]));
-                    dst[(c0 / 8 + 1) * GA] = make_uint4(pack_relu_h2(v[8], v[9]), pack_relu_h2(v[10], v[11]), pack_relu_h2(v[12], v[13]), pack_relu_h2(v[14], v[15]));
-                }
-            }
-            fence_async_smem();
-            tc_fence_before();
-            __syncthreads();
-            if (t == 0) {
+            T += CO;
+            asm volatile("bar.sync 1, 128;" ::: "memory");  // every producer is done with the observation bytes
+            if (t == 0 && g + gridDim.x < n_groups) load_obs(g + gridDim.x);
+        }
+    } else if (warp == kMmaWarp) {
+        // ------------------------------------------------------------------ MMA issue (one thread)
+        if (lane == 0) {
+            constexpr uint32_t kI1 = umma_idesc(GA, N1), kI2 = umma_idesc(GA, N2), kI3 = umma_idesc(GA, N3);
+            const uint32_t sRing = smem_u32(smem + kOffRing), sC = smem_u32(smem + kOffC), sX3 = smem_u32(smem + kOffX3);
+            const uint32_t sB1 = smem_u32(smem + kOffB1), sB3 = smem_u32(smem + kOffB3), sW1 = smem_u32(smem + kOffW1);
+            uint32_t rows_seen = 0, T = 0, gi = 0;
+            auto dense_partial = [&](uint32_t Tp, int i_local) {  // D2 (+)= C[Tp % 2] * W1 block
+                const uint32_t b = Tp & 1;
+                mbar_wait(bars + BAR_C_FULL + b, (Tp >> 1) & 1);
                 tc_fence_after();
 #pragma unroll
                 for (int ks = 0; ks < K2 / 16; ++ks)
-                    umma_f16(tmem + kColD2, umma_desc(sA + ks * 2 * GA * 16, GA * 16, 128),
-                             umma_desc(sB2 + i * kB2Bytes + ks * 2 * N2 * 16, N2 * 16, 128), kI2, (i | ks) != 0);
-                umma_commit(bar);
+                    umma_f16(tmem + kColD2, umma_desc(sC + b * kCBytes + ks * 2 * GA * 16, GA * 16, 128),
+                             umma_desc(sW1 + b * kB2Bytes + ks * 2 * N2 * 16, N2 * 16, 128), kI2, (i_local | ks) != 0);
+                umma_commit(bars + BAR_C_FREE + b);
+            };
+            for (long long g = blockIdx.x; g < n_groups; g += gridDim.x, ++gi) {
+                const uint32_t R0 = gi * V;
+#pragma unroll 1
+                for (int i = 0; i < CO; ++i, ++T) {
+                    while (rows_seen < R0 + i + 3) {
+                        mbar_wait(bars + BAR_ROW_FULL + (rows_seen & (RING - 1)), (rows_seen >> 2) & 1);
+                        ++rows_seen;
+                    }
+                    const uint32_t b = T & 1;
+                    mbar_wait(bars + BAR_D1_FREE + b, ((T >> 1) & 1) ^ 1);
+                    tc_fence_after();
+#pragma unroll
+                    for (int di = 0; di < 3; ++di)
+#pragma unroll
+                        for (int ks = 0; ks < ROWK / 16; ++ks)
+                            umma_f16(tmem + (b ? kColD1b : kColD1a),
+                                     umma_desc(sRing + ((R0 + i + di) & (RING - 1)) * kRowBytes + ks * 2 * GA * 16, GA * 16, 128),
+                                     umma_desc(sB1 + (di * (ROWK / 16) + ks) * 2 * N1 * 16, N1 * 16, 128), kI1, (di | ks) != 0);
+                    umma_commit(bars + BAR_D1_FULL + b);
+                    umma_commit(bars + BAR_ROW_FREE + ((R0 + i) & (RING - 1)));  // image row i is not needed again
+                    if (i == CO - 1) {
+                        umma_commit(bars + BAR_ROW_FREE + ((R0 + i + 1) & (RING - 1)));
+                        umma_commit(bars + BAR_ROW_FREE + ((R0 + i + 2) & (RING - 1)));
+                    }
+                    if (i >= 1) dense_partial(T - 1, i - 1);
+                }
+                dense_partial(T - 1, CO - 1);
+                umma_commit(bars + BAR_D2);
+                mbar_wait(bars + BAR_X3, gi & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int ks = 0; ks < K3 / 16; ++ks)
+                    umma_f16(tmem + kColD3, umma_desc(sX3 + ks * 2 * GA * 16, GA * 16, 128), umma_desc(sB3 + ks * 2 * N3 * 16, N3 * 16, 128), kI3, ks > 0);
+                umma_commit(bars + BAR_D3);
             }
-            bar_wait(bar, parity);  // C is consumed: the buffer can take the next window
-            parity ^= 1;
         }
-        tc_fence_after();
-        {   // fc2 operand = fp16(relu(D2 + b1))
-            uint4* dst = reinterpret_cast<uint4*>(smem + kOffA + t * 16);
+    } else {
+        // ------------------------------------------------------------------ drain warps: thread = accumulator row = agent
+        const int q = warp & 3, row = q * 32 + lane;
+        const uint32_t trow = tmem + (static_cast<uint32_t>(q * 32) << 16);
+        uint32_t T = 0, gi = 0;
+        for (long long g = blockIdx.x; g < n_groups; g += gridDim.x, ++gi) {
+            const long long a0 = g * GA;
+            const int rem = static_cast<int>(M - a0 < GA ? M - a0 : GA);
+#pragma unroll 1
+            for (int i = 0; i < CO; ++i, ++T) {
+                const uint32_t b = T & 1;
+                mbar_wait(bars + BAR_D1_FULL + b, (T >> 1) & 1);
+                tc_fence_after();
+                uint32_t acc[N1];
 #pragma unroll
-            for (int c0 = 0; c0 < N2; c0 += 16) {
-                float v[16];
-                tmem_ld16(trow + kColD2 + c0, v);
+                for (int c0 = 0; c0 < N1; c0 += 16) tmem_ld16(trow + (b ? kColD1b : kColD1a) + c0, acc + c0);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bars + BAR_D1_FREE + b);
+                uint32_t h[N1 / 2];   // C = fp16(relu(D1 / 255 + cb))
 #pragma unroll
-                for (int q = 0; q < 16; ++q) v[q] += s_const[N1 + c0 + q];
-                dst[(c0 / 8) * GA] = make_uint4(pack_relu_h2(v[0], v[1]), pack_relu_h2(v[2], v[3]), pack_relu_h2(v[4], v[5]), pack_relu_h2(v[6], v[7]));
-                dst[(c0 / 8 + 1) * GA] = make_uint4(pack_relu_h2(v[8], v[9]), pack_relu_h2(v[10], v[11]), pack_relu_h2(v[12], v[13]), pack_relu_h2(v[14], v[15]));
+                for (int c = 0; c < N1; c += 2)
+                    h[c / 2] = pack_relu_h2(__uint_as_float(acc[c]) * (1.0f / 255.0f) + s_const[c], __uint_as_float(acc[c + 1]) * (1.0f / 255.0f) + s_const[c + 1]);
+                mbar_wait(bars + BAR_C_FREE + b, ((T >> 1) & 1) ^ 1);
+                uint4* dst = reinterpret_cast<uint4*>(smem + kOffC + b * kCBytes + row * 16);
+#pragma unroll
+                for (int kc = 0; kc < K2 / 8; ++kc) dst[kc * GA] = make_uint4(h[4 * kc], h[4 * kc + 1], h[4 * kc + 2], h[4 * kc + 3]);
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bars + BAR_C_FULL + b);
             }
-        }
-        fence_async_smem();
-        tc_fence_before();
-        __syncthreads();
-        if (t == 0) {
-            tc_fence_after();
+            {   // fc2 operand = fp16(relu(D2 + b1))
+                mbar_wait(bars + BAR_D2, gi & 1);
+                tc_fence_after();
+                uint32_t acc[N2];
+                tmem_ld16(trow + kColD2, acc);
+                tmem_ld16(trow + kColD2 + 16, acc + 16);
+                tmem_ld_wait();
+                uint4* dst = reinterpret_cast<uint4*>(smem + kOffX3 + row * 16);
 #pragma unroll
-            for (int ks = 0; ks < K3 / 16; ++ks)
-                umma_f16(tmem + kColD3, umma_desc(sA + ks * 2 * GA * 16, GA * 16, 128), umma_desc(sB3 + ks * 2 * N3 * 16, N3 * 16, 128), kI3, ks > 0);
-            umma_commit(bar);
-        }
-        bar_wait(bar, parity);
-        parity ^= 1;
-        tc_fence_after();
-        {   // features = relu(D3 + b2), one 128-byte row per agent
-            float4* dst = reinterpret_cast<float4*>(out + (a0 + t) * FEAT);
+                for (int kc = 0; kc < K3 / 8; ++kc) {
+                    uint32_t h[4];
 #pragma unroll
-            for (int c0 = 0; c0 < N3; c0 += 16) {
-                float v[16];
-                tmem_ld16(trow + kColD3 + c0, v);
+                    for (int e = 0; e < 4; ++e)
+                        h[e] = pack_relu_h2(__uint_as_float(acc[8 * kc + 2 * e]) + s_const[N1 + 8 * kc + 2 * e],
+                                            __uint_as_float(acc[8 * kc + 2 * e + 1]) + s_const[N1 + 8 * kc + 2 * e + 1]);
+                    dst[kc * GA] = make_uint4(h[0], h[1], h[2], h[3]);
+                }
+                fence_async_smem();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bars + BAR_X3);
+            }
+            {   // features = relu(D3 + b2), one 128-byte row per agent
+                mbar_wait(bars + BAR_D3, gi & 1);
+                tc_fence_after();
+                uint32_t acc[N3];
+                tmem_ld16(trow + kColD3, acc);
+                tmem_ld16(trow + kColD3 + 16, acc + 16);
+                tmem_ld_wait();
+                tc_fence_before();
+                if (row < rem) {
+                    float4* dst = reinterpret_cast<float4*>(out + (a0 + row) * FEAT);
 #pragma unroll
-                for (int q = 0; q < 16; ++q) v[q] = fmaxf(v[q] + s_const[N1 + N2 + c0 + q], 0.f);
-                if (t < rem) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) dst[c0 / 4 + q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    for (int c = 0; c < N3; c += 4)
+                        dst[c / 4] = make_float4(fmaxf(__uint_as_float(acc[c]) + s_const[N1 + N2 + c], 0.f), fmaxf(__uint_as_float(acc[c + 1]) + s_const[N1 + N2 + c + 1], 0.f),
+                                                 fmaxf(__uint_as_float(acc[c + 2]) + s_const[N1 + N2 + c + 2], 0.f), fmaxf(__uint_as_float(acc[c + 3]) + s_const[N1 + N2 + c + 3], 0.f));
                 }
             }
         }
-        tc_fence_before();
-        __syncthreads();  // the observation buffer and the accumulators are free for the next group
-        tc_fence_after();
     }
+    tc_fence_before();
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+    if (warp == kMmaWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
 }
 
 }  // namespace policy
@@ -268,12 +339,12 @@ int ssd_policy_create(int view_radius, int device, const float* conv_w, const fl
     if (!conv_w || !conv_b || !fc1_w || !fc1_b || !fc2_w || !fc2_b) return ssd::set_error(SSD_ERR_INVALID, "null weight pointer");
     if (2 * view_radius + 1 != V) return ssd::set_error(SSD_ERR_UNSUPPORTED, "the feature kernel is built for 15x15 observations (view radius 7)");
     std::vector<uint8_t> blob(kBlobBytes, 0);
-    __half* b1 = reinterpret_cast<__half*>(blob.data());
-    __half* b2 = reinterpret_cast<__half*>(blob.data() + kB1Bytes);
-    __half* b3 = reinterpret_cast<__half*>(blob.data() + kB1Bytes + CO * kB2Bytes);
-    float* cst = reinterpret_cast<float*>(blob.data() + kB1Bytes + CO * kB2Bytes + kB3Bytes);
+    __half* b1 = reinterpret_cast<__half*>(blob.data());                          // resident: conv, fc2, constants
+    __half* b3 = reinterpret_cast<__half*>(blob.data() + kB1Bytes);
+    float* cst = reinterpret_cast<float*>(blob.data() + kB1Bytes + kB3Bytes);
+    __half* b2 = reinterpret_cast<__half*>(blob.data() + kHeadBytes);             // streamed: the 13 row blocks of Dense(32)
     auto at = [](int rows, int n, int k) { return ((k >> 3) * rows + n) * 8 + (k & 7); };  // canonical K-major, no swizzle
-    // banded conv weights: conv_w[di][dj][c][f] (Keras kernel layout) at tap k = 45 di + 3 (j + dj) + c of column n = 6 j + f
+    // banded conv weights: conv_w[di][dj][c][f] (Keras kernel layout) at tap k = 48 di + 3 (j + dj) + c of column n = 6 j + f
     for (int j = 0; j < CO; ++j)
         for (int f = 0; f < NF; ++f) {
             double sum16 = 0.0;
@@ -281,7 +352,7 @@ int ssd_policy_create(int view_radius, int device, const float* conv_w, const fl
                 for (int dj = 0; dj < 3; ++dj)
                     for (int c = 0; c < 3; ++c) {
                         const __half h = __float2half_rn(conv_w[((di * 3 + dj) * 3 + c) * NF + f]);
-                        b1[at(N1, j * NF + f, di * ROWB + (j + dj) * 3 + c)] = h;
+                        b1[at(N1, j * NF + f, di * ROWK + (j + dj) * 3 + c)] = h;
                         sum16 += static_cast<double>(__half2float(h));
                     }
             // relu(conv((x - 128) / 255) + b) with the operand holding 1024 + x
