@@ -24,5 +24,18 @@ int main(int argc, char** argv) {
     cudaEventRecord(e1); cudaEventSynchronize(e1);
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     printf("M=%lld  %.4f ms per call  (%s)\n", M, ms / 20, cudaGetErrorString(cudaGetLastError()));
+#ifdef SSD_POLICY_TIMING
+    unsigned long long c[3][8];
+    cudaMemcpyFromSymbol(c, g_policy_cycles, sizeof c);
+    const char* names[3][8] = {{"wait obs", "wait row_free", "build row", "arrive / W1 issue", "group end", "", "", ""},
+                               {"wait row_full", "wait d1_free", "issue conv", "wait c_full", "issue dense", "wait x3", "issue fc2", ""},
+                               {"wait d1_full", "tmem ld", "convert", "wait c_free", "store C", "group tail", "", ""}};
+    const char* roles[3] = {"producer thread 0", "MMA thread", "drain thread 160"};
+    for (int r = 0; r < 3; ++r) {
+        unsigned long long tot = 0; for (int i = 0; i < 8; ++i) tot += c[r][i];
+        printf("%s: %llu cycles\n", roles[r], tot);
+        for (int i = 0; i < 8; ++i) if (names[r][i][0]) printf("    %-20s %10llu  %5.1f %%\n", names[r][i], c[r][i], 100.0 * c[r][i] / tot);
+    }
+#endif
     return 0;
 }

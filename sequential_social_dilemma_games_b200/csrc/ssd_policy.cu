@@ -24,6 +24,17 @@
 #include "ssd_internal.h"
 #include "ssd_device.cuh"
 
+#ifdef SSD_POLICY_TIMING  // profiles/micro/policy_timing.cu: cycles per phase of one thread per role of CTA 0
+__device__ unsigned long long g_policy_cycles[3][8];
+#define SSD_PT_DECL unsigned long long pt_[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long pt_t = clock64()
+#define SSD_PT(slot) do { const long long n_ = clock64(); pt_[slot] += n_ - pt_t; pt_t = n_; } while (0)
+#define SSD_PT_FLUSH(role) do { if (blockIdx.x == 0) for (int q_ = 0; q_ < 8; ++q_) g_policy_cycles[role][q_] = pt_[q_]; } while (0)
+#else
+#define SSD_PT_DECL
+#define SSD_PT(slot)
+#define SSD_PT_FLUSH(role)
+#endif
+
 namespace ssd {
 namespace policy {
 
@@ -33,15 +44,16 @@ constexpr int ROWK = 48;                      // one image row: 45 taps padded t
 constexpr int N1 = 80;                        // 13 * 6 = 78 conv outputs of one output row, padded
 constexpr int K2 = 80, N2 = FEAT;             // one row block of Dense(32)
 constexpr int K3 = FEAT, N3 = FEAT;
-constexpr int RING = 4;                       // image-row operand blocks in flight
+constexpr int RING = 4;                       // image-row operand blocks (and Dense weight blocks) in flight
 constexpr int kProducerWarps = 4, kMmaWarp = 4, kThreads = 288;   // warps 0-3 build operands, warp 4 issues MMAs, warps 5-8 drain
-constexpr int kTmemCols = 256;
-constexpr int kColD1a = 0, kColD2 = 96, kColD1b = 128, kColD3 = 224;
+// tensor memory (512 columns x 128 lanes x 32 bit): accumulators, and the A operands -- a lane is an agent, a column two fp16
+constexpr int kTmemCols = 512;
+constexpr int kColD1a = 0, kColD2 = 96, kColD1b = 128, kColD3 = 224;   // fp32 accumulators
+constexpr int kColRing = 256;                 // + 32 * slot: one image row, 24 columns
+constexpr int kColC = 384;                    // + 64 * buffer: relu(conv) of one output row, 40 columns
+constexpr int kColX3 = 496;                   // fc2 operand, 16 columns
 
-// shared-memory carve-up (bytes)
-constexpr int kRowBytes = (ROWK / 8) * GA * 16;           // 12 288 per image-row block
-constexpr int kCBytes = (K2 / 8) * GA * 16;               // 20 480
-constexpr int kX3Bytes = (K3 / 8) * GA * 16;              // 8 192
+// shared-memory carve-up (bytes): the group's observation bytes and the B operands
 constexpr int kB1Bytes = (3 * ROWK / 8) * N1 * 16;        // 23 040
 constexpr int kB2Bytes = (K2 / 8) * N2 * 16;              // 5 120 per row block of Dense(32)
 constexpr int kB3Bytes = (K3 / 8) * N3 * 16;              // 2 048
@@ -49,16 +61,13 @@ constexpr int kConstFloats = N1 + N2 + N3;                // cb[80], b1[32], b2[
 constexpr int kHeadBytes = kB1Bytes + kB3Bytes + kConstFloats * 4;   // resident part of the blob: 25 664
 constexpr int kBlobBytes = kHeadBytes + CO * kB2Bytes;    // + the 13 row blocks of Dense(32), streamed: 92 224
 constexpr int kOffObs = 0;                                // 128 * 675 = 86 400 + slack for the padded taps of the last agent
-constexpr int kOffRing = 86528;
-constexpr int kOffC = kOffRing + RING * kRowBytes;
-constexpr int kOffX3 = kOffC + 2 * kCBytes;
-constexpr int kOffB1 = kOffX3 + kX3Bytes, kOffB3 = kOffB1 + kB1Bytes, kOffConst = kOffB3 + kB3Bytes;
+constexpr int kOffB1 = 86528, kOffB3 = kOffB1 + kB1Bytes, kOffConst = kOffB3 + kB3Bytes;
 constexpr int kOffW1 = kOffB1 + kHeadBytes;
-constexpr int kOffBar = kOffW1 + 2 * kB2Bytes;
-enum { BAR_OBS = 0, BAR_ROW_FULL = 1, BAR_ROW_FREE = 5, BAR_D1_FULL = 9, BAR_D1_FREE = 11, BAR_C_FULL = 13, BAR_C_FREE = 15, BAR_D2 = 17, BAR_X3 = 18,
-       BAR_D3 = 19, BAR_COUNT = 20 };
+constexpr int kOffBar = kOffW1 + RING * kB2Bytes;
+enum { BAR_OBS = 0, BAR_ROW_FULL = 1, BAR_ROW_FREE = 5, BAR_D1_FULL = 9, BAR_D1_FREE = 11, BAR_C_FULL = 13, BAR_C_FREE = 15, BAR_W1_FREE = 17,
+       BAR_D2 = 21, BAR_X3 = 22, BAR_D3 = 23, BAR_COUNT = 24 };
 constexpr int kSmemBytes = kOffBar + BAR_COUNT * 8;
-static_assert(kHeadBytes % 16 == 0 && kOffRing % 128 == 0 && kOffB1 % 128 == 0 && kOffW1 % 16 == 0 && kOffBar % 8 == 0, "alignment");
+static_assert(kHeadBytes % 16 == 0 && kOffB1 % 128 == 0 && kOffW1 % 16 == 0 && kOffBar % 8 == 0, "alignment");
 static_assert(kSmemBytes <= 227 * 1024, "one CTA per SM");
 
 // UMMA shared-memory descriptor, K-major, no swizzle: LBO = distance of the two 8-element k-halves of one MMA,
@@ -71,10 +80,11 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint
 __host__ __device__ constexpr uint32_t umma_idesc(int m, int n) {
     return 1u << 4 | static_cast<uint32_t>(n >> 3) << 17 | static_cast<uint32_t>(m >> 4) << 24;
 }
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[tmem] * B[smem]: 128 x N x 16, A = eight columns of the 128 lanes
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {  // arrives on `bar` when every MMA issued so far has completed
@@ -85,7 +95,7 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// 16 consecutive accumulator columns of this thread's row (TMEM lane = 32 * (warp % 4) + lane); no wait
+// 16 consecutive columns of this thread's lane (TMEM lane = 32 * (warp % 4) + lane); no wait
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -95,18 +105,27 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ uint32_t pack_relu_h2(float a, float b) {
-    const __half2 h = __floats2half2_rn(fmaxf(a, 0.f), fmaxf(b, 0.f));
-    return *reinterpret_cast<const uint32_t*>(&h);
+// 8 consecutive columns of this thread's lane
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
+                 "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t pack_relu_h2(float lo, float hi) {  // {fp16(max(lo, 0)), fp16(max(hi, 0))}, lo in the low half
+    uint32_t d;
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
 }
 
 // Three roles, each looping over the same groups g = blockIdx.x, blockIdx.x + gridDim.x, ...:
-//   producers (warps 0-3, thread = agent): image row r of the group -> operand block ring[R % 4] (R counts rows over all
-//       groups of the CTA); thread 0 also streams the Dense(32) row block of output row r - 2 and the next group's bytes;
+//   producers (warps 0-3, thread = agent = TMEM lane): image row r of the group -> fp16(1024 + byte) in ring block R % 4 of
+//       tensor memory (R counts rows over all groups of the CTA); thread 0 also streams the Dense(32) weight block of output
+//       row r - 2 into shared memory and, at the end of a group, the next group's observation bytes;
 //   MMA thread (warp 4): conv(i) = 9 MMAs over ring blocks i..i+2 into D1[T % 2] (T counts output rows), then the
 //       Dense(32) partial of output row i - 1 while the drain warps convert row i;
-//   drain warps (5-8, thread = accumulator row): D1 -> relu -> fp16 -> C[T % 2]; at the end of a group D2 -> fc2 operand,
-//       D3 -> features in HBM.
+//   drain warps (5-8, thread = accumulator lane = agent): D1 -> relu -> fp16 -> C[T % 2] (tensor memory again: the A
+//       operand of the Dense partial); at the end of a group D2 -> fc2 operand, D3 -> features in HBM.
 // Barrier parities: the n-th use of a full barrier waits parity n & 1; the n-th reuse of a slot waits its free barrier on
 // parity (n & 1) ^ 1 (passes at once for n = 0).
 __global__ void __launch_bounds__(kThreads, 1) policy_features_kernel(const uint8_t* __restrict__ obs, long long M, const uint8_t* __restrict__ blob,
@@ -125,7 +144,7 @@ __global__ void __launch_bounds__(kThreads, 1) policy_features_kernel(const uint
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == kMmaWarp) {  // tensor memory for the accumulators
+    if (warp == kMmaWarp) {  // all of the SM's tensor memory (one CTA per SM)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -140,6 +159,7 @@ __global__ void __launch_bounds__(kThreads, 1) policy_features_kernel(const uint
     if (warp < kProducerWarps) {
         // ------------------------------------------------------------------ producers
         const int t = tid;
+        const uint32_t tlane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
         auto load_obs = [&](long long g) {  // thread 0: the group's rem * 675 contiguous bytes (a group starts 16-byte aligned)
             const long long a0 = g * GA;
             const int rem = static_cast<int>(M - a0 < GA ? M - a0 : GA);
@@ -151,60 +171,74 @@ __global__ void __launch_bounds__(kThreads, 1) policy_features_kernel(const uint
         };
         if (t == 0 && blockIdx.x < n_groups) load_obs(blockIdx.x);
         uint32_t R = 0, T = 0, gi = 0;
+        SSD_PT_DECL;
         for (long long g = blockIdx.x; g < n_groups; g += gridDim.x, ++gi) {
             mbar_wait(bars + BAR_OBS, gi & 1);
+            SSD_PT(0);
 #pragma unroll 1
             for (int r = 0; r < V; ++r, ++R) {
                 const uint32_t slot = R & (RING - 1);
-                mbar_wait(bars + BAR_ROW_FREE + slot, ((R >> 2) & 1) ^ 1);
-                {   // fp16(1024 + byte) of this agent's 48-byte window, eight taps per 16-byte store
+                uint32_t h[ROWK / 2];
+                {   // fp16(1024 + byte) of this agent's 48-byte window: 0x6400 | byte
                     const int base = t * IMG + r * ROWB;
                     const uint32_t* w = reinterpret_cast<const uint32_t*>(smem + kOffObs + (base & ~3));
                     const uint32_t sh = static_cast<uint32_t>(base & 3) * 8;
-                    uint4* dst = reinterpret_cast<uint4*>(smem + kOffRing + slot * kRowBytes + t * 16);
                     uint32_t x[ROWK / 4 + 1];
 #pragma unroll
                     for (int q = 0; q <= ROWK / 4; ++q) x[q] = w[q];
 #pragma unroll
-                    for (int kc = 0; kc < ROWK / 8; ++kc) {
-                        const uint32_t lo = __funnelshift_r(x[2 * kc], x[2 * kc + 1], sh), hi = __funnelshift_r(x[2 * kc + 1], x[2 * kc + 2], sh);
-                        dst[kc * GA] = make_uint4(__byte_perm(lo, 0x64646464u, 0x4140), __byte_perm(lo, 0x64646464u, 0x4342),
-                                                  __byte_perm(hi, 0x64646464u, 0x4140), __byte_perm(hi, 0x64646464u, 0x4342));
+                    for (int q = 0; q < ROWK / 4; ++q) {
+                        const uint32_t b4 = __funnelshift_r(x[q], x[q + 1], sh);
+                        h[2 * q] = __byte_perm(b4, 0x64646464u, 0x4140);
+                        h[2 * q + 1] = __byte_perm(b4, 0x64646464u, 0x4342);
                     }
                 }
-                fence_async_smem();
+                SSD_PT(2);
+                mbar_wait(bars + BAR_ROW_FREE + slot, ((R >> 2) & 1) ^ 1);
+                SSD_PT(1);
+                tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < ROWK / 2; c += 8) tmem_st8(tlane + kColRing + slot * 32 + c, h + c);
+                tmem_st_wait();
+                tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
-                    if (warp == 0 && r >= 2) {  // the Dense(32) row block of output row r - 2 rides on the same barrier
-                        const uint32_t Tt = T + (r - 2), b = Tt & 1;
-                        mbar_wait(bars + BAR_C_FREE + b, ((Tt >> 1) & 1) ^ 1);  // its buffer: read last by the partial of row Tt - 2
+                    if (warp == 0 && r >= 2) {  // the Dense(32) weight block of output row r - 2 rides on the same barrier
+                        const uint32_t Tt = T + (r - 2), ws = Tt & (RING - 1);
+                        mbar_wait(bars + BAR_W1_FREE + ws, ((Tt >> 2) & 1) ^ 1);  // read last by the partial of row Tt - 4
                         mbar_expect_tx(bars + BAR_ROW_FULL + slot, kB2Bytes);
-                        bulk_g2s(smem + kOffW1 + b * kB2Bytes, blob + kHeadBytes + (r - 2) * kB2Bytes, kB2Bytes, bars + BAR_ROW_FULL + slot);
+                        bulk_g2s(smem + kOffW1 + ws * kB2Bytes, blob + kHeadBytes + (r - 2) * kB2Bytes, kB2Bytes, bars + BAR_ROW_FULL + slot);
                     } else {
                         mbar_arrive(bars + BAR_ROW_FULL + slot);
                     }
                 }
+                SSD_PT(3);
             }
             T += CO;
             asm volatile("bar.sync 1, 128;" ::: "memory");  // every producer is done with the observation bytes
             if (t == 0 && g + gridDim.x < n_groups) load_obs(g + gridDim.x);
+            SSD_PT(4);
         }
+        if (t == 0) SSD_PT_FLUSH(0);
     } else if (warp == kMmaWarp) {
         // ------------------------------------------------------------------ MMA issue (one thread)
         if (lane == 0) {
             constexpr uint32_t kI1 = umma_idesc(GA, N1), kI2 = umma_idesc(GA, N2), kI3 = umma_idesc(GA, N3);
-            const uint32_t sRing = smem_u32(smem + kOffRing), sC = smem_u32(smem + kOffC), sX3 = smem_u32(smem + kOffX3);
             const uint32_t sB1 = smem_u32(smem + kOffB1), sB3 = smem_u32(smem + kOffB3), sW1 = smem_u32(smem + kOffW1);
             uint32_t rows_seen = 0, T = 0, gi = 0;
+            SSD_PT_DECL;
             auto dense_partial = [&](uint32_t Tp, int i_local) {  // D2 (+)= C[Tp % 2] * W1 block
-                const uint32_t b = Tp & 1;
+                const uint32_t b = Tp & 1, ws = Tp & (RING - 1);
                 mbar_wait(bars + BAR_C_FULL + b, (Tp >> 1) & 1);
+                SSD_PT(3);
                 tc_fence_after();
 #pragma unroll
                 for (int ks = 0; ks < K2 / 16; ++ks)
-                    umma_f16(tmem + kColD2, umma_desc(sC + b * kCBytes + ks * 2 * GA * 16, GA * 16, 128),
-                             umma_desc(sW1 + b * kB2Bytes + ks * 2 * N2 * 16, N2 * 16, 128), kI2, (i_local | ks) != 0);
+                    umma_f16_ts(tmem + kColD2, tmem + kColC + b * 64 + ks * 8, umma_desc(sW1 + ws * kB2Bytes + ks * 2 * N2 * 16, N2 * 16, 128), kI2,
+                                (i_local | ks) != 0);
                 umma_commit(bars + BAR_C_FREE + b);
+                umma_commit(bars + BAR_W1_FREE + ws);
+                SSD_PT(4);
             };
             for (long long g = blockIdx.x; g < n_groups; g += gridDim.x, ++gi) {
                 const uint32_t R0 = gi * V;
@@ -214,39 +248,48 @@ __global__ void __launch_bounds__(kThreads, 1) policy_features_kernel(const uint
                         mbar_wait(bars + BAR_ROW_FULL + (rows_seen & (RING - 1)), (rows_seen >> 2) & 1);
                         ++rows_seen;
                     }
+                    SSD_PT(0);
                     const uint32_t b = T & 1;
                     mbar_wait(bars + BAR_D1_FREE + b, ((T >> 1) & 1) ^ 1);
+                    SSD_PT(1);
                     tc_fence_after();
 #pragma unroll
                     for (int di = 0; di < 3; ++di)
 #pragma unroll
                         for (int ks = 0; ks < ROWK / 16; ++ks)
-                            umma_f16(tmem + (b ? kColD1b : kColD1a),
-                                     umma_desc(sRing + ((R0 + i + di) & (RING - 1)) * kRowBytes + ks * 2 * GA * 16, GA * 16, 128),
-                                     umma_desc(sB1 + (di * (ROWK / 16) + ks) * 2 * N1 * 16, N1 * 16, 128), kI1, (di | ks) != 0);
+                            umma_f16_ts(tmem + (b ? kColD1b : kColD1a), tmem + kColRing + ((R0 + i + di) & (RING - 1)) * 32 + ks * 8,
+                                        umma_desc(sB1 + (di * (ROWK / 16) + ks) * 2 * N1 * 16, N1 * 16, 128), kI1, (di | ks) != 0);
                     umma_commit(bars + BAR_D1_FULL + b);
                     umma_commit(bars + BAR_ROW_FREE + ((R0 + i) & (RING - 1)));  // image row i is not needed again
                     if (i == CO - 1) {
                         umma_commit(bars + BAR_ROW_FREE + ((R0 + i + 1) & (RING - 1)));
                         umma_commit(bars + BAR_ROW_FREE + ((R0 + i + 2) & (RING - 1)));
                     }
+                    SSD_PT(2);
                     if (i >= 1) dense_partial(T - 1, i - 1);
                 }
                 dense_partial(T - 1, CO - 1);
                 umma_commit(bars + BAR_D2);
                 mbar_wait(bars + BAR_X3, gi & 1);
+                SSD_PT(5);
                 tc_fence_after();
 #pragma unroll
                 for (int ks = 0; ks < K3 / 16; ++ks)
-                    umma_f16(tmem + kColD3, umma_desc(sX3 + ks * 2 * GA * 16, GA * 16, 128), umma_desc(sB3 + ks * 2 * N3 * 16, N3 * 16, 128), kI3, ks > 0);
+                    umma_f16_ts(tmem + kColD3, tmem + kColX3 + ks * 8, umma_desc(sB3 + ks * 2 * N3 * 16, N3 * 16, 128), kI3, ks > 0);
                 umma_commit(bars + BAR_D3);
+                SSD_PT(6);
             }
+            SSD_PT_FLUSH(1);
         }
     } else {
-        // ------------------------------------------------------------------ drain warps: thread = accumulator row = agent
+        // ------------------------------------------------------------------ drain warps: thread = accumulator lane = agent
         const int q = warp & 3, row = q * 32 + lane;
         const uint32_t trow = tmem + (static_cast<uint32_t>(q * 32) << 16);
+        float cb[N1];  // bias, -128 / 255 and the 1024 offset of the operand, per conv column
+#pragma unroll
+        for (int c = 0; c < N1; ++c) cb[c] = s_const[c];
         uint32_t T = 0, gi = 0;
+        SSD_PT_DECL;
         for (long long g = blockIdx.x; g < n_groups; g += gridDim.x, ++gi) {
             const long long a0 = g * GA;
             const int rem = static_cast<int>(M - a0 < GA ? M - a0 : GA);
@@ -254,6 +297,7 @@ __global__ void __launch_bounds__(kThreads, 1) policy_features_kernel(const uint
             for (int i = 0; i < CO; ++i, ++T) {
                 const uint32_t b = T & 1;
                 mbar_wait(bars + BAR_D1_FULL + b, (T >> 1) & 1);
+                SSD_PT(0);
                 tc_fence_after();
                 uint32_t acc[N1];
 #pragma unroll
@@ -262,36 +306,35 @@ __global__ void __launch_bounds__(kThreads, 1) policy_features_kernel(const uint
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bars + BAR_D1_FREE + b);
+                SSD_PT(1);
                 uint32_t h[N1 / 2];   // C = fp16(relu(D1 / 255 + cb))
 #pragma unroll
                 for (int c = 0; c < N1; c += 2)
-                    h[c / 2] = pack_relu_h2(__uint_as_float(acc[c]) * (1.0f / 255.0f) + s_const[c], __uint_as_float(acc[c + 1]) * (1.0f / 255.0f) + s_const[c + 1]);
+                    h[c / 2] = pack_relu_h2(fmaf(__uint_as_float(acc[c]), 1.0f / 255.0f, cb[c]), fmaf(__uint_as_float(acc[c + 1]), 1.0f / 255.0f, cb[c + 1]));
+                SSD_PT(2);
                 mbar_wait(bars + BAR_C_FREE + b, ((T >> 1) & 1) ^ 1);
-                uint4* dst = reinterpret_cast<uint4*>(smem + kOffC + b * kCBytes + row * 16);
+                SSD_PT(3);
+                tc_fence_after();
 #pragma unroll
-                for (int kc = 0; kc < K2 / 8; ++kc) dst[kc * GA] = make_uint4(h[4 * kc], h[4 * kc + 1], h[4 * kc + 2], h[4 * kc + 3]);
-                fence_async_smem();
+                for (int c = 0; c < N1 / 2; c += 8) tmem_st8(trow + kColC + b * 64 + c, h + c);
+                tmem_st_wait();
+                tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bars + BAR_C_FULL + b);
+                SSD_PT(4);
             }
             {   // fc2 operand = fp16(relu(D2 + b1))
                 mbar_wait(bars + BAR_D2, gi & 1);
                 tc_fence_after();
-                uint32_t acc[N2];
+                uint32_t acc[N2], h[N2 / 2];
                 tmem_ld16(trow + kColD2, acc);
                 tmem_ld16(trow + kColD2 + 16, acc + 16);
                 tmem_ld_wait();
-                uint4* dst = reinterpret_cast<uint4*>(smem + kOffX3 + row * 16);
 #pragma unroll
-                for (int kc = 0; kc < K3 / 8; ++kc) {
-                    uint32_t h[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e)
-                        h[e] = pack_relu_h2(__uint_as_float(acc[8 * kc + 2 * e]) + s_const[N1 + 8 * kc + 2 * e],
-                                            __uint_as_float(acc[8 * kc + 2 * e + 1]) + s_const[N1 + 8 * kc + 2 * e + 1]);
-                    dst[kc * GA] = make_uint4(h[0], h[1], h[2], h[3]);
-                }
-                fence_async_smem();
+                for (int c = 0; c < N2; c += 2) h[c / 2] = pack_relu_h2(__uint_as_float(acc[c]) + s_const[N1 + c], __uint_as_float(acc[c + 1]) + s_const[N1 + c + 1]);
+                tmem_st8(trow + kColX3, h);
+                tmem_st8(trow + kColX3 + 8, h + 8);
+                tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bars + BAR_X3);
@@ -312,7 +355,9 @@ __global__ void __launch_bounds__(kThreads, 1) policy_features_kernel(const uint
                                                  fmaxf(__uint_as_float(acc[c + 2]) + s_const[N1 + N2 + c + 2], 0.f), fmaxf(__uint_as_float(acc[c + 3]) + s_const[N1 + N2 + c + 3], 0.f));
                 }
             }
+            SSD_PT(5);
         }
+        if (tid == 160) SSD_PT_FLUSH(2);
     }
     tc_fence_before();
     __syncthreads();
