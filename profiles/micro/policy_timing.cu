@@ -27,10 +27,10 @@ int main(int argc, char** argv) {
 #ifdef SSD_POLICY_TIMING
     unsigned long long c[3][8];
     cudaMemcpyFromSymbol(c, g_policy_cycles, sizeof c);
-    const char* names[3][8] = {{"wait obs", "wait row_free", "build row", "arrive / W1 issue", "group end", "", "", ""},
-                               {"wait row_full", "wait d1_free", "issue conv", "wait c_full", "issue dense", "wait x3", "issue fc2", ""},
+    const char* names[3][8] = {{"wait obs", "wait row_free", "build row", "publish previous row", "group end", "issue tmem st", "wait::st", "syncwarp"},
+                               {"wait row_full", "wait rows+d1_free (o)", "issue e+d, commit", "wait c_full/w1", "issue o", "", "last fc2", ""},
                                {"wait d1_full", "tmem ld", "convert", "wait c_free", "store C", "group tail", "", ""}};
-    const char* roles[3] = {"producer thread 0", "MMA thread", "drain thread 160"};
+    const char* roles[3] = {"producer thread 0", "MMA thread", "drain thread 160 (warp 5)"};
     for (int r = 0; r < 3; ++r) {
         unsigned long long tot = 0; for (int i = 0; i < 8; ++i) tot += c[r][i];
         printf("%s: %llu cycles\n", roles[r], tot);

@@ -44,28 +44,34 @@ constexpr int ROWK = 48;                      // one image row: 45 taps padded t
 constexpr int N1 = 80;                        // 13 * 6 = 78 conv outputs of one output row, padded
 constexpr int K2 = 80, N2 = FEAT;             // one row block of Dense(32)
 constexpr int K3 = FEAT, N3 = FEAT;
-constexpr int RING = 4;                       // image-row operand blocks (and Dense weight blocks) in flight
-constexpr int kProducerWarps = 4, kMmaWarp = 4, kThreads = 288;   // warps 0-3 build operands, warp 4 issues MMAs, warps 5-8 drain
+constexpr int RING = 6;                       // image-row operand blocks in flight (tensor memory)
+constexpr int WRING = 6;                      // Dense weight blocks in flight (shared memory)
+constexpr int kProducerWarps = 4, kMmaWarp = 4, kDrainWarp0 = 5, kDrainWarps = 8, kLoadWarp = kDrainWarp0 + kDrainWarps, kThreads = 32 * (kLoadWarp + 1);
 // tensor memory (512 columns x 128 lanes x 32 bit): accumulators, and the A operands -- a lane is an agent, a column two fp16
 constexpr int kTmemCols = 512;
-constexpr int kColD1a = 0, kColD2 = 96, kColD1b = 128, kColD3 = 224;   // fp32 accumulators
-constexpr int kColRing = 256;                 // + 32 * slot: one image row, 24 columns
-constexpr int kColC = 384;                    // + 64 * buffer: relu(conv) of one output row, 40 columns
-constexpr int kColX3 = 496;                   // fc2 operand, 16 columns
+constexpr int kColD1a = 0, kColD1b = 144;     // conv accumulators of even / odd output rows (80 columns)
+constexpr int kColD2a = 80, kColD2b = 112;    // Dense(32) accumulators of even / odd groups
+constexpr int kColD3 = 224;                   // fc2 accumulator
+constexpr int kColX3 = 256;                   // fc2 operand, 16 columns
+constexpr int kColC = 272;                    // + 40 * buffer: relu(conv) of one output row, 40 columns
+constexpr int kColRing = 352;                 // + 24 * slot: one image row, 24 columns
+constexpr int kDrainSplit = 48;               // conv columns [0, 48) drain on warps 5-8, [48, 80) on warps 9-12
 
-// shared-memory carve-up (bytes): the group's observation bytes and the B operands
+// shared-memory carve-up (bytes): two groups of observation bytes and the B operands
 constexpr int kB1Bytes = (3 * ROWK / 8) * N1 * 16;        // 23 040
 constexpr int kB2Bytes = (K2 / 8) * N2 * 16;              // 5 120 per row block of Dense(32)
 constexpr int kB3Bytes = (K3 / 8) * N3 * 16;              // 2 048
 constexpr int kConstFloats = N1 + N2 + N3;                // cb[80], b1[32], b2[32]
 constexpr int kHeadBytes = kB1Bytes + kB3Bytes + kConstFloats * 4;   // resident part of the blob: 25 664
 constexpr int kBlobBytes = kHeadBytes + CO * kB2Bytes;    // + the 13 row blocks of Dense(32), streamed: 92 224
-constexpr int kOffObs = 0;                                // 128 * 675 = 86 400 + slack for the padded taps of the last agent
-constexpr int kOffB1 = 86528, kOffB3 = kOffB1 + kB1Bytes, kOffConst = kOffB3 + kB3Bytes;
+constexpr int kObsStride = 86528;                         // 128 * 675 = 86 400 + slack for the padded taps of the last agent (128-byte multiple)
+constexpr int kOffObs = 0;
+constexpr int kOffB1 = 2 * kObsStride, kOffB3 = kOffB1 + kB1Bytes, kOffConst = kOffB3 + kB3Bytes;
 constexpr int kOffW1 = kOffB1 + kHeadBytes;
-constexpr int kOffBar = kOffW1 + RING * kB2Bytes;
-enum { BAR_OBS = 0, BAR_ROW_FULL = 1, BAR_ROW_FREE = 5, BAR_D1_FULL = 9, BAR_D1_FREE = 11, BAR_C_FULL = 13, BAR_C_FREE = 15, BAR_W1_FREE = 17,
-       BAR_D2 = 21, BAR_X3 = 22, BAR_D3 = 23, BAR_COUNT = 24 };
+constexpr int kOffBar = kOffW1 + WRING * kB2Bytes;
+enum { BAR_OBS = 0, BAR_ROW_FULL = 2, BAR_ROW_FREE = 8, BAR_D1_FULL = 14, BAR_D1_FREE = 16, BAR_C_FULL = 18, BAR_C_FREE = 20, BAR_W1_FREE = 22,
+       BAR_D2 = 28, BAR_X3 = 30, BAR_D3 = 31, BAR_W1_FULL = 32, BAR_OBS_FREE = 38, BAR_STEP = 40, BAR_COUNT = 48 };
+constexpr int STEPS = 8;                      // ring of "first block of MMA step s has completed" barriers
 constexpr int kSmemBytes = kOffBar + BAR_COUNT * 8;
 static_assert(kHeadBytes % 16 == 0 && kOffB1 % 128 == 0 && kOffW1 % 16 == 0 && kOffBar % 8 == 0, "alignment");
 static_assert(kSmemBytes <= 227 * 1024, "one CTA per SM");
@@ -92,6 +98,11 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {  // arrives on `bar
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// one lane polls, the warp follows (__syncwarp orders the other lanes' accesses after lane 0's acquire)
+__device__ __forceinline__ void warp_wait(uint64_t* bar, uint32_t parity) {
+    if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+    __syncwarp();
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -118,14 +129,19 @@ __device__ __forceinline__ uint32_t pack_relu_h2(float lo, float hi) {  // {fp16
     return d;
 }
 
-// Three roles, each looping over the same groups g = blockIdx.x, blockIdx.x + gridDim.x, ...:
-//   producers (warps 0-3, thread = agent = TMEM lane): image row r of the group -> fp16(1024 + byte) in ring block R % 4 of
-//       tensor memory (R counts rows over all groups of the CTA); thread 0 also streams the Dense(32) weight block of output
-//       row r - 2 into shared memory and, at the end of a group, the next group's observation bytes;
-//   MMA thread (warp 4): conv(i) = 9 MMAs over ring blocks i..i+2 into D1[T % 2] (T counts output rows), then the
-//       Dense(32) partial of output row i - 1 while the drain warps convert row i;
-//   drain warps (5-8, thread = accumulator lane = agent): D1 -> relu -> fp16 -> C[T % 2] (tensor memory again: the A
-//       operand of the Dense partial); at the end of a group D2 -> fc2 operand, D3 -> features in HBM.
+// The CTA works through its groups g = blockIdx.x, blockIdx.x + gridDim.x, ... as ONE sequence of output rows
+// T = 13 * (group ordinal) + i and image rows R = 15 * (group ordinal) + r; three roles run that sequence concurrently:
+//   producers (warps 0-3, thread = agent = TMEM lane): image row R -> fp16(1024 + byte) in ring block R % 6 of tensor
+//       memory;
+//   loader thread (warp 13): TMA bulk copies -- two groups of observation bytes in flight, the Dense(32) weight blocks
+//       through a 6-deep ring in shared memory;
+//   MMA thread (warp 4): step s issues the last six MMAs of conv(s) interleaved with the five of the Dense partial of
+//       row s - 2, then -- once the drain warps have read the accumulator of row s - 1 -- the first three of conv(s + 1)
+//       into it, so the tensor pipe always has queued work while an accumulator is drained; fc2 of a group four steps
+//       after its last row;
+//   drain warps (5-12, thread = accumulator lane = agent, two warps per lane quarter splitting the columns):
+//       D1[T % 2] -> relu -> fp16 -> C[T % 2] (tensor memory again: the A operand of the Dense partial); two rows into
+//       the next group D2 -> fc2 operand, four rows in D3 -> features in HBM.
 // Barrier parities: the n-th use of a full barrier waits parity n & 1; the n-th reuse of a slot waits its free barrier on
 // parity (n & 1) ^ 1 (passes at once for n = 0).
 __global__ void __launch_bounds__(kThreads, 1) policy_features_kernel(const uint8_t* __restrict__ obs, long long M, const uint8_t* __restrict__ blob,
@@ -136,11 +152,14 @@ __global__ void __launch_bounds__(kThreads, 1) policy_features_kernel(const uint
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
     const float* s_const = reinterpret_cast<const float*>(smem + kOffConst);
     const long long n_groups = (M + GA - 1) / GA;
+    const uint32_t n_my = blockIdx.x < n_groups ? static_cast<uint32_t>((n_groups - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;  // groups of this CTA
+    const uint32_t NT = n_my * CO;
 
     if (tid == 0) {
         for (int b = 0; b < BAR_COUNT; ++b) {
-            const bool by_warps = (b >= BAR_ROW_FULL && b < BAR_ROW_FREE) || (b >= BAR_D1_FREE && b < BAR_C_FREE) || b == BAR_X3;
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bars + b)), "r"(by_warps ? 4 : 1) : "memory");
+            const int count = ((b >= BAR_ROW_FULL && b < BAR_ROW_FREE) || (b >= BAR_OBS_FREE && b < BAR_STEP)) ? kProducerWarps
+                              : ((b >= BAR_D1_FREE && b < BAR_C_FREE) || b == BAR_X3) ? kDrainWarps : 1;
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bars + b)), "r"(count) : "memory");
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -160,32 +179,32 @@ __global__ void __launch_bounds__(kThreads, 1) policy_features_kernel(const uint
         // ------------------------------------------------------------------ producers
         const int t = tid;
         const uint32_t tlane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
-        auto load_obs = [&](long long g) {  // thread 0: the group's rem * 675 contiguous bytes (a group starts 16-byte aligned)
-            const long long a0 = g * GA;
-            const int rem = static_cast<int>(M - a0 < GA ? M - a0 : GA);
-            const uint8_t* src = obs + a0 * IMG;
-            const uint32_t bytes = static_cast<uint32_t>(rem) * IMG, b16 = bytes & ~15u;
-            for (uint32_t i = b16; i < bytes; ++i) smem[kOffObs + i] = src[i];
-            mbar_expect_tx(bars + BAR_OBS, b16);
-            bulk_g2s(smem + kOffObs, src, b16, bars + BAR_OBS);
-        };
-        if (t == 0 && blockIdx.x < n_groups) load_obs(blockIdx.x);
-        uint32_t R = 0, T = 0, gi = 0;
+        uint32_t R = 0;
         SSD_PT_DECL;
-        for (long long g = blockIdx.x; g < n_groups; g += gridDim.x, ++gi) {
-            mbar_wait(bars + BAR_OBS, gi & 1);
+        // The stores of a row into tensor memory complete while the next row is assembled in registers: a row is published
+        // (wait::st, fence, arrive) one iteration after its stores were issued.
+        auto publish = [&](uint32_t Rp) {
+            tmem_st_wait();
+            SSD_PT(6);
+            tc_fence_before();
+            __syncwarp();
+            SSD_PT(7);
+            if (lane == 0) mbar_arrive(bars + BAR_ROW_FULL + Rp % RING);
+        };
+        for (uint32_t gi = 0; gi < n_my; ++gi) {
+            warp_wait(bars + BAR_OBS + (gi & 1), (gi >> 1) & 1);
             SSD_PT(0);
+            const uint8_t* img = smem + kOffObs + (gi & 1) * kObsStride + t * IMG;
 #pragma unroll 1
             for (int r = 0; r < V; ++r, ++R) {
-                const uint32_t slot = R & (RING - 1);
+                const uint32_t slot = R % RING;
                 uint32_t h[ROWK / 2];
                 {   // fp16(1024 + byte) of this agent's 48-byte window: 0x6400 | byte
-                    const int base = t * IMG + r * ROWB;
-                    const uint32_t* w = reinterpret_cast<const uint32_t*>(smem + kOffObs + (base & ~3));
-                    const uint32_t sh = static_cast<uint32_t>(base & 3) * 8;
+                    const uint32_t base = smem_u32(img + r * ROWB);
+                    const uint32_t sh = (base & 3u) * 8;
                     uint32_t x[ROWK / 4 + 1];
 #pragma unroll
-                    for (int q = 0; q <= ROWK / 4; ++q) x[q] = w[q];
+                    for (int q = 0; q <= ROWK / 4; ++q) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(x[q]) : "r"((base & ~3u) + 4 * q));
 #pragma unroll
                     for (int q = 0; q < ROWK / 4; ++q) {
                         const uint32_t b4 = __funnelshift_r(x[q], x[q + 1], sh);
@@ -194,170 +213,242 @@ __global__ void __launch_bounds__(kThreads, 1) policy_features_kernel(const uint
                     }
                 }
                 SSD_PT(2);
-                mbar_wait(bars + BAR_ROW_FREE + slot, ((R >> 2) & 1) ^ 1);
+                if (R > 0) publish(R - 1);
+                SSD_PT(3);
+                if (R >= RING) {  // the block's previous image row: last read by conv of its own output row (rows 13, 14: of row 12)
+                    const uint32_t Rq = R - RING, iq = Rq % V, xs = (Rq / V) * CO + (iq < CO ? iq : CO - 1);
+                    warp_wait(bars + BAR_STEP + xs % STEPS, (xs / STEPS) & 1);
+                }
                 SSD_PT(1);
                 tc_fence_after();
 #pragma unroll
-                for (int c = 0; c < ROWK / 2; c += 8) tmem_st8(tlane + kColRing + slot * 32 + c, h + c);
-                tmem_st_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) {
-                    if (warp == 0 && r >= 2) {  // the Dense(32) weight block of output row r - 2 rides on the same barrier
-                        const uint32_t Tt = T + (r - 2), ws = Tt & (RING - 1);
-                        mbar_wait(bars + BAR_W1_FREE + ws, ((Tt >> 2) & 1) ^ 1);  // read last by the partial of row Tt - 4
-                        mbar_expect_tx(bars + BAR_ROW_FULL + slot, kB2Bytes);
-                        bulk_g2s(smem + kOffW1 + ws * kB2Bytes, blob + kHeadBytes + (r - 2) * kB2Bytes, kB2Bytes, bars + BAR_ROW_FULL + slot);
-                    } else {
-                        mbar_arrive(bars + BAR_ROW_FULL + slot);
-                    }
-                }
-                SSD_PT(3);
+                for (int c = 0; c < ROWK / 2; c += 8) tmem_st8(tlane + kColRing + slot * (ROWK / 2) + c, h + c);
+                SSD_PT(5);
             }
-            T += CO;
-            asm volatile("bar.sync 1, 128;" ::: "memory");  // every producer is done with the observation bytes
-            if (t == 0 && g + gridDim.x < n_groups) load_obs(g + gridDim.x);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bars + BAR_OBS_FREE + (gi & 1));  // this warp is done with the buffer of observation bytes
             SSD_PT(4);
         }
+        if (R > 0) publish(R - 1);
         if (t == 0) SSD_PT_FLUSH(0);
     } else if (warp == kMmaWarp) {
-        // ------------------------------------------------------------------ MMA issue (one thread)
-        if (lane == 0) {
+        // ------------------------------------------------------------------ MMA issue (one elected thread)
+        // Everything an MMA needs is a 32-bit add away: descriptors are (lo, hi) pairs whose lo word advances by a constant
+        // per k-step, tensor-memory operands are base + 24 * ring slot + 8 * k-step.  elect.sync (not `lane == 0`) tells ptxas
+        // the block runs on one lane, so the UTCHMMAs are issued without a per-instruction convergence loop.
+        if (NT > 0 && elect_one()) {
+#ifdef SSD_EXP_N16  // timing experiment only (wrong results): how does the MMA time depend on N?
+            constexpr uint32_t kI1 = umma_idesc(GA, 16), kI2 = umma_idesc(GA, 16), kI3 = umma_idesc(GA, N3);
+#else
             constexpr uint32_t kI1 = umma_idesc(GA, N1), kI2 = umma_idesc(GA, N2), kI3 = umma_idesc(GA, N3);
-            const uint32_t sB1 = smem_u32(smem + kOffB1), sB3 = smem_u32(smem + kOffB3), sW1 = smem_u32(smem + kOffW1);
-            uint32_t rows_seen = 0, T = 0, gi = 0;
+#endif
+            constexpr uint32_t kDescHi = (128u >> 4) | 1u << 14;   // SBO = 128 bytes, descriptor version 1
+            auto desc_lo = [](uint32_t saddr, uint32_t lbo) { return ((saddr & 0x3FFFFu) >> 4) | (lbo >> 4) << 16; };
+            auto mk = [](uint32_t lo) { return static_cast<uint64_t>(kDescHi) << 32 | lo; };
+            const uint32_t b1_lo = desc_lo(smem_u32(smem + kOffB1), N1 * 16);   // + (2 * N1 * 16 >> 4) per k-step
+            const uint32_t w1_lo = desc_lo(smem_u32(smem + kOffW1), N2 * 16);   // + (kB2Bytes >> 4) per buffer, + (2 * N2 * 16 >> 4) per k-step
+            const uint32_t b3_lo = desc_lo(smem_u32(smem + kOffB3), N3 * 16);
+            constexpr uint32_t kB1Step = 2 * N1 * 16 >> 4, kW1Step = 2 * N2 * 16 >> 4, kW1Buf = kB2Bytes >> 4, kB3Step = 2 * N3 * 16 >> 4;
+            const uint32_t ring = tmem + kColRing;
+            uint32_t rows_seen = 0;
             SSD_PT_DECL;
-            auto dense_partial = [&](uint32_t Tp, int i_local) {  // D2 (+)= C[Tp % 2] * W1 block
-                const uint32_t b = Tp & 1, ws = Tp & (RING - 1);
-                mbar_wait(bars + BAR_C_FULL + b, (Tp >> 1) & 1);
+            auto wait_rows = [&](uint32_t need) {  // image rows [0, need) of the CTA's sequence
+                while (rows_seen < need) {
+                    mbar_wait(bars + BAR_ROW_FULL + rows_seen % RING, (rows_seen / RING) & 1);
+                    ++rows_seen;
+                }
+            };
+            auto fc2 = [&](uint32_t gi) {
+                mbar_wait(bars + BAR_X3, gi & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int ks = 0; ks < K3 / 16; ++ks) umma_f16_ts(tmem + kColD3, tmem + kColX3 + ks * 8, mk(b3_lo + ks * kB3Step), kI3, ks > 0);
+                umma_commit(bars + BAR_D3);
+            };
+            // state of output row s (e), s + 1 (o) and s - 2 (d): index in its group, ring slot of its first image row, group parity
+            uint32_t i_e = 0, slot_e = 0, row_e = 0, g_e = 0;   // row_e = first image row of conv(s) in the CTA's sequence
+            uint32_t i_d1 = 0, g_d1 = 0, i_d = 0, g_d = 0;      // rows s - 1 and s - 2
+            wait_rows(1);
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < 3; ++k) umma_f16_ts(tmem + kColD1a, ring + k * 8, mk(b1_lo + k * kB1Step), kI1, k != 0);
+#pragma unroll 1
+            for (uint32_t s = 0; s < NT + 2; ++s) {
+                const bool has_e = s < NT, has_o = s + 1 < NT, has_d = s >= 2;
+#ifdef SSD_EXP_NO_DENSE  // timing experiment only (wrong results): the step without its five Dense MMAs
+#define SSD_DENSE_MMA(...)
+#else
+#define SSD_DENSE_MMA(...) umma_f16_ts(__VA_ARGS__)
+#endif
+                const bool last_e = i_e == CO - 1;
+                const uint32_t slot_o = (slot_e + (last_e ? 3 : 1)) % RING, row_o = row_e + (last_e ? 3 : 1);
+                // ---- first block: the six remaining MMAs of conv(s) (image rows i + 1, i + 2) interleaved with the Dense partial of
+                // row s - 2.  Nothing here needs the accumulator the drain warps are reading.
+                if (has_e) wait_rows(row_e + 3);
+                SSD_PT(0);
+                if (has_d) {
+                    mbar_wait(bars + BAR_C_FULL + (s & 1), ((s - 2) >> 1) & 1);
+                    mbar_wait(bars + BAR_W1_FULL + (s - 2) % WRING, ((s - 2) / WRING) & 1);
+                }
                 SSD_PT(3);
                 tc_fence_after();
-#pragma unroll
-                for (int ks = 0; ks < K2 / 16; ++ks)
-                    umma_f16_ts(tmem + kColD2, tmem + kColC + b * 64 + ks * 8, umma_desc(sW1 + ws * kB2Bytes + ks * 2 * N2 * 16, N2 * 16, 128), kI2,
-                                (i_local | ks) != 0);
-                umma_commit(bars + BAR_C_FREE + b);
-                umma_commit(bars + BAR_W1_FREE + ws);
-                SSD_PT(4);
-            };
-            for (long long g = blockIdx.x; g < n_groups; g += gridDim.x, ++gi) {
-                const uint32_t R0 = gi * V;
-#pragma unroll 1
-                for (int i = 0; i < CO; ++i, ++T) {
-                    while (rows_seen < R0 + i + 3) {
-                        mbar_wait(bars + BAR_ROW_FULL + (rows_seen & (RING - 1)), (rows_seen >> 2) & 1);
-                        ++rows_seen;
-                    }
-                    SSD_PT(0);
-                    const uint32_t b = T & 1;
-                    mbar_wait(bars + BAR_D1_FREE + b, ((T >> 1) & 1) ^ 1);
+                {
+                    const uint32_t d_e = tmem + ((s & 1) ? kColD1b : kColD1a);
+                    const uint32_t a_e1 = ring + ((slot_e + 1) % RING) * (ROWK / 2), a_e2 = ring + ((slot_e + 2) % RING) * (ROWK / 2);
+                    const uint32_t d_d = tmem + (g_d ? kColD2b : kColD2a), a_d = tmem + kColC + (s & 1) * (K2 / 2);
+                    const uint32_t w_d = w1_lo + ((s - 2) % WRING) * kW1Buf;
+                    const uint32_t acc_d = i_d != 0;
+                    if (has_e) umma_f16_ts(d_e, a_e1, mk(b1_lo + 3 * kB1Step), kI1, 1);
+                    if (has_d) SSD_DENSE_MMA(d_d, a_d, mk(w_d), kI2, acc_d);
+                    if (has_e) umma_f16_ts(d_e, a_e1 + 8, mk(b1_lo + 4 * kB1Step), kI1, 1);
+                    if (has_d) SSD_DENSE_MMA(d_d, a_d + 8, mk(w_d + kW1Step), kI2, 1);
+                    if (has_e) umma_f16_ts(d_e, a_e1 + 16, mk(b1_lo + 5 * kB1Step), kI1, 1);
+                    if (has_d) SSD_DENSE_MMA(d_d, a_d + 16, mk(w_d + 2 * kW1Step), kI2, 1);
+                    if (has_e) umma_f16_ts(d_e, a_e2, mk(b1_lo + 6 * kB1Step), kI1, 1);
+                    if (has_d) SSD_DENSE_MMA(d_d, a_d + 24, mk(w_d + 3 * kW1Step), kI2, 1);
+                    if (has_e) umma_f16_ts(d_e, a_e2 + 8, mk(b1_lo + 7 * kB1Step), kI1, 1);
+                    if (has_d) SSD_DENSE_MMA(d_d, a_d + 32, mk(w_d + 4 * kW1Step), kI2, 1);
+                    if (has_e) umma_f16_ts(d_e, a_e2 + 16, mk(b1_lo + 8 * kB1Step), kI1, 1);
+                }
+                // ONE commit per step: conv(s) is complete (accumulator full, image row i -- and at the end of a group rows
+                // 13, 14 -- free) and so is the Dense partial of row s - 2 (C buffer and weight block free, D2 full after row 12)
+                umma_commit(bars + BAR_STEP + s % STEPS);
+                SSD_PT(2);
+                if (s >= 4 && (s - 4) % CO == CO - 1) fc2((s - 4) / CO);  // the drain warps delivered its operand a step ago
+                // ---- second block: the first image row of conv(s + 1), into the accumulator of row s - 1 once it is drained
+                if (has_o) {
+                    wait_rows(row_o + 1);
+                    mbar_wait(bars + BAR_D1_FREE + ((s + 1) & 1), (((s + 1) >> 1) & 1) ^ 1);
                     SSD_PT(1);
                     tc_fence_after();
-#pragma unroll
-                    for (int di = 0; di < 3; ++di)
-#pragma unroll
-                        for (int ks = 0; ks < ROWK / 16; ++ks)
-                            umma_f16_ts(tmem + (b ? kColD1b : kColD1a), tmem + kColRing + ((R0 + i + di) & (RING - 1)) * 32 + ks * 8,
-                                        umma_desc(sB1 + (di * (ROWK / 16) + ks) * 2 * N1 * 16, N1 * 16, 128), kI1, (di | ks) != 0);
-                    umma_commit(bars + BAR_D1_FULL + b);
-                    umma_commit(bars + BAR_ROW_FREE + ((R0 + i) & (RING - 1)));  // image row i is not needed again
-                    if (i == CO - 1) {
-                        umma_commit(bars + BAR_ROW_FREE + ((R0 + i + 1) & (RING - 1)));
-                        umma_commit(bars + BAR_ROW_FREE + ((R0 + i + 2) & (RING - 1)));
-                    }
-                    SSD_PT(2);
-                    if (i >= 1) dense_partial(T - 1, i - 1);
+                    const uint32_t d_o = tmem + ((s & 1) ? kColD1a : kColD1b), a_o0 = ring + slot_o * (ROWK / 2);
+                    umma_f16_ts(d_o, a_o0, mk(b1_lo), kI1, 0);
+                    umma_f16_ts(d_o, a_o0 + 8, mk(b1_lo + kB1Step), kI1, 1);
+                    umma_f16_ts(d_o, a_o0 + 16, mk(b1_lo + 2 * kB1Step), kI1, 1);
                 }
-                dense_partial(T - 1, CO - 1);
-                umma_commit(bars + BAR_D2);
-                mbar_wait(bars + BAR_X3, gi & 1);
-                SSD_PT(5);
-                tc_fence_after();
-#pragma unroll
-                for (int ks = 0; ks < K3 / 16; ++ks)
-                    umma_f16_ts(tmem + kColD3, tmem + kColX3 + ks * 8, umma_desc(sB3 + ks * 2 * N3 * 16, N3 * 16, 128), kI3, ks > 0);
-                umma_commit(bars + BAR_D3);
-                SSD_PT(6);
+                // shift the window of rows
+                i_d = i_d1; g_d = g_d1; i_d1 = i_e; g_d1 = g_e;
+                if (last_e) { i_e = 0; g_e ^= 1; } else { ++i_e; }
+                slot_e = slot_o; row_e = row_o;
+                SSD_PT(4);
             }
+            fc2(n_my - 1);  // the last group's fc2 step lies beyond the sequence
+            SSD_PT(6);
             SSD_PT_FLUSH(1);
+        }
+    } else if (warp == kLoadWarp) {
+        // ------------------------------------------------------------------ loader (one elected thread): TMA bulk copies only
+        if (n_my > 0 && elect_one()) {
+            auto load_obs = [&](uint32_t gi) {  // the group's rem * 675 contiguous bytes (a group starts 16-byte aligned)
+                const long long a0 = (blockIdx.x + static_cast<long long>(gi) * gridDim.x) * GA;
+                const int rem = static_cast<int>(M - a0 < GA ? M - a0 : GA);
+                const uint8_t* src = obs + a0 * IMG;
+                uint8_t* dst = smem + kOffObs + (gi & 1) * kObsStride;
+                const uint32_t bytes = static_cast<uint32_t>(rem) * IMG, b16 = bytes & ~15u;
+                for (uint32_t i = b16; i < bytes; ++i) dst[i] = src[i];
+                mbar_expect_tx(bars + BAR_OBS + (gi & 1), b16);
+                bulk_g2s(dst, src, b16, bars + BAR_OBS + (gi & 1));
+            };
+            load_obs(0);
+            if (n_my > 1) load_obs(1);
+            uint32_t next_obs = 2;  // next group whose bytes want a buffer: group next_obs - 2 must have been consumed
+#pragma unroll 1
+            for (uint32_t T = 0; T < NT; ++T) {  // Dense(32) weight block of output row T, six rows ahead of its use
+                const uint32_t ws = T % WRING;
+                while (T >= WRING && !mbar_try_wait(bars + BAR_STEP + (T - 4) % STEPS, ((T - 4) / STEPS) & 1)) {  // Dense partial of row T - 6
+                    if (next_obs < n_my && mbar_try_wait(bars + BAR_OBS_FREE + (next_obs & 1), ((next_obs - 2) >> 1) & 1)) load_obs(next_obs++);
+                }
+                mbar_expect_tx(bars + BAR_W1_FULL + ws, kB2Bytes);
+                bulk_g2s(smem + kOffW1 + ws * kB2Bytes, blob + kHeadBytes + (T % CO) * kB2Bytes, kB2Bytes, bars + BAR_W1_FULL + ws);
+                if (next_obs < n_my && mbar_try_wait(bars + BAR_OBS_FREE + (next_obs & 1), ((next_obs - 2) >> 1) & 1)) load_obs(next_obs++);
+            }
+            while (next_obs < n_my) {
+                mbar_wait(bars + BAR_OBS_FREE + (next_obs & 1), ((next_obs - 2) >> 1) & 1);
+                load_obs(next_obs++);
+            }
         }
     } else {
         // ------------------------------------------------------------------ drain warps: thread = accumulator lane = agent
-        const int q = warp & 3, row = q * 32 + lane;
+        const int q = warp & 3, row = q * 32 + lane, half = (warp - kDrainWarp0) >> 2;
         const uint32_t trow = tmem + (static_cast<uint32_t>(q * 32) << 16);
-        float cb[N1];  // bias, -128 / 255 and the 1024 offset of the operand, per conv column
+        const int col0 = half ? kDrainSplit : 0;   // this warp's conv columns [col0, col0 + ncol)
+        float cb[kDrainSplit];  // bias, -128 / 255 and the 1024 offset of the operand, per conv column
 #pragma unroll
-        for (int c = 0; c < N1; ++c) cb[c] = s_const[c];
-        uint32_t T = 0, gi = 0;
+        for (int c = 0; c < kDrainSplit; ++c) cb[c] = (col0 + c < N1) ? s_const[col0 + c] : 0.f;
         SSD_PT_DECL;
-        for (long long g = blockIdx.x; g < n_groups; g += gridDim.x, ++gi) {
-            const long long a0 = g * GA;
-            const int rem = static_cast<int>(M - a0 < GA ? M - a0 : GA);
+        auto tail1 = [&](uint32_t gi) {  // this warp's 16 columns of the fc2 operand = fp16(relu(D2 + b1))
+            const uint32_t xs = gi * CO + CO + 1;  // the step that issued the Dense partial of the group's last row
+            warp_wait(bars + BAR_STEP + xs % STEPS, (xs / STEPS) & 1);
+            tc_fence_after();
+            uint32_t acc[16], h[8];
+            tmem_ld16(trow + ((gi & 1) ? kColD2b : kColD2a) + 16 * half, acc);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 16; c += 2)
+                h[c / 2] = pack_relu_h2(__uint_as_float(acc[c]) + s_const[N1 + 16 * half + c], __uint_as_float(acc[c + 1]) + s_const[N1 + 16 * half + c + 1]);
+            tmem_st8(trow + kColX3 + 8 * half, h);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bars + BAR_X3);
+        };
+        auto tail2 = [&](uint32_t gi) {  // this warp's 16 features = relu(D3 + b2): 64 of the agent's 128 bytes
+            warp_wait(bars + BAR_D3, gi & 1);
+            tc_fence_after();
+            uint32_t acc[16];
+            tmem_ld16(trow + kColD3 + 16 * half, acc);
+            tmem_ld_wait();
+            tc_fence_before();
+            const long long a0 = (blockIdx.x + static_cast<long long>(gi) * gridDim.x) * GA;
+            if (a0 + row < M) {
+                float4* dst = reinterpret_cast<float4*>(out + (a0 + row) * FEAT + 16 * half);
+                const float* b2 = s_const + N1 + N2 + 16 * half;
+#pragma unroll
+                for (int c = 0; c < 16; c += 4)
+                    dst[c / 4] = make_float4(fmaxf(__uint_as_float(acc[c]) + b2[c], 0.f), fmaxf(__uint_as_float(acc[c + 1]) + b2[c + 1], 0.f),
+                                             fmaxf(__uint_as_float(acc[c + 2]) + b2[c + 2], 0.f), fmaxf(__uint_as_float(acc[c + 3]) + b2[c + 3], 0.f));
+            }
+        };
 #pragma unroll 1
-            for (int i = 0; i < CO; ++i, ++T) {
-                const uint32_t b = T & 1;
-                mbar_wait(bars + BAR_D1_FULL + b, (T >> 1) & 1);
-                SSD_PT(0);
-                tc_fence_after();
-                uint32_t acc[N1];
+        for (uint32_t T = 0; T < NT; ++T) {
+            const uint32_t b = T & 1;
+            warp_wait(bars + BAR_STEP + T % STEPS, (T / STEPS) & 1);   // conv(T) complete; so is the Dense partial that read C[b]
+            SSD_PT(0);
+            tc_fence_after();
+            uint32_t acc[kDrainSplit];
+            const uint32_t src = trow + (b ? kColD1b : kColD1a) + col0;
+            tmem_ld16(src, acc);
+            tmem_ld16(src + 16, acc + 16);
+            if (half == 0) tmem_ld16(src + 32, acc + 32);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bars + BAR_D1_FREE + b);
+            SSD_PT(1);
+            uint32_t h[kDrainSplit / 2];   // C = fp16(relu(D1 / 255 + cb))
 #pragma unroll
-                for (int c0 = 0; c0 < N1; c0 += 16) tmem_ld16(trow + (b ? kColD1b : kColD1a) + c0, acc + c0);
-                tmem_ld_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bars + BAR_D1_FREE + b);
-                SSD_PT(1);
-                uint32_t h[N1 / 2];   // C = fp16(relu(D1 / 255 + cb))
-#pragma unroll
-                for (int c = 0; c < N1; c += 2)
+            for (int c = 0; c < kDrainSplit; c += 2)
+                if (half == 0 || c < N1 - kDrainSplit)
                     h[c / 2] = pack_relu_h2(fmaf(__uint_as_float(acc[c]), 1.0f / 255.0f, cb[c]), fmaf(__uint_as_float(acc[c + 1]), 1.0f / 255.0f, cb[c + 1]));
-                SSD_PT(2);
-                mbar_wait(bars + BAR_C_FREE + b, ((T >> 1) & 1) ^ 1);
-                SSD_PT(3);
-                tc_fence_after();
-#pragma unroll
-                for (int c = 0; c < N1 / 2; c += 8) tmem_st8(trow + kColC + b * 64 + c, h + c);
-                tmem_st_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bars + BAR_C_FULL + b);
-                SSD_PT(4);
-            }
-            {   // fc2 operand = fp16(relu(D2 + b1))
-                mbar_wait(bars + BAR_D2, gi & 1);
-                tc_fence_after();
-                uint32_t acc[N2], h[N2 / 2];
-                tmem_ld16(trow + kColD2, acc);
-                tmem_ld16(trow + kColD2 + 16, acc + 16);
-                tmem_ld_wait();
-#pragma unroll
-                for (int c = 0; c < N2; c += 2) h[c / 2] = pack_relu_h2(__uint_as_float(acc[c]) + s_const[N1 + c], __uint_as_float(acc[c + 1]) + s_const[N1 + c + 1]);
-                tmem_st8(trow + kColX3, h);
-                tmem_st8(trow + kColX3 + 8, h + 8);
-                tmem_st_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bars + BAR_X3);
-            }
-            {   // features = relu(D3 + b2), one 128-byte row per agent
-                mbar_wait(bars + BAR_D3, gi & 1);
-                tc_fence_after();
-                uint32_t acc[N3];
-                tmem_ld16(trow + kColD3, acc);
-                tmem_ld16(trow + kColD3 + 16, acc + 16);
-                tmem_ld_wait();
-                tc_fence_before();
-                if (row < rem) {
-                    float4* dst = reinterpret_cast<float4*>(out + (a0 + row) * FEAT);
-#pragma unroll
-                    for (int c = 0; c < N3; c += 4)
-                        dst[c / 4] = make_float4(fmaxf(__uint_as_float(acc[c]) + s_const[N1 + N2 + c], 0.f), fmaxf(__uint_as_float(acc[c + 1]) + s_const[N1 + N2 + c + 1], 0.f),
-                                                 fmaxf(__uint_as_float(acc[c + 2]) + s_const[N1 + N2 + c + 2], 0.f), fmaxf(__uint_as_float(acc[c + 3]) + s_const[N1 + N2 + c + 3], 0.f));
-                }
-            }
+            SSD_PT(2);
+            const uint32_t dstc = trow + kColC + b * (K2 / 2) + col0 / 2;
+            tmem_st8(dstc, h);
+            tmem_st8(dstc + 8, h + 8);
+            if (half == 0) tmem_st8(dstc + 16, h + 16);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bars + BAR_C_FULL + b);
+            SSD_PT(4);
+            if (T >= 2 && (T - 2) % CO == CO - 1) tail1((T - 2) / CO);
+            if (T >= 4 && (T - 4) % CO == CO - 1) tail2((T - 4) / CO);
             SSD_PT(5);
         }
-        if (tid == 160) SSD_PT_FLUSH(2);
+        if (n_my > 0) {
+            tail1(n_my - 1);
+            tail2(n_my - 1);
+        }
+        if (tid == 32 * kDrainWarp0) SSD_PT_FLUSH(2);
     }
     tc_fence_before();
     __syncthreads();
