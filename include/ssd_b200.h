@@ -175,8 +175,9 @@ int ssd_step_host(ssd_handle h, const int8_t* actions_host, uint8_t* obs_host, i
  * The feature trunk of the reference's policy network, models/conv_to_fcnet_v2.py:36-66: Conv2D(6, 3x3, stride 1,
  * 'valid') -> ReLU -> flatten -> Dense(32) -> ReLU -> Dense(32) -> ReLU, applied to (obs - 128) / 255 (map_env.py:199)
  * of uint8 observations resident in HBM -- what ssd_step / ssd_rollout wrote -- in one fused tensor-core kernel
- * (fp16 operands, fp32 accumulation; nothing but the features returns to HBM).  The LSTM cell and the two heads that
- * follow (conv_to_fcnet_v2.py:68-92) are plain GEMMs on [M, 32] / [M, 128] and are left to the caller's BLAS.
+ * (fp16 operands, fp32 accumulation; nothing but the features returns to HBM).  The LSTM and the two heads that
+ * follow (conv_to_fcnet_v2.py:68-92) are plain GEMMs on [M, 32] / [M, 128], left to the caller's BLAS, plus the
+ * elementwise cell update ssd_policy_lstm_cell.
  *
  * Weights are HOST fp32 arrays in the Keras layouts: conv_w [3][3][3][6] (kh, kw, in, out), conv_b [6],
  * fc1_w [1014][32] (inputs flattened (row, col, filter) as keras Flatten does), fc1_b [32], fc2_w [32][32], fc2_b [32].
@@ -188,6 +189,12 @@ int ssd_policy_create(int view_radius, int device, const float* conv_w, const fl
  * features dev f32[num_agents][32] (16-byte aligned). */
 int ssd_policy_features(ssd_policy_t p, const uint8_t* obs, int64_t num_agents, float* features, void* stream);
 void ssd_policy_destroy(ssd_policy_t p);
+/* LSTM cell update after the gate GEMM (conv_to_fcnet_v2.py:68-80; Keras gate order i, f, c~, o; sigmoid recurrent
+ * activation): gates dev bf16[num_agents][4*units] = x W + h U without the bias, bias dev f32[4*units],
+ * c_prev / c_out / h_out dev f32[num_agents][units] (c_out may alias c_prev), h_bf16_out dev bf16[num_agents][units]
+ * (the operand of the next step's GEMM).  One pass over HBM; all pointers 16-byte aligned, units a multiple of 8. */
+int ssd_policy_lstm_cell(const void* gates_bf16, const float* bias, const float* c_prev, float* c_out, float* h_out, void* h_bf16_out,
+                         int64_t num_agents, int units, void* stream);
 
 /* Tuning options.
  * SSD_OPT_CHAIN_STEPS (default 0): when 1, consecutive ssd_step calls on the same stream are launched

@@ -36,6 +36,18 @@ int main(int argc, char** argv) {
         printf("%s: %llu cycles\n", roles[r], tot);
         for (int i = 0; i < 8; ++i) if (names[r][i][0]) printf("    %-20s %10llu  %5.1f %%\n", names[r][i], c[r][i], 100.0 * c[r][i] / tot);
     }
+    {
+        long long tl[3][32][4];
+        cudaMemcpyFromSymbol(tl, g_policy_tl, sizeof tl);
+        const long long base = tl[1][0][0];
+        printf("timeline of CTA 0 (cycles relative to MMA step 40 block 1)\n");
+        printf("idx | producer(row idx): built  free  stored  published(prev) | MMA(step idx): b1  commit  b2  b2done | drain(tile idx): step_seen  ld_done  c_full  iter_end\n");
+        for (int i = 0; i < 20; ++i) {
+            printf("%3d |", 40 + i);
+            for (int r = 0; r < 3; ++r) { for (int e = 0; e < 4; ++e) printf(" %7lld", tl[r][i][e] - base); printf(" |"); }
+            printf("\n");
+        }
+    }
 #endif
     return 0;
 }

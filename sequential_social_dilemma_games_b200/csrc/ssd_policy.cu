@@ -14,6 +14,7 @@
 //
 // Operands live in shared memory in the canonical K-major no-swizzle layout (8 x 16-byte core matrices: element (row, k) at
 // (k / 8) * rows * 16 + row * 16 + (k % 8) * 2), accumulators in tensor memory, all MMAs issued by one thread.
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
 #include <cstdio>
@@ -29,7 +30,10 @@ __device__ unsigned long long g_policy_cycles[3][8];
 #define SSD_PT_DECL unsigned long long pt_[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long pt_t = clock64()
 #define SSD_PT(slot) do { const long long n_ = clock64(); pt_[slot] += n_ - pt_t; pt_t = n_; } while (0)
 #define SSD_PT_FLUSH(role) do { if (blockIdx.x == 0) for (int q_ = 0; q_ < 8; ++q_) g_policy_cycles[role][q_] = pt_[q_]; } while (0)
+__device__ long long g_policy_tl[3][32][4];   // [role][step - 40][event] clock64 stamps of CTA 0
+#define SSD_TL(role, idx, ev) do { if (blockIdx.x == 0 && (idx) >= 40 && (idx) < 72) g_policy_tl[role][(idx) - 40][ev] = clock64(); } while (0)
 #else
+#define SSD_TL(role, idx, ev)
 #define SSD_PT_DECL
 #define SSD_PT(slot)
 #define SSD_PT_FLUSH(role)
@@ -69,8 +73,8 @@ constexpr int kOffObs = 0;
 constexpr int kOffB1 = 2 * kObsStride, kOffB3 = kOffB1 + kB1Bytes, kOffConst = kOffB3 + kB3Bytes;
 constexpr int kOffW1 = kOffB1 + kHeadBytes;
 constexpr int kOffBar = kOffW1 + WRING * kB2Bytes;
-enum { BAR_OBS = 0, BAR_ROW_FULL = 2, BAR_ROW_FREE = 8, BAR_D1_FULL = 14, BAR_D1_FREE = 16, BAR_C_FULL = 18, BAR_C_FREE = 20, BAR_W1_FREE = 22,
-       BAR_D2 = 28, BAR_X3 = 30, BAR_D3 = 31, BAR_W1_FULL = 32, BAR_OBS_FREE = 38, BAR_STEP = 40, BAR_COUNT = 48 };
+enum { BAR_OBS = 0, BAR_OBS_FREE = 2, BAR_ROW_FULL = 4, BAR_D1_FREE = 10, BAR_C_FULL = 12, BAR_W1_FULL = 14, BAR_X3 = 20, BAR_D3 = 21, BAR_STEP = 22,
+       BAR_COUNT = 30 };
 constexpr int STEPS = 8;                      // ring of "first block of MMA step s has completed" barriers
 constexpr int kSmemBytes = kOffBar + BAR_COUNT * 8;
 static_assert(kHeadBytes % 16 == 0 && kOffB1 % 128 == 0 && kOffW1 % 16 == 0 && kOffBar % 8 == 0, "alignment");
@@ -98,9 +102,23 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {  // arrives on `bar
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-// one lane polls, the warp follows (__syncwarp orders the other lanes' accesses after lane 0's acquire)
+// (a suspend-time hint on try_wait measured slower: wake-ups come later)
+__device__ __forceinline__ bool try_wait_sleep(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void wait_sleep(uint64_t* bar, uint32_t parity) {
+    while (!try_wait_sleep(bar, parity)) {
+    }
+}
+// one lane waits, the warp follows (__syncwarp orders the other lanes' accesses after lane 0's acquire)
 __device__ __forceinline__ void warp_wait(uint64_t* bar, uint32_t parity) {
-    if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+    if ((threadIdx.x & 31) == 0) wait_sleep(bar, parity);
     __syncwarp();
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -142,8 +160,11 @@ __device__ __forceinline__ uint32_t pack_relu_h2(float lo, float hi) {  // {fp16
 //   drain warps (5-12, thread = accumulator lane = agent, two warps per lane quarter splitting the columns):
 //       D1[T % 2] -> relu -> fp16 -> C[T % 2] (tensor memory again: the A operand of the Dense partial); two rows into
 //       the next group D2 -> fc2 operand, four rows in D3 -> features in HBM.
-// Barrier parities: the n-th use of a full barrier waits parity n & 1; the n-th reuse of a slot waits its free barrier on
-// parity (n & 1) ^ 1 (passes at once for n = 0).
+// Hand-offs: mbarriers.  "Full" barriers (image row published, C written, weight block landed, ...) are waited on parity
+// n & 1 at their n-th use.  Everything the MMAs release -- accumulator full, image-row block / C buffer / weight block free,
+// D2 complete -- hangs on ONE tcgen05.commit per step into a ring of eight step barriers (a commit costs the issuing
+// thread ~40 cycles, five per step were 15 % of the kernel): whoever needs "the first block of step x is complete" waits
+// barrier x % 8 on parity (x / 8) & 1; no waiter is ever more than six steps from the MMA thread, so phases cannot alias.
 __global__ void __launch_bounds__(kThreads, 1) policy_features_kernel(const uint8_t* __restrict__ obs, long long M, const uint8_t* __restrict__ blob,
                                                                      float* __restrict__ out) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -157,8 +178,8 @@ __global__ void __launch_bounds__(kThreads, 1) policy_features_kernel(const uint
 
     if (tid == 0) {
         for (int b = 0; b < BAR_COUNT; ++b) {
-            const int count = ((b >= BAR_ROW_FULL && b < BAR_ROW_FREE) || (b >= BAR_OBS_FREE && b < BAR_STEP)) ? kProducerWarps
-                              : ((b >= BAR_D1_FREE && b < BAR_C_FREE) || b == BAR_X3) ? kDrainWarps : 1;
+            const int count = (b >= BAR_OBS_FREE && b < BAR_D1_FREE) ? kProducerWarps      // one arrival per producer warp
+                              : ((b >= BAR_D1_FREE && b < BAR_W1_FULL) || b == BAR_X3) ? kDrainWarps : 1;  // per drain warp; else TMA / commit
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bars + b)), "r"(count) : "memory");
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -213,17 +234,21 @@ __global__ void __launch_bounds__(kThreads, 1) policy_features_kernel(const uint
                     }
                 }
                 SSD_PT(2);
+                if (t == 0) SSD_TL(0, R, 0);
                 if (R > 0) publish(R - 1);
                 SSD_PT(3);
+                if (t == 0) SSD_TL(0, R, 3);
                 if (R >= RING) {  // the block's previous image row: last read by conv of its own output row (rows 13, 14: of row 12)
                     const uint32_t Rq = R - RING, iq = Rq % V, xs = (Rq / V) * CO + (iq < CO ? iq : CO - 1);
                     warp_wait(bars + BAR_STEP + xs % STEPS, (xs / STEPS) & 1);
                 }
                 SSD_PT(1);
+                if (t == 0) SSD_TL(0, R, 1);
                 tc_fence_after();
 #pragma unroll
                 for (int c = 0; c < ROWK / 2; c += 8) tmem_st8(tlane + kColRing + slot * (ROWK / 2) + c, h + c);
                 SSD_PT(5);
+                if (t == 0) SSD_TL(0, R, 2);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(bars + BAR_OBS_FREE + (gi & 1));  // this warp is done with the buffer of observation bytes
@@ -237,11 +262,7 @@ __global__ void __launch_bounds__(kThreads, 1) policy_features_kernel(const uint
         // per k-step, tensor-memory operands are base + 24 * ring slot + 8 * k-step.  elect.sync (not `lane == 0`) tells ptxas
         // the block runs on one lane, so the UTCHMMAs are issued without a per-instruction convergence loop.
         if (NT > 0 && elect_one()) {
-#ifdef SSD_EXP_N16  // timing experiment only (wrong results): how does the MMA time depend on N?
-            constexpr uint32_t kI1 = umma_idesc(GA, 16), kI2 = umma_idesc(GA, 16), kI3 = umma_idesc(GA, N3);
-#else
             constexpr uint32_t kI1 = umma_idesc(GA, N1), kI2 = umma_idesc(GA, N2), kI3 = umma_idesc(GA, N3);
-#endif
             constexpr uint32_t kDescHi = (128u >> 4) | 1u << 14;   // SBO = 128 bytes, descriptor version 1
             auto desc_lo = [](uint32_t saddr, uint32_t lbo) { return ((saddr & 0x3FFFFu) >> 4) | (lbo >> 4) << 16; };
             auto mk = [](uint32_t lo) { return static_cast<uint64_t>(kDescHi) << 32 | lo; };
@@ -254,12 +275,12 @@ __global__ void __launch_bounds__(kThreads, 1) policy_features_kernel(const uint
             SSD_PT_DECL;
             auto wait_rows = [&](uint32_t need) {  // image rows [0, need) of the CTA's sequence
                 while (rows_seen < need) {
-                    mbar_wait(bars + BAR_ROW_FULL + rows_seen % RING, (rows_seen / RING) & 1);
+                    wait_sleep(bars + BAR_ROW_FULL + rows_seen % RING, (rows_seen / RING) & 1);
                     ++rows_seen;
                 }
             };
             auto fc2 = [&](uint32_t gi) {
-                mbar_wait(bars + BAR_X3, gi & 1);
+                wait_sleep(bars + BAR_X3, gi & 1);
                 tc_fence_after();
 #pragma unroll
                 for (int ks = 0; ks < K3 / 16; ++ks) umma_f16_ts(tmem + kColD3, tmem + kColX3 + ks * 8, mk(b3_lo + ks * kB3Step), kI3, ks > 0);
@@ -275,11 +296,6 @@ __global__ void __launch_bounds__(kThreads, 1) policy_features_kernel(const uint
 #pragma unroll 1
             for (uint32_t s = 0; s < NT + 2; ++s) {
                 const bool has_e = s < NT, has_o = s + 1 < NT, has_d = s >= 2;
-#ifdef SSD_EXP_NO_DENSE  // timing experiment only (wrong results): the step without its five Dense MMAs
-#define SSD_DENSE_MMA(...)
-#else
-#define SSD_DENSE_MMA(...) umma_f16_ts(__VA_ARGS__)
-#endif
                 const bool last_e = i_e == CO - 1;
                 const uint32_t slot_o = (slot_e + (last_e ? 3 : 1)) % RING, row_o = row_e + (last_e ? 3 : 1);
                 // ---- first block: the six remaining MMAs of conv(s) (image rows i + 1, i + 2) interleaved with the Dense partial of
@@ -287,10 +303,11 @@ __global__ void __launch_bounds__(kThreads, 1) policy_features_kernel(const uint
                 if (has_e) wait_rows(row_e + 3);
                 SSD_PT(0);
                 if (has_d) {
-                    mbar_wait(bars + BAR_C_FULL + (s & 1), ((s - 2) >> 1) & 1);
-                    mbar_wait(bars + BAR_W1_FULL + (s - 2) % WRING, ((s - 2) / WRING) & 1);
+                    wait_sleep(bars + BAR_C_FULL + (s & 1), ((s - 2) >> 1) & 1);
+                    wait_sleep(bars + BAR_W1_FULL + (s - 2) % WRING, ((s - 2) / WRING) & 1);
                 }
                 SSD_PT(3);
+                SSD_TL(1, s, 0);
                 tc_fence_after();
                 {
                     const uint32_t d_e = tmem + ((s & 1) ? kColD1b : kColD1a);
@@ -299,32 +316,35 @@ __global__ void __launch_bounds__(kThreads, 1) policy_features_kernel(const uint
                     const uint32_t w_d = w1_lo + ((s - 2) % WRING) * kW1Buf;
                     const uint32_t acc_d = i_d != 0;
                     if (has_e) umma_f16_ts(d_e, a_e1, mk(b1_lo + 3 * kB1Step), kI1, 1);
-                    if (has_d) SSD_DENSE_MMA(d_d, a_d, mk(w_d), kI2, acc_d);
+                    if (has_d) umma_f16_ts(d_d, a_d, mk(w_d), kI2, acc_d);
                     if (has_e) umma_f16_ts(d_e, a_e1 + 8, mk(b1_lo + 4 * kB1Step), kI1, 1);
-                    if (has_d) SSD_DENSE_MMA(d_d, a_d + 8, mk(w_d + kW1Step), kI2, 1);
+                    if (has_d) umma_f16_ts(d_d, a_d + 8, mk(w_d + kW1Step), kI2, 1);
                     if (has_e) umma_f16_ts(d_e, a_e1 + 16, mk(b1_lo + 5 * kB1Step), kI1, 1);
-                    if (has_d) SSD_DENSE_MMA(d_d, a_d + 16, mk(w_d + 2 * kW1Step), kI2, 1);
+                    if (has_d) umma_f16_ts(d_d, a_d + 16, mk(w_d + 2 * kW1Step), kI2, 1);
                     if (has_e) umma_f16_ts(d_e, a_e2, mk(b1_lo + 6 * kB1Step), kI1, 1);
-                    if (has_d) SSD_DENSE_MMA(d_d, a_d + 24, mk(w_d + 3 * kW1Step), kI2, 1);
+                    if (has_d) umma_f16_ts(d_d, a_d + 24, mk(w_d + 3 * kW1Step), kI2, 1);
                     if (has_e) umma_f16_ts(d_e, a_e2 + 8, mk(b1_lo + 7 * kB1Step), kI1, 1);
-                    if (has_d) SSD_DENSE_MMA(d_d, a_d + 32, mk(w_d + 4 * kW1Step), kI2, 1);
+                    if (has_d) umma_f16_ts(d_d, a_d + 32, mk(w_d + 4 * kW1Step), kI2, 1);
                     if (has_e) umma_f16_ts(d_e, a_e2 + 16, mk(b1_lo + 8 * kB1Step), kI1, 1);
                 }
                 // ONE commit per step: conv(s) is complete (accumulator full, image row i -- and at the end of a group rows
                 // 13, 14 -- free) and so is the Dense partial of row s - 2 (C buffer and weight block free, D2 full after row 12)
                 umma_commit(bars + BAR_STEP + s % STEPS);
+                SSD_TL(1, s, 1);
                 SSD_PT(2);
                 if (s >= 4 && (s - 4) % CO == CO - 1) fc2((s - 4) / CO);  // the drain warps delivered its operand a step ago
                 // ---- second block: the first image row of conv(s + 1), into the accumulator of row s - 1 once it is drained
                 if (has_o) {
                     wait_rows(row_o + 1);
-                    mbar_wait(bars + BAR_D1_FREE + ((s + 1) & 1), (((s + 1) >> 1) & 1) ^ 1);
+                    wait_sleep(bars + BAR_D1_FREE + ((s + 1) & 1), (((s + 1) >> 1) & 1) ^ 1);
                     SSD_PT(1);
+                    SSD_TL(1, s, 2);
                     tc_fence_after();
                     const uint32_t d_o = tmem + ((s & 1) ? kColD1a : kColD1b), a_o0 = ring + slot_o * (ROWK / 2);
                     umma_f16_ts(d_o, a_o0, mk(b1_lo), kI1, 0);
                     umma_f16_ts(d_o, a_o0 + 8, mk(b1_lo + kB1Step), kI1, 1);
                     umma_f16_ts(d_o, a_o0 + 16, mk(b1_lo + 2 * kB1Step), kI1, 1);
+                    SSD_TL(1, s, 3);
                 }
                 // shift the window of rows
                 i_d = i_d1; g_d = g_d1; i_d1 = i_e; g_d1 = g_e;
@@ -357,13 +377,14 @@ __global__ void __launch_bounds__(kThreads, 1) policy_features_kernel(const uint
                 const uint32_t ws = T % WRING;
                 while (T >= WRING && !mbar_try_wait(bars + BAR_STEP + (T - 4) % STEPS, ((T - 4) / STEPS) & 1)) {  // Dense partial of row T - 6
                     if (next_obs < n_my && mbar_try_wait(bars + BAR_OBS_FREE + (next_obs & 1), ((next_obs - 2) >> 1) & 1)) load_obs(next_obs++);
+                    __nanosleep(200);
                 }
                 mbar_expect_tx(bars + BAR_W1_FULL + ws, kB2Bytes);
                 bulk_g2s(smem + kOffW1 + ws * kB2Bytes, blob + kHeadBytes + (T % CO) * kB2Bytes, kB2Bytes, bars + BAR_W1_FULL + ws);
                 if (next_obs < n_my && mbar_try_wait(bars + BAR_OBS_FREE + (next_obs & 1), ((next_obs - 2) >> 1) & 1)) load_obs(next_obs++);
             }
             while (next_obs < n_my) {
-                mbar_wait(bars + BAR_OBS_FREE + (next_obs & 1), ((next_obs - 2) >> 1) & 1);
+                wait_sleep(bars + BAR_OBS_FREE + (next_obs & 1), ((next_obs - 2) >> 1) & 1);
                 load_obs(next_obs++);
             }
         }
@@ -414,6 +435,7 @@ __global__ void __launch_bounds__(kThreads, 1) policy_features_kernel(const uint
             const uint32_t b = T & 1;
             warp_wait(bars + BAR_STEP + T % STEPS, (T / STEPS) & 1);   // conv(T) complete; so is the Dense partial that read C[b]
             SSD_PT(0);
+            if (tid == 32 * kDrainWarp0) SSD_TL(2, T, 0);
             tc_fence_after();
             uint32_t acc[kDrainSplit];
             const uint32_t src = trow + (b ? kColD1b : kColD1a) + col0;
@@ -425,6 +447,7 @@ __global__ void __launch_bounds__(kThreads, 1) policy_features_kernel(const uint
             __syncwarp();
             if (lane == 0) mbar_arrive(bars + BAR_D1_FREE + b);
             SSD_PT(1);
+            if (tid == 32 * kDrainWarp0) SSD_TL(2, T, 1);
             uint32_t h[kDrainSplit / 2];   // C = fp16(relu(D1 / 255 + cb))
 #pragma unroll
             for (int c = 0; c < kDrainSplit; c += 2)
@@ -440,9 +463,11 @@ __global__ void __launch_bounds__(kThreads, 1) policy_features_kernel(const uint
             __syncwarp();
             if (lane == 0) mbar_arrive(bars + BAR_C_FULL + b);
             SSD_PT(4);
+            if (tid == 32 * kDrainWarp0) SSD_TL(2, T, 2);
             if (T >= 2 && (T - 2) % CO == CO - 1) tail1((T - 2) / CO);
             if (T >= 4 && (T - 4) % CO == CO - 1) tail2((T - 4) / CO);
             SSD_PT(5);
+            if (tid == 32 * kDrainWarp0) SSD_TL(2, T, 3);
         }
         if (n_my > 0) {
             tail1(n_my - 1);
@@ -453,6 +478,51 @@ __global__ void __launch_bounds__(kThreads, 1) policy_features_kernel(const uint
     tc_fence_before();
     __syncthreads();
     if (warp == kMmaWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+}
+
+// LSTM cell update after the gate GEMM (conv_to_fcnet_v2.py:68-80, Keras gate order i, f, c~, o):
+//   c' = sigmoid(f) * c + sigmoid(i) * tanh(c~),  h' = sigmoid(o) * tanh(c').
+// One pass over HBM: bf16 gate pre-activations [M][4u] (+ fp32 bias) and c in, c', h' (fp32) and h' (bf16, the next GEMM
+// operand) out.  A thread owns eight consecutive units of one agent.
+__global__ void __launch_bounds__(256) lstm_cell_kernel(const uint4* __restrict__ gates, const float* __restrict__ bias, const float4* __restrict__ c_prev,
+                                                        float4* __restrict__ c_out, float4* __restrict__ h_out, uint4* __restrict__ h16_out, long long M, int units) {
+    const int per_row = units >> 3;
+    const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (idx >= M * per_row) return;
+    const long long m = idx / per_row;
+    const int j8 = static_cast<int>(idx - m * per_row);
+    float g[4][8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint4 v = gates[(m * 4 + q) * per_row + j8];
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        const float* b = bias + q * units + j8 * 8;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {  // bf16 -> fp32 is a shift
+            g[q][2 * e] = __uint_as_float(w[e] << 16) + b[2 * e];
+            g[q][2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u) + b[2 * e + 1];
+        }
+    }
+    const float4 c0 = c_prev[idx * 2], c1 = c_prev[idx * 2 + 1];
+    const float c[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+    float cn[8], hn[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const float si = 1.f / (1.f + __expf(-g[0][e])), sf = 1.f / (1.f + __expf(-g[1][e])), so = 1.f / (1.f + __expf(-g[3][e]));
+        cn[e] = sf * c[e] + si * tanhf(g[2][e]);
+        hn[e] = so * tanhf(cn[e]);
+    }
+    c_out[idx * 2] = make_float4(cn[0], cn[1], cn[2], cn[3]);
+    c_out[idx * 2 + 1] = make_float4(cn[4], cn[5], cn[6], cn[7]);
+    h_out[idx * 2] = make_float4(hn[0], hn[1], hn[2], hn[3]);
+    h_out[idx * 2 + 1] = make_float4(hn[4], hn[5], hn[6], hn[7]);
+    uint32_t p[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const __nv_bfloat162 v = __floats2bfloat162_rn(hn[2 * e], hn[2 * e + 1]);
+        p[e] = *reinterpret_cast<const uint32_t*>(&v);
+    }
+    h16_out[idx] = make_uint4(p[0], p[1], p[2], p[3]);
 }
 
 }  // namespace policy
@@ -528,6 +598,24 @@ int ssd_policy_features(ssd_policy_t p, const uint8_t* obs, int64_t num_agents, 
     const long long groups = (num_agents + GA - 1) / GA;
     const int grid = static_cast<int>(groups < p->sms ? groups : p->sms);
     policy_features_kernel<<<grid, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(obs, num_agents, p->d_blob, features);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return ssd::set_error(SSD_ERR_CUDA, cudaGetErrorString(e));
+    return SSD_OK;
+}
+
+int ssd_policy_lstm_cell(const void* gates_bf16, const float* bias, const float* c_prev, float* c_out, float* h_out, void* h_bf16_out,
+                         int64_t num_agents, int units, void* stream) {
+    using namespace ssd::policy;
+    if (!gates_bf16 || !bias || !c_prev || !c_out || !h_out || !h_bf16_out || num_agents < 0) return ssd::set_error(SSD_ERR_INVALID, "bad argument");
+    if (units <= 0 || units % 8 != 0) return ssd::set_error(SSD_ERR_INVALID, "units must be a positive multiple of 8");
+    const void* ptrs[6] = {gates_bf16, bias, c_prev, c_out, h_out, h_bf16_out};
+    for (const void* q : ptrs)
+        if (reinterpret_cast<uintptr_t>(q) % 16 != 0) return ssd::set_error(SSD_ERR_INVALID, "pointers must be 16-byte aligned");
+    if (num_agents == 0) return SSD_OK;
+    const long long n = num_agents * (units / 8);
+    lstm_cell_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint4*>(gates_bf16), bias, reinterpret_cast<const float4*>(c_prev), reinterpret_cast<float4*>(c_out),
+        reinterpret_cast<float4*>(h_out), static_cast<uint4*>(h_bf16_out), num_agents, units);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return ssd::set_error(SSD_ERR_CUDA, cudaGetErrorString(e));
     return SSD_OK;

@@ -5,8 +5,9 @@ models/conv_to_fcnet_v2.py (ConvToFCNetv2) evaluated on uint8 observations that 
             (conv_to_fcnet_v2.py:36-66, filters as train_baseline.py:104 configures them) -- ONE fused tcgen05 kernel
             behind the C ABI (`ssd_policy_features`, csrc/ssd_policy.cu) that reads the uint8 [B, N, 15, 15, 3] tensor
             `BatchedSSDEnv.step` wrote and folds the (x - 128) / 255 of map_env.py:199 into the first layer;
-    head    LSTM(cell_size) -> logits / value (conv_to_fcnet_v2.py:68-92): plain GEMMs on [M, 32] and [M, cell] --
-            torch / cuBLAS calls here, library plumbing.
+    head    LSTM(cell_size) -> logits / value (conv_to_fcnet_v2.py:68-92): the gate and head GEMMs on [M, 32] / [M, cell] are
+            plain library GEMMs (torch / cuBLAS, bf16 operands, fp32 accumulation); the elementwise cell update between
+            them is one fused pass (`ssd_policy_lstm_cell`).
 
 Weights are numpy fp32 arrays in the Keras layouts (conv kernel [kh, kw, in, out], dense kernels [in, out], LSTM kernel
 [in, 4u] / recurrent kernel [u, 4u] / bias [4u] with gates ordered i, f, c, o), so a checkpoint of the reference model
@@ -68,8 +69,14 @@ class ConvToFCNet(object):
         _lib.check(_lib.lib.ssd_policy_create(VIEW_RADIUS, self.device.index or 0, ptr(w["conv_w"]), ptr(w["conv_b"]), ptr(w["fc1_w"]),
                                               ptr(w["fc1_b"]), ptr(w["fc2_w"]), ptr(w["fc2_b"]), C.byref(self._h)))
         self.cell_size = w["lstm_u"].shape[0] if "lstm_u" in w else 0
-        self._head = {k: torch.from_numpy(w[k]).to(self.device) for k in
-                      ("lstm_w", "lstm_u", "lstm_b", "logits_w", "logits_b", "value_w", "value_b") if k in w}
+        self._head = {}
+        if self.cell_size:
+            if self.cell_size % 8:
+                raise ValueError("cell_size must be a multiple of 8")
+            dev = lambda k, dt: torch.from_numpy(w[k]).to(self.device, dtype=dt).contiguous()
+            self._head = {"lstm_w": dev("lstm_w", torch.bfloat16), "lstm_u": dev("lstm_u", torch.bfloat16), "lstm_b": dev("lstm_b", torch.float32),
+                          "logits_w": dev("logits_w", torch.bfloat16), "logits_b": dev("logits_b", torch.float32),
+                          "value_w": dev("value_w", torch.bfloat16), "value_b": dev("value_b", torch.float32)}
 
     def close(self):
         if self._h:
@@ -99,16 +106,20 @@ class ConvToFCNet(object):
         return z, z.clone()
 
     def forward(self, obs, h, c):
-        """-> (logits [M, A], value [M], h', c'): the trunk kernel, then the LSTM cell and the heads as library GEMMs."""
-        x = self.features(obs)
+        """-> (logits [M, A], value [M], h', c'), all float32: the trunk kernel, the gate GEMMs (cuBLAS, bf16 x bf16 -> fp32
+        accumulate), the fused cell update, the head GEMMs."""
         hd = self._head
-        gates = torch.addmm(hd["lstm_b"], x, hd["lstm_w"]).addmm_(h, hd["lstm_u"])
-        i, f, g, o = gates.chunk(4, dim=1)   # Keras gate order
-        c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
-        h = torch.sigmoid(o) * torch.tanh(c)
-        logits = torch.addmm(hd["logits_b"], h, hd["logits_w"])
-        value = torch.addmm(hd["value_b"], h, hd["value_w"]).squeeze(1)
-        return logits, value, h, c
+        x16 = self.features(obs).to(torch.bfloat16)
+        gates = torch.mm(x16, hd["lstm_w"]).addmm_(h.to(torch.bfloat16), hd["lstm_u"])   # bf16 [M, 4u], bias added in the cell kernel
+        m, u = h.shape
+        c_new, h_new = torch.empty_like(c), torch.empty_like(h)
+        h16 = torch.empty((m, u), dtype=torch.bfloat16, device=self.device)
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        p = lambda t: C.c_void_p(t.data_ptr())
+        _lib.check(_lib.lib.ssd_policy_lstm_cell(p(gates), p(hd["lstm_b"]), p(c.contiguous()), p(c_new), p(h_new), p(h16), m, u, stream))
+        logits = torch.mm(h16, hd["logits_w"]).float() + hd["logits_b"]
+        value = (torch.mm(h16, hd["value_w"]).float() + hd["value_b"]).squeeze(1)
+        return logits, value, h_new, c_new
 
     def act(self, obs, h, c, generator=None):
         """Sample int8 actions [M] on the device for the next `BatchedSSDEnv.step`."""

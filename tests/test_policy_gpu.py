@@ -39,6 +39,38 @@ def test_trunk_matches_fp32_reference_random_pixels(m):
     assert want.abs().max().item() > 0.1   # the comparison is not vacuous
 
 
+def _reference_forward(w, obs, h, c):
+    """conv_to_fcnet_v2.py:68-92 in fp32: Keras LSTM cell (gates i, f, c~, o; sigmoid recurrent activation), linear heads."""
+    t = lambda k: torch.from_numpy(w[k]).to(obs.device)
+    x = _reference_features(w, obs)
+    gates = x @ t("lstm_w") + h @ t("lstm_u") + t("lstm_b")
+    i, f, g, o = gates.chunk(4, dim=1)
+    c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
+    h = torch.sigmoid(o) * torch.tanh(c)
+    return h @ t("logits_w") + t("logits_b"), (h @ t("value_w") + t("value_b")).squeeze(1), h, c
+
+
+def test_forward_matches_fp32_reference_over_steps():
+    """Three recurrent steps: bf16 GEMM operands and the fused cell update against the fp32 reference carried alongside."""
+    from sequential_social_dilemma_games_b200 import policy
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    m = 1000
+    w = policy.random_weights(num_outputs=9, cell_size=128, seed=11)
+    net = policy.ConvToFCNet(w)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    h, c = net.initial_state(m)
+    hr, cr = h.clone(), c.clone()
+    for _ in range(3):
+        obs = torch.randint(0, 256, (m, 15, 15, 3), dtype=torch.uint8, device="cuda", generator=g)
+        logits, value, h, c = net.forward(obs, h, c)
+        lr, vr, hr, cr = _reference_forward(w, obs, hr, cr)
+        assert logits.shape == (m, 9) and value.shape == (m,)
+        for got, want in ((logits, lr), (value, vr), (h, hr), (c, cr)):
+            assert torch.allclose(got, want, atol=3e-2, rtol=3e-2), (got - want).abs().max().item()   # bf16 operands: 8 significant bits
+    net.close()
+
+
 def test_trunk_on_env_observations_and_rollout_loop():
     """Observations straight from the step kernel; a short closed loop env -> policy -> env with no host round trip."""
     from sequential_social_dilemma_games_b200 import policy
