@@ -246,6 +246,35 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(tot)  # the only collective: end-of-run stats
     clocks = clk.summary()
 
+    # informational: the same step with its consumer on the device (policy forward pass + sampled actions, no PCIe).  Not
+    # the contract's e2e; harvest r = 7 only (the trunk kernel is built for 15x15 observations); never fatal.
+    on_device = None
+    if rank == 0 and args.view == 7 and not args.no_e2e:
+        try:
+            from sequential_social_dilemma_games_b200 import policy
+            net = policy.ConvToFCNet(policy.random_weights(num_outputs=cfg.num_actions, seed=0), device=dev)
+            st = {"obs": env.reset(), "hc": net.initial_state(B * N)}
+
+            def loop_step():
+                a, _, h, c = net.act(st["obs"].reshape(-1, 15, 15, 3), *st["hc"])
+                st["hc"] = (h, c)
+                st["obs"], _ = env.step(a.reshape(B, N))
+            for _ in range(5):
+                loop_step()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(20):
+                loop_step()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ms_loop = e0.elapsed_time(e1) / 20
+            on_device = {"value": B * N / (ms_loop * 1e-3), "unit": UNIT, "ms_per_step": ms_loop, "n_gpus": 1,
+                         "what": "env.step + ConvToFCNet.act (tcgen05 trunk, cuBLAS LSTM/head GEMMs, fused cell, sampled actions), "
+                                 "observations and actions never leave the device; random-init weights"}
+            net.close()
+        except Exception as exc:  # noqa: BLE001
+            on_device = {"unavailable": repr(exc)[:200]}
+
     if rank == 0:
         peaks, peak_src = {}, "fallback 6650 GB/s (B200_PROFILING.md)"
         try:
@@ -277,6 +306,8 @@ def run_ours(args, rank, world, local_rank):
                              "algorithmic_bytes_per_env_step": alg, "units_per_launch": B},
                 "clocks": clocks, "gpu_launches": launches, "e2e": e2e,
                 "totals": {"env_steps": int(tot[0]), "reward_sum": int(tot[1]), "apples_eaten": int(tot[2]), "hits": int(tot[3])}}
+        if on_device is not None:
+            line["on_device_loop"] = on_device
         if world == 1 and not args.no_cpu_baseline:
             rate, cores, sample, _ = cpu_port_rate(args, 12.0)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
