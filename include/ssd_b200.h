@@ -189,7 +189,18 @@ int ssd_policy_create(int view_radius, int device, const float* conv_w, const fl
  * features dev f32[num_agents][32] (16-byte aligned). */
 int ssd_policy_features(ssd_policy_t p, const uint8_t* obs, int64_t num_agents, float* features, void* stream);
 void ssd_policy_destroy(ssd_policy_t p);
-/* LSTM cell update after the gate GEMM (conv_to_fcnet_v2.py:68-80; Keras gate order i, f, c~, o; sigmoid recurrent
+/* LSTM(128) + logits / value heads + action sampling in ONE kernel (conv_to_fcnet_v2.py:68-92; Keras gate order i, f, c~, o,
+ * sigmoid recurrent activation).  ssd_policy_set_head packs HOST fp32 weights in the Keras layouts: lstm_w [32][4u],
+ * lstm_u [u][4u], lstm_b [4u], logits_w [u][num_outputs], logits_b, value_w [u][1], value_b [1]; units must be 128,
+ * num_outputs 1..15.  ssd_policy_lstm_heads: features dev f32[M][32] (ssd_policy_features), h_in / c_in / h_out / c_out dev
+ * f32[M][128] (out may alias in), logits dev f32[M][num_outputs], value dev f32[M], actions dev i8[M] or NULL: a sample
+ * of softmax(logits) by the Gumbel-max rule on Philox4x32-10 (key = seed, counter words = agent index, `counter`) -- pass a
+ * fresh `counter` every step.  fp16 GEMM operands, fp32 accumulation and state. */
+int ssd_policy_set_head(ssd_policy_t p, int units, int num_outputs, const float* lstm_w, const float* lstm_u, const float* lstm_b,
+                        const float* logits_w, const float* logits_b, const float* value_w, const float* value_b);
+int ssd_policy_lstm_heads(ssd_policy_t p, const float* features, const float* h_in, const float* c_in, float* h_out, float* c_out, float* logits,
+                          float* value, int8_t* actions, int64_t num_agents, uint64_t seed, uint32_t counter, void* stream);
+/* The unfused alternative for other cell sizes: LSTM cell update after the gate GEMM (conv_to_fcnet_v2.py:68-80; Keras gate order i, f, c~, o; sigmoid recurrent
  * activation): gates dev bf16[num_agents][4*units] = x W + h U without the bias, bias dev f32[4*units],
  * c_prev / c_out / h_out dev f32[num_agents][units] (c_out may alias c_prev), h_bf16_out dev bf16[num_agents][units]
  * (the operand of the next step's GEMM).  One pass over HBM; all pointers 16-byte aligned, units a multiple of 8. */

@@ -50,7 +50,18 @@ def main():
           (flop_useful / ms / 1e9, flop_issued / ms / 1e9, peaks.get("bf16_tflops", peaks)))
     h, c = net.initial_state(M)
     ms_fwd = timed(lambda: net.forward(flat, h, c), 20)
-    print("forward (trunk + LSTM + heads via cuBLAS): %.4f ms" % ms_fwd)
+    print("forward (trunk + fused LSTM/heads kernel): %.4f ms" % ms_fwd)
+    feats = net.features(flat)
+    import ctypes as C
+    from sequential_social_dilemma_games_b200 import _lib
+    hn, cn = torch.empty_like(h), torch.empty_like(c)
+    lg = torch.empty((M, 8), device="cuda"); vl = torch.empty((M,), device="cuda"); ac = torch.empty((M,), dtype=torch.int8, device="cuda")
+    p = lambda t: C.c_void_p(t.data_ptr())
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    ms_head = timed(lambda: _lib.check(_lib.lib.ssd_policy_lstm_heads(net._h, p(feats), p(h), p(c), p(hn), p(cn), p(lg), p(vl), p(ac), M, 1, 2, st)), 20)
+    print("  ssd_policy_lstm_heads alone: %.4f ms (%.0f GB/s of its 2.3 KB per agent)" % (ms_head, M * 2340 / ms_head / 1e6))
+    ms_unf = timed(lambda: net.forward_unfused(flat, h, c), 20)
+    print("forward, unfused route (cuBLAS GEMMs + cell kernel): %.4f ms" % ms_unf)
     state = {"obs": obs, "h": h, "c": c}
 
     def loop():

@@ -5,9 +5,11 @@ models/conv_to_fcnet_v2.py (ConvToFCNetv2) evaluated on uint8 observations that 
             (conv_to_fcnet_v2.py:36-66, filters as train_baseline.py:104 configures them) -- ONE fused tcgen05 kernel
             behind the C ABI (`ssd_policy_features`, csrc/ssd_policy.cu) that reads the uint8 [B, N, 15, 15, 3] tensor
             `BatchedSSDEnv.step` wrote and folds the (x - 128) / 255 of map_env.py:199 into the first layer;
-    head    LSTM(cell_size) -> logits / value (conv_to_fcnet_v2.py:68-92): the gate and head GEMMs on [M, 32] / [M, cell] are
-            plain library GEMMs (torch / cuBLAS, bf16 operands, fp32 accumulation); the elementwise cell update between
-            them is one fused pass (`ssd_policy_lstm_cell`).
+    head    LSTM(cell_size) -> logits / value (conv_to_fcnet_v2.py:68-92).  For the reference's cell_size 128 this is a second
+            fused tcgen05 kernel (`ssd_policy_lstm_heads`: gate GEMM in tensor memory, cell update, head GEMM and -- in
+            `act` -- Gumbel-max sampling of the action, one pass over the recurrent state).  Other cell sizes take the
+            unfused route: library GEMMs (torch / cuBLAS, bf16 operands) around the one-pass cell update
+            `ssd_policy_lstm_cell`.
 
 Weights are numpy fp32 arrays in the Keras layouts (conv kernel [kh, kw, in, out], dense kernels [in, out], LSTM kernel
 [in, 4u] / recurrent kernel [u, 4u] / bias [4u] with gates ordered i, f, c, o), so a checkpoint of the reference model
@@ -69,7 +71,14 @@ class ConvToFCNet(object):
         _lib.check(_lib.lib.ssd_policy_create(VIEW_RADIUS, self.device.index or 0, ptr(w["conv_w"]), ptr(w["conv_b"]), ptr(w["fc1_w"]),
                                               ptr(w["fc1_b"]), ptr(w["fc2_w"]), ptr(w["fc2_b"]), C.byref(self._h)))
         self.cell_size = w["lstm_u"].shape[0] if "lstm_u" in w else 0
+        self.num_outputs = w["logits_w"].shape[1] if "logits_w" in w else 0
         self._head = {}
+        self._fused_head = False
+        self._sample_seed, self._sample_counter = 0, 0
+        if self.cell_size == 128 and 1 <= self.num_outputs <= 15:
+            _lib.check(_lib.lib.ssd_policy_set_head(self._h, self.cell_size, self.num_outputs, ptr(w["lstm_w"]), ptr(w["lstm_u"]), ptr(w["lstm_b"]),
+                                                    ptr(w["logits_w"]), ptr(w["logits_b"]), ptr(w["value_w"]), ptr(w["value_b"])))
+            self._fused_head = True
         if self.cell_size:
             if self.cell_size % 8:
                 raise ValueError("cell_size must be a multiple of 8")
@@ -105,9 +114,35 @@ class ConvToFCNet(object):
         z = torch.zeros((m, self.cell_size), dtype=torch.float32, device=self.device)
         return z, z.clone()
 
+    def seed_sampling(self, seed):
+        """Key of the Philox streams `act` samples from (counter = number of `act` calls since)."""
+        self._sample_seed, self._sample_counter = int(seed) & (2 ** 64 - 1), 0
+
+    def _fused(self, obs, h, c, sample):
+        x = self.features(obs)
+        m = x.shape[0]
+        h, c = h.contiguous(), c.contiguous()
+        h_new, c_new = torch.empty_like(h), torch.empty_like(c)
+        logits = torch.empty((m, self.num_outputs), dtype=torch.float32, device=self.device)
+        value = torch.empty((m,), dtype=torch.float32, device=self.device)
+        actions = torch.empty((m,), dtype=torch.int8, device=self.device) if sample else None
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        p = lambda t: C.c_void_p(t.data_ptr() if t is not None else None)
+        _lib.check(_lib.lib.ssd_policy_lstm_heads(self._h, p(x), p(h), p(c), p(h_new), p(c_new), p(logits), p(value), p(actions), m,
+                                                  self._sample_seed, self._sample_counter & 0xFFFFFFFF, stream))
+        if sample:
+            self._sample_counter += 1
+        return logits, value, h_new, c_new, actions
+
     def forward(self, obs, h, c):
-        """-> (logits [M, A], value [M], h', c'), all float32: the trunk kernel, the gate GEMMs (cuBLAS, bf16 x bf16 -> fp32
-        accumulate), the fused cell update, the head GEMMs."""
+        """-> (logits [M, A], value [M], h', c'), all float32."""
+        if not self._fused_head:
+            return self.forward_unfused(obs, h, c)
+        return self._fused(obs, h, c, sample=False)[:4]
+
+    def forward_unfused(self, obs, h, c):
+        """The same forward pass with library GEMMs: the trunk kernel, the gate GEMMs (cuBLAS, bf16 x bf16 -> fp32 accumulate), the
+        one-pass cell update, the head GEMMs.  Any cell size that is a multiple of 8."""
         hd = self._head
         x16 = self.features(obs).to(torch.bfloat16)
         gates = torch.mm(x16, hd["lstm_w"]).addmm_(h.to(torch.bfloat16), hd["lstm_u"])   # bf16 [M, 4u], bias added in the cell kernel
@@ -122,7 +157,11 @@ class ConvToFCNet(object):
         return logits, value, h_new, c_new
 
     def act(self, obs, h, c, generator=None):
-        """Sample int8 actions [M] on the device for the next `BatchedSSDEnv.step`."""
+        """Sample int8 actions [M] on the device for the next `BatchedSSDEnv.step`: inside the fused kernel (Philox streams,
+        see `seed_sampling`), or with torch.multinomial (`generator`) on the unfused route."""
+        if self._fused_head and generator is None:
+            logits, value, h, c, a = self._fused(obs, h, c, sample=True)
+            return a, value, h, c
         logits, value, h, c = self.forward(obs, h, c)
         a = torch.multinomial(torch.softmax(logits, dim=1), 1, generator=generator).squeeze(1).to(torch.int8)
         return a, value, h, c

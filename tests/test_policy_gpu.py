@@ -61,13 +61,43 @@ def test_forward_matches_fp32_reference_over_steps():
     g = torch.Generator(device="cuda").manual_seed(5)
     h, c = net.initial_state(m)
     hr, cr = h.clone(), c.clone()
+    hu, cu = h.clone(), c.clone()
     for _ in range(3):
         obs = torch.randint(0, 256, (m, 15, 15, 3), dtype=torch.uint8, device="cuda", generator=g)
-        logits, value, h, c = net.forward(obs, h, c)
+        logits, value, h, c = net.forward(obs, h, c)            # fused tcgen05 LSTM + heads (cell_size 128)
+        l2, v2, h2, c2 = net.forward_unfused(obs, hu, cu)       # library GEMMs + one-pass cell update
+        hu, cu = h2, c2
         lr, vr, hr, cr = _reference_forward(w, obs, hr, cr)
         assert logits.shape == (m, 9) and value.shape == (m,)
         for got, want in ((logits, lr), (value, vr), (h, hr), (c, cr)):
+            assert torch.allclose(got, want, atol=2e-2, rtol=2e-2), (got - want).abs().max().item()   # fp16 operands, fp32 accumulation
+        for got, want in ((l2, lr), (v2, vr), (h2, hr), (c2, cr)):
             assert torch.allclose(got, want, atol=3e-2, rtol=3e-2), (got - want).abs().max().item()   # bf16 operands: 8 significant bits
+    net.close()
+
+
+def test_fused_sampling_follows_softmax():
+    """`act` samples inside the kernel (Gumbel-max on Philox): frequencies over many agents with IDENTICAL inputs must match
+    softmax(logits); a different counter gives different draws, the same (seed, counter) the same ones."""
+    from sequential_social_dilemma_games_b200 import policy
+    m = 200000
+    w = policy.random_weights(num_outputs=8, cell_size=128, seed=2)
+    w["logits_w"] = (w["logits_w"] * 4).astype(np.float32)      # spread the probabilities
+    net = policy.ConvToFCNet(w)
+    one = torch.randint(0, 256, (1, 15, 15, 3), dtype=torch.uint8, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+    obs = one.expand(m, 15, 15, 3).contiguous()
+    h, c = net.initial_state(m)
+    net.seed_sampling(77)
+    a1, value, h1, c1 = net.act(obs, h, c)
+    a2, _, _, _ = net.act(obs, h, c)
+    net.seed_sampling(77)
+    a3, _, _, _ = net.act(obs, h, c)
+    logits = net.forward(obs[:1], h[:1], c[:1])[0][0]
+    p = torch.softmax(logits.double(), 0).cpu().numpy()
+    assert a1.dtype == torch.int8 and int(a1.min()) >= 0 and int(a1.max()) < 8
+    freq = np.bincount(a1.cpu().numpy().astype(np.int64), minlength=8) / m
+    assert np.abs(freq - p).max() < 5 * np.sqrt(p.max() / m) + 1e-3, (freq, p)   # five sigma of a binomial frequency
+    assert torch.equal(a1, a3) and not torch.equal(a1, a2)
     net.close()
 
 
