@@ -20,6 +20,17 @@
 #include "ssd_policy.h"
 #include "ssd_umma.cuh"
 
+#ifdef SSD_POLICY_TIMING  // profiles/micro/policy_head_timing.cu: cycles per phase of thread 0 of CTA 0
+__device__ unsigned long long g_head_cycles[8];
+#define SSD_HT_DECL unsigned long long ht_[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long ht_t = clock64()
+#define SSD_HT(slot) do { const long long n_ = clock64(); ht_[slot] += n_ - ht_t; ht_t = n_; } while (0)
+#define SSD_HT_FLUSH do { if (blockIdx.x == 0 && threadIdx.x == 0) for (int q_ = 0; q_ < 8; ++q_) g_head_cycles[q_] = ht_[q_]; } while (0)
+#else
+#define SSD_HT_DECL
+#define SSD_HT(slot)
+#define SSD_HT_FLUSH
+#endif
+
 namespace ssd {
 namespace policy_head {
 using namespace ssd::umma;
@@ -41,8 +52,14 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
     const __half2 v = __floats2half2_rn(lo, hi);
     return *reinterpret_cast<const uint32_t*>(&v);
 }
-__device__ __forceinline__ float sigmoidf(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
-__device__ __forceinline__ float tanh_fast(float x) { return 2.f * sigmoidf(2.f * x) - 1.f; }   // |error| ~1e-6 against tanhf: far inside the fp16 operand rounding
+// one MUFU op each (tanh.approx.f32, ~2^-11 relative error: below the fp16 rounding of the GEMM operands); the cell update
+// is transcendental-bound: 5 per unit, 640 per agent
+__device__ __forceinline__ float tanh_fast(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(tanh_fast(0.5f * x), 0.5f, 0.5f); }
 
 __global__ void __launch_bounds__(kThreads, 1)
 lstm_heads_kernel(const float* __restrict__ feat, const float* h_in, const float* c_in, float* h_out, float* c_out, float* __restrict__ logits,
@@ -66,25 +83,38 @@ lstm_heads_kernel(const float* __restrict__ feat, const float* h_in, const float
     uint32_t parity = 0;
 
     const long long n_groups = (M + GA - 1) / GA;
+    SSD_HT_DECL;
     for (long long g = blockIdx.x; g < n_groups; g += gridDim.x) {
         const long long a0 = g * GA;
         const int rem = static_cast<int>(M - a0 < GA ? M - a0 : GA);
-        {   // A = fp16([features | h]): thread (row, half of the 20 eight-element chunks)
-            const int row = tid & (GA - 1), c0 = (tid >> 7) * (K / 16);
-            const bool live = row < rem;
+        {   // A = fp16([features | h]).  HBM is read in full 128-byte row segments (eight lanes x 16 bytes; a thread walking its
+            // own row in 32-byte steps reached 2.3 TB/s); two lanes then own one 8-element operand chunk and store 8 bytes each.
+            // All loads before the stores: the compiler keeps a global load below a store through a generic pointer.
+            const int seg = tid & 7, r8 = tid >> 3;          // 32 rows per pass, 4 passes
+            float4 vx[4], vh[4][4];
 #pragma unroll
-            for (int j = 0; j < K / 16; ++j) {
-                const int kc = c0 + j;
-                const float* src = kc < KX / 8 ? feat + (a0 + row) * KX + kc * 8 : h_in + (a0 + row) * U + (kc - KX / 8) * 8;
-                float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-                if (live) { v0 = reinterpret_cast<const float4*>(src)[0]; v1 = reinterpret_cast<const float4*>(src)[1]; }
-                *reinterpret_cast<uint4*>(smem + kOffA + kc * (GA * 16) + row * 16) =
-                    make_uint4(pack_h2(v0.x, v0.y), pack_h2(v0.z, v0.w), pack_h2(v1.x, v1.y), pack_h2(v1.z, v1.w));
+            for (int ps = 0; ps < 4; ++ps) {
+                const int row = ps * 32 + r8;
+                const bool live = row < rem;
+                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                vx[ps] = live ? __ldcs(reinterpret_cast<const float4*>(feat + (a0 + row) * KX) + seg) : z;           // features: one 128-byte row
+#pragma unroll
+                for (int j = 0; j < 4; ++j) vh[ps][j] = live ? __ldcs(reinterpret_cast<const float4*>(h_in + (a0 + row) * U) + j * 8 + seg) : z;   // h: four
+            }
+#pragma unroll
+            for (int ps = 0; ps < 4; ++ps) {
+                const int row = ps * 32 + r8;
+                uint8_t* base = smem + kOffA + row * 16 + (seg & 1) * 8;   // elements 4 seg .. 4 seg + 3 of a 32-element segment: chunk seg / 2
+                *reinterpret_cast<uint2*>(base + (seg >> 1) * (GA * 16)) = make_uint2(pack_h2(vx[ps].x, vx[ps].y), pack_h2(vx[ps].z, vx[ps].w));
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<uint2*>(base + (KX / 8 + j * 4 + (seg >> 1)) * (GA * 16)) = make_uint2(pack_h2(vh[ps][j].x, vh[ps][j].y), pack_h2(vh[ps][j].z, vh[ps][j].w));
             }
         }
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
+        SSD_HT(0);
         if (warp == 0 && elect_one()) {  // gates: two column halves of 256, k-steps interleaved
             tc_fence_after();
 #pragma unroll
@@ -98,10 +128,15 @@ lstm_heads_kernel(const float* __restrict__ feat, const float* h_in, const float
         mbar_wait(bar, parity);
         parity ^= 1;
         tc_fence_after();
+        SSD_HT(1);
         {   // cell update: thread = agent (TMEM lane), warps 0-3 take units 0-63, warps 4-7 units 64-127
             const int q = warp & 3, row = q * 32 + lane, uh = warp >> 2;
             const uint32_t trow = tmem + (static_cast<uint32_t>(q * 32) << 16);
             const bool live = row < rem;
+            const float4* cp = reinterpret_cast<const float4*>(c_in + (a0 + row) * U + uh * 64);
+            float4 cn[4];   // the next 16 units of c, fetched one iteration ahead
+#pragma unroll
+            for (int e = 0; e < 4; ++e) cn[e] = live ? __ldcs(cp + e) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
             for (int ub = 0; ub < 4; ++ub) {
                 const int u0 = uh * 64 + ub * 16;
@@ -110,31 +145,26 @@ lstm_heads_kernel(const float* __restrict__ feat, const float* h_in, const float
                 tmem_ld16(trow + U + u0, gf);
                 tmem_ld16(trow + 2 * U + u0, gg);
                 tmem_ld16(trow + 3 * U + u0, go);
-                float c[16];
-                if (live) {
+                const float c[16] = {cn[0].x, cn[0].y, cn[0].z, cn[0].w, cn[1].x, cn[1].y, cn[1].z, cn[1].w,
+                                     cn[2].x, cn[2].y, cn[2].z, cn[2].w, cn[3].x, cn[3].y, cn[3].z, cn[3].w};
+                if (ub < 3) {
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float4 v = reinterpret_cast<const float4*>(c_in + (a0 + row) * U + u0)[e];
-                        c[4 * e] = v.x; c[4 * e + 1] = v.y; c[4 * e + 2] = v.z; c[4 * e + 3] = v.w;
-                    }
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) c[e] = 0.f;
+                    for (int e = 0; e < 4; ++e) cn[e] = live ? __ldcs(cp + 4 * (ub + 1) + e) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
                 tmem_ld_wait();
-                float hn[16];
+                float c2[16], hn[16];
 #pragma unroll
                 for (int e = 0; e < 16; ++e) {
-                    const float si = sigmoidf(__uint_as_float(gi[e]) + s_bias[u0 + e]), sf = sigmoidf(__uint_as_float(gf[e]) + s_bias[U + u0 + e]);
-                    const float so = sigmoidf(__uint_as_float(go[e]) + s_bias[3 * U + u0 + e]);
-                    c[e] = sf * c[e] + si * tanh_fast(__uint_as_float(gg[e]) + s_bias[2 * U + u0 + e]);
-                    hn[e] = so * tanh_fast(c[e]);
+                    const float si = sigmoid_fast(__uint_as_float(gi[e]) + s_bias[u0 + e]), sf = sigmoid_fast(__uint_as_float(gf[e]) + s_bias[U + u0 + e]);
+                    const float so = sigmoid_fast(__uint_as_float(go[e]) + s_bias[3 * U + u0 + e]);
+                    c2[e] = sf * c[e] + si * tanh_fast(__uint_as_float(gg[e]) + s_bias[2 * U + u0 + e]);
+                    hn[e] = so * tanh_fast(c2[e]);
                 }
                 if (live) {
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        reinterpret_cast<float4*>(c_out + (a0 + row) * U + u0)[e] = make_float4(c[4 * e], c[4 * e + 1], c[4 * e + 2], c[4 * e + 3]);
-                        reinterpret_cast<float4*>(h_out + (a0 + row) * U + u0)[e] = make_float4(hn[4 * e], hn[4 * e + 1], hn[4 * e + 2], hn[4 * e + 3]);
+                        __stcs(reinterpret_cast<float4*>(c_out + (a0 + row) * U + u0) + e, make_float4(c2[4 * e], c2[4 * e + 1], c2[4 * e + 2], c2[4 * e + 3]));
+                        __stcs(reinterpret_cast<float4*>(h_out + (a0 + row) * U + u0) + e, make_float4(hn[4 * e], hn[4 * e + 1], hn[4 * e + 2], hn[4 * e + 3]));
                     }
                 }
                 // fp16(h') is the A operand of the heads: the gate MMAs are complete, their operand buffer is free
@@ -146,6 +176,7 @@ lstm_heads_kernel(const float* __restrict__ feat, const float* h_in, const float
         fence_async_smem();
         tc_fence_before();
         __syncthreads();  // every gate column has been read: tensor memory can take the heads
+        SSD_HT(2);
         if (warp == 0 && elect_one()) {
             tc_fence_after();
 #pragma unroll
@@ -156,6 +187,7 @@ lstm_heads_kernel(const float* __restrict__ feat, const float* h_in, const float
         mbar_wait(bar, parity);
         parity ^= 1;
         tc_fence_after();
+        SSD_HT(3);
         if (warp < 4) {  // heads: logits, value, sampled action
             const int row = warp * 32 + lane;
             uint32_t y[16];
@@ -191,7 +223,9 @@ lstm_heads_kernel(const float* __restrict__ feat, const float* h_in, const float
         tc_fence_before();
         __syncthreads();  // tensor memory and the operand buffer are free for the next group
         tc_fence_after();
+        SSD_HT(4);
     }
+    SSD_HT_FLUSH;
     __syncthreads();
     if (warp == 0) tmem_free(tmem, 512);
 }
