@@ -269,7 +269,7 @@ def run_ours(args, rank, world, local_rank):
             torch.cuda.synchronize(dev)
             ms_loop = e0.elapsed_time(e1) / 20
             on_device = {"value": B * N / (ms_loop * 1e-3), "unit": UNIT, "ms_per_step": ms_loop, "n_gpus": 1,
-                         "what": "env.step + ConvToFCNet.act (tcgen05 trunk, cuBLAS LSTM/head GEMMs, fused cell, sampled actions), "
+                         "what": "env.step + ConvToFCNet.act (tcgen05 trunk kernel, tcgen05 LSTM + heads + Gumbel-max sampling kernel); "
                                  "observations and actions never leave the device; random-init weights"}
             net.close()
         except Exception as exc:  # noqa: BLE001
