@@ -192,8 +192,11 @@ void ssd_policy_destroy(ssd_policy_t p);
 /* LSTM(128) + logits / value heads + action sampling in ONE kernel (conv_to_fcnet_v2.py:68-92; Keras gate order i, f, c~, o,
  * sigmoid recurrent activation).  ssd_policy_set_head packs HOST fp32 weights in the Keras layouts: lstm_w [32][4u],
  * lstm_u [u][4u], lstm_b [4u], logits_w [u][num_outputs], logits_b, value_w [u][1], value_b [1]; units must be 128,
- * num_outputs 1..15.  ssd_policy_lstm_heads: features dev f32[M][32] (ssd_policy_features), h_in / c_in / h_out / c_out dev
- * f32[M][128] (out may alias in), logits dev f32[M][num_outputs], value dev f32[M], actions dev i8[M] or NULL: a sample
+ * num_outputs 1..15.  ssd_policy_lstm_heads: features dev f32[M][32] (ssd_policy_features); h_in / c_in / h_out / c_out dev
+ * f32 recurrent state in the library's TILED layout [ceil(M/128)][8][128][16]: element (agent m, unit u) at
+ * ((m / 128 * 8 + u / 16) * 128 + m % 128) * 16 + u % 16 -- buffers of ceil(M/128) * 16384 floats, zero for an initial
+ * state, out may alias in (a warp then moves 2 KB contiguous per access instead of 64-byte row pieces);
+ * logits dev f32[M][num_outputs], value dev f32[M], actions dev i8[M] or NULL: a sample
  * of softmax(logits) by the Gumbel-max rule on Philox4x32-10 (key = seed, counter words = agent index, `counter`) -- pass a
  * fresh `counter` every step.  fp16 GEMM operands, fp32 accumulation and state. */
 int ssd_policy_set_head(ssd_policy_t p, int units, int num_outputs, const float* lstm_w, const float* lstm_u, const float* lstm_b,

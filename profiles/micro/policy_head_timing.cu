@@ -15,9 +15,10 @@ int main(int argc, char** argv) {
     SsdPolicy pol; pol.device = 0; cudaDeviceGetAttribute(&pol.sms, cudaDevAttrMultiProcessorCount, 0);
     if (ssd_policy_set_head(&pol, 128, A, lw.data(), lu.data(), lb.data(), gw.data(), gb.data(), vw.data(), vb.data())) return 1;
     float *feat, *h, *c, *h2, *c2, *lg, *vl; int8_t* ac;
-    cudaMalloc(&feat, M * 32 * 4); cudaMalloc(&h, M * 512); cudaMalloc(&c, M * 512); cudaMalloc(&h2, M * 512); cudaMalloc(&c2, M * 512);
+    const long long Mp = (M + 127) / 128 * 128;
+    cudaMalloc(&feat, M * 32 * 4); cudaMalloc(&h, Mp * 512); cudaMalloc(&c, Mp * 512); cudaMalloc(&h2, Mp * 512); cudaMalloc(&c2, Mp * 512);
     cudaMalloc(&lg, M * A * 4); cudaMalloc(&vl, M * 4); cudaMalloc(&ac, M);
-    cudaMemset(feat, 0, M * 128); cudaMemset(h, 0, M * 512); cudaMemset(c, 0, M * 512);
+    cudaMemset(feat, 0, M * 128); cudaMemset(h, 0, Mp * 512); cudaMemset(c, 0, Mp * 512);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     for (int i = 0; i < 3; ++i) ssd_policy_lstm_heads(&pol, feat, h, c, h2, c2, lg, vl, ac, M, 1, i, nullptr);
     cudaEventRecord(e0);

@@ -60,7 +60,8 @@ def main():
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     ms_head = timed(lambda: _lib.check(_lib.lib.ssd_policy_lstm_heads(net._h, p(feats), p(h), p(c), p(hn), p(cn), p(lg), p(vl), p(ac), M, 1, 2, st)), 20)
     print("  ssd_policy_lstm_heads alone: %.4f ms (%.0f GB/s of its 2.3 KB per agent)" % (ms_head, M * 2340 / ms_head / 1e6))
-    ms_unf = timed(lambda: net.forward_unfused(flat, h, c), 20)
+    hu, cu = torch.zeros((M, 128), device="cuda"), torch.zeros((M, 128), device="cuda")
+    ms_unf = timed(lambda: net.forward_unfused(flat, hu, cu), 20)
     print("forward, unfused route (cuBLAS GEMMs + cell kernel): %.4f ms" % ms_unf)
     state = {"obs": obs, "h": h, "c": c}
 

@@ -7,6 +7,10 @@
 //   Y[128 x 16]   = fp16(h') * [logits_w | value_w]                        8 MMAs 128 x 16 x 16 into the freed columns
 //   action        = argmax(logits + Gumbel noise)                          Philox4x32-10 keyed (seed; agent, counter)
 //
+// The recurrent state lives in HBM in a TILED layout chosen for this kernel: [group of 128 agents][block of 16 units (8)]
+// [agent in group (128)][16 floats] -- element (agent m, unit u) at ((m / 128 * 8 + u / 16) * 128 + m % 128) * 16 + u % 16.
+// A thread owns an agent and works through 16 units at a time, so a warp's loads and stores of c / h are 2 KB contiguous
+// (with row-major [M][128] state they were 64-byte pieces 512 bytes apart and the cell update ran at 2.9 TB/s of HBM).
 // HBM traffic per agent: 128 B features + 1 KB (h, c) in, 1 KB (h', c') + logits / value / action out -- one pass, against
 // ~7.5 KB for the unfused gate GEMMs + cell update.  The B operand [W; U] (160 KB as fp16) stays resident in shared memory;
 // the grid is persistent (one CTA per SM).
@@ -87,29 +91,35 @@ lstm_heads_kernel(const float* __restrict__ feat, const float* h_in, const float
     for (long long g = blockIdx.x; g < n_groups; g += gridDim.x) {
         const long long a0 = g * GA;
         const int rem = static_cast<int>(M - a0 < GA ? M - a0 : GA);
-        {   // A = fp16([features | h]).  HBM is read in full 128-byte row segments (eight lanes x 16 bytes; a thread walking its
-            // own row in 32-byte steps reached 2.3 TB/s); two lanes then own one 8-element operand chunk and store 8 bytes each.
+        {   // A = fp16([features | h]).  HBM is read in long contiguous runs (features: a 128-byte row per eight lanes; h: the tiled
+            // state, 64 bytes per lane, 2 KB per warp -- a thread walking a row-major row in 32-byte steps reached 2.3 TB/s).
             // All loads before the stores: the compiler keeps a global load below a store through a generic pointer.
-            const int seg = tid & 7, r8 = tid >> 3;          // 32 rows per pass, 4 passes
+            const int seg = tid & 7, r8 = tid >> 3;          // features: 32 rows per pass, 4 passes, a 128-byte row per eight lanes
+            const int hrow = tid & (GA - 1), hb0 = (tid >> 7) * 4;   // h: thread = (agent, four of the eight 16-unit blocks), 64 bytes per block
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
             float4 vx[4], vh[4][4];
 #pragma unroll
             for (int ps = 0; ps < 4; ++ps) {
                 const int row = ps * 32 + r8;
-                const bool live = row < rem;
-                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-                vx[ps] = live ? __ldcs(reinterpret_cast<const float4*>(feat + (a0 + row) * KX) + seg) : z;           // features: one 128-byte row
-#pragma unroll
-                for (int j = 0; j < 4; ++j) vh[ps][j] = live ? __ldcs(reinterpret_cast<const float4*>(h_in + (a0 + row) * U) + j * 8 + seg) : z;   // h: four
+                vx[ps] = row < rem ? __ldcs(reinterpret_cast<const float4*>(feat + (a0 + row) * KX) + seg) : z;
             }
 #pragma unroll
-            for (int ps = 0; ps < 4; ++ps) {
-                const int row = ps * 32 + r8;
-                uint8_t* base = smem + kOffA + row * 16 + (seg & 1) * 8;   // elements 4 seg .. 4 seg + 3 of a 32-element segment: chunk seg / 2
-                *reinterpret_cast<uint2*>(base + (seg >> 1) * (GA * 16)) = make_uint2(pack_h2(vx[ps].x, vx[ps].y), pack_h2(vx[ps].z, vx[ps].w));
+            for (int b = 0; b < 4; ++b) {
+                const float4* src = reinterpret_cast<const float4*>(h_in + ((g * (U / 16) + hb0 + b) * GA + hrow) * 16);
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    *reinterpret_cast<uint2*>(base + (KX / 8 + j * 4 + (seg >> 1)) * (GA * 16)) = make_uint2(pack_h2(vh[ps][j].x, vh[ps][j].y), pack_h2(vh[ps][j].z, vh[ps][j].w));
+                for (int j = 0; j < 4; ++j) vh[b][j] = hrow < rem ? __ldcs(src + j) : z;
             }
+#pragma unroll
+            for (int ps = 0; ps < 4; ++ps)   // elements 4 seg .. 4 seg + 3 of the 32 features: half of operand chunk seg / 2
+                *reinterpret_cast<uint2*>(smem + kOffA + (seg >> 1) * (GA * 16) + (ps * 32 + r8) * 16 + (seg & 1) * 8) =
+                    make_uint2(pack_h2(vx[ps].x, vx[ps].y), pack_h2(vx[ps].z, vx[ps].w));
+#pragma unroll
+            for (int b = 0; b < 4; ++b)      // units 16 (hb0 + b) .. + 15: operand chunks 4 + 2 (hb0 + b) and the next
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf)
+                    *reinterpret_cast<uint4*>(smem + kOffA + (KX / 8 + 2 * (hb0 + b) + hf) * (GA * 16) + hrow * 16) =
+                        make_uint4(pack_h2(vh[b][2 * hf].x, vh[b][2 * hf].y), pack_h2(vh[b][2 * hf].z, vh[b][2 * hf].w),
+                                   pack_h2(vh[b][2 * hf + 1].x, vh[b][2 * hf + 1].y), pack_h2(vh[b][2 * hf + 1].z, vh[b][2 * hf + 1].w));
         }
         fence_async_smem();
         tc_fence_before();
@@ -133,10 +143,10 @@ lstm_heads_kernel(const float* __restrict__ feat, const float* h_in, const float
             const int q = warp & 3, row = q * 32 + lane, uh = warp >> 2;
             const uint32_t trow = tmem + (static_cast<uint32_t>(q * 32) << 16);
             const bool live = row < rem;
-            const float4* cp = reinterpret_cast<const float4*>(c_in + (a0 + row) * U + uh * 64);
+            const long long tile0 = ((g * (U / 16) + uh * 4) * GA + row) * 16;   // this agent's 16 floats of unit block 4 uh; + GA * 16 per block
             float4 cn[4];   // the next 16 units of c, fetched one iteration ahead
 #pragma unroll
-            for (int e = 0; e < 4; ++e) cn[e] = live ? __ldcs(cp + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int e = 0; e < 4; ++e) cn[e] = live ? __ldcs(reinterpret_cast<const float4*>(c_in + tile0) + e) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
             for (int ub = 0; ub < 4; ++ub) {
                 const int u0 = uh * 64 + ub * 16;
@@ -149,7 +159,8 @@ lstm_heads_kernel(const float* __restrict__ feat, const float* h_in, const float
                                      cn[2].x, cn[2].y, cn[2].z, cn[2].w, cn[3].x, cn[3].y, cn[3].z, cn[3].w};
                 if (ub < 3) {
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) cn[e] = live ? __ldcs(cp + 4 * (ub + 1) + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int e = 0; e < 4; ++e)
+                        cn[e] = live ? __ldcs(reinterpret_cast<const float4*>(c_in + tile0 + (ub + 1) * (GA * 16)) + e) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
                 tmem_ld_wait();
                 float c2[16], hn[16];
@@ -163,8 +174,8 @@ lstm_heads_kernel(const float* __restrict__ feat, const float* h_in, const float
                 if (live) {
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        __stcs(reinterpret_cast<float4*>(c_out + (a0 + row) * U + u0) + e, make_float4(c2[4 * e], c2[4 * e + 1], c2[4 * e + 2], c2[4 * e + 3]));
-                        __stcs(reinterpret_cast<float4*>(h_out + (a0 + row) * U + u0) + e, make_float4(hn[4 * e], hn[4 * e + 1], hn[4 * e + 2], hn[4 * e + 3]));
+                        __stcs(reinterpret_cast<float4*>(c_out + tile0 + ub * (GA * 16)) + e, make_float4(c2[4 * e], c2[4 * e + 1], c2[4 * e + 2], c2[4 * e + 3]));
+                        __stcs(reinterpret_cast<float4*>(h_out + tile0 + ub * (GA * 16)) + e, make_float4(hn[4 * e], hn[4 * e + 1], hn[4 * e + 2], hn[4 * e + 3]));
                     }
                 }
                 // fp16(h') is the A operand of the heads: the gate MMAs are complete, their operand buffer is free

@@ -11,7 +11,10 @@ models/conv_to_fcnet_v2.py (ConvToFCNetv2) evaluated on uint8 observations that 
             unfused route: library GEMMs (torch / cuBLAS, bf16 operands) around the one-pass cell update
             `ssd_policy_lstm_cell`.
 
-Weights are numpy fp32 arrays in the Keras layouts (conv kernel [kh, kw, in, out], dense kernels [in, out], LSTM kernel
+The recurrent state (h, c) of the fused route lives in HBM in the kernel's tiled layout, shape [ceil(M/128), 8, 128, 16]
+(group of 128 agents, block of 16 units, agent, unit): a warp of the cell update then moves 2 KB contiguous per access.  Treat
+it as opaque between steps (as RLlib does with state_out -> state_in); `state_rows` / `state_from_rows` convert to and from
+[M, cell_size].  Weights are numpy fp32 arrays in the Keras layouts (conv kernel [kh, kw, in, out], dense kernels [in, out], LSTM kernel
 [in, 4u] / recurrent kernel [u, 4u] / bias [4u] with gates ordered i, f, c, o), so a checkpoint of the reference model
 loads without transposition.  There is no CPU path: the trunk raises without the CUDA library.
 """
@@ -111,8 +114,27 @@ class ConvToFCNet(object):
         return out
 
     def initial_state(self, m):
-        z = torch.zeros((m, self.cell_size), dtype=torch.float32, device=self.device)
+        """Zero (h, c) for m agents, in the layout `forward` / `act` carry (tiled for the fused route, [m, cell_size] otherwise)."""
+        shape = ((m + 127) // 128, self.cell_size // 16, 128, 16) if self._fused_head else (m, self.cell_size)
+        z = torch.zeros(shape, dtype=torch.float32, device=self.device)
         return z, z.clone()
+
+    @staticmethod
+    def state_rows(state, m):
+        """Tiled state [G, 8, 128, 16] -> [m, cell_size] (a copy)."""
+        if state.dim() == 2:
+            return state[:m]
+        g, b, r, e = state.shape
+        return state.permute(0, 2, 1, 3).reshape(g * r, b * e)[:m].contiguous()
+
+    @staticmethod
+    def state_from_rows(rows):
+        """[m, cell_size] -> tiled state [ceil(m/128), cell_size/16, 128, 16], zero padded."""
+        m, u = rows.shape
+        g = (m + 127) // 128
+        full = torch.zeros((g * 128, u), dtype=rows.dtype, device=rows.device)
+        full[:m] = rows
+        return full.reshape(g, 128, u // 16, 16).permute(0, 2, 1, 3).contiguous()
 
     def seed_sampling(self, seed):
         """Key of the Philox streams `act` samples from (counter = number of `act` calls since)."""
@@ -121,6 +143,8 @@ class ConvToFCNet(object):
     def _fused(self, obs, h, c, sample):
         x = self.features(obs)
         m = x.shape[0]
+        if h.dim() != 4 or h.shape[0] * 128 < m:
+            raise ValueError("the fused route carries (h, c) in the tiled layout of initial_state / state_from_rows")
         h, c = h.contiguous(), c.contiguous()
         h_new, c_new = torch.empty_like(h), torch.empty_like(c)
         logits = torch.empty((m, self.num_outputs), dtype=torch.float32, device=self.device)
@@ -135,14 +159,14 @@ class ConvToFCNet(object):
         return logits, value, h_new, c_new, actions
 
     def forward(self, obs, h, c):
-        """-> (logits [M, A], value [M], h', c'), all float32."""
+        """-> (logits [M, A], value [M], h', c'), all float32; (h, c) in the layout of `initial_state`."""
         if not self._fused_head:
             return self.forward_unfused(obs, h, c)
         return self._fused(obs, h, c, sample=False)[:4]
 
     def forward_unfused(self, obs, h, c):
         """The same forward pass with library GEMMs: the trunk kernel, the gate GEMMs (cuBLAS, bf16 x bf16 -> fp32 accumulate), the
-        one-pass cell update, the head GEMMs.  Any cell size that is a multiple of 8."""
+        one-pass cell update, the head GEMMs.  Any cell size that is a multiple of 8; (h, c) are [M, cell_size] here."""
         hd = self._head
         x16 = self.features(obs).to(torch.bfloat16)
         gates = torch.mm(x16, hd["lstm_w"]).addmm_(h.to(torch.bfloat16), hd["lstm_u"])   # bf16 [M, 4u], bias added in the cell kernel

@@ -59,9 +59,12 @@ def test_forward_matches_fp32_reference_over_steps():
     w = policy.random_weights(num_outputs=9, cell_size=128, seed=11)
     net = policy.ConvToFCNet(w)
     g = torch.Generator(device="cuda").manual_seed(5)
-    h, c = net.initial_state(m)
-    hr, cr = h.clone(), c.clone()
-    hu, cu = h.clone(), c.clone()
+    h, c = net.initial_state(m)                                 # tiled layout of the fused kernel
+    assert h.shape == (8, 8, 128, 16)
+    hr, cr = torch.zeros((m, 128), device="cuda"), torch.zeros((m, 128), device="cuda")
+    hu, cu = hr.clone(), cr.clone()
+    assert torch.equal(net.state_rows(net.state_from_rows(torch.arange(m * 128.0, device="cuda").reshape(m, 128)), m),
+                       torch.arange(m * 128.0, device="cuda").reshape(m, 128))
     for _ in range(3):
         obs = torch.randint(0, 256, (m, 15, 15, 3), dtype=torch.uint8, device="cuda", generator=g)
         logits, value, h, c = net.forward(obs, h, c)            # fused tcgen05 LSTM + heads (cell_size 128)
@@ -69,7 +72,7 @@ def test_forward_matches_fp32_reference_over_steps():
         hu, cu = h2, c2
         lr, vr, hr, cr = _reference_forward(w, obs, hr, cr)
         assert logits.shape == (m, 9) and value.shape == (m,)
-        for got, want in ((logits, lr), (value, vr), (h, hr), (c, cr)):
+        for got, want in ((logits, lr), (value, vr), (net.state_rows(h, m), hr), (net.state_rows(c, m), cr)):
             assert torch.allclose(got, want, atol=2e-2, rtol=2e-2), (got - want).abs().max().item()   # fp16 operands, fp32 accumulation
         for got, want in ((l2, lr), (v2, vr), (h2, hr), (c2, cr)):
             assert torch.allclose(got, want, atol=3e-2, rtol=3e-2), (got - want).abs().max().item()   # bf16 operands: 8 significant bits
@@ -92,7 +95,7 @@ def test_fused_sampling_follows_softmax():
     a2, _, _, _ = net.act(obs, h, c)
     net.seed_sampling(77)
     a3, _, _, _ = net.act(obs, h, c)
-    logits = net.forward(obs[:1], h[:1], c[:1])[0][0]
+    logits = net.forward(obs[:1], *net.initial_state(1))[0][0]
     p = torch.softmax(logits.double(), 0).cpu().numpy()
     assert a1.dtype == torch.int8 and int(a1.min()) >= 0 and int(a1.max()) < 8
     freq = np.bincount(a1.cpu().numpy().astype(np.int64), minlength=8) / m
