@@ -3,17 +3,18 @@
 // reading the uint8 observations the step kernel left in HBM (the (x - 128) / 255 of map_env.py:199 is folded into the first
 // layer).  One fused kernel on the 5th-generation tensor cores: nothing but the [M, 32] features goes back to HBM.
 //
-//   per group of 128 agents (= UMMA M, one accumulator row per agent, one CTA):
-//     for each of the 13 output rows i of the convolution:
-//       A1[agent][k]  = fp16(1024 + obs[agent][45 i + k]),  k < 135: image rows i..i+2 are CONTIGUOUS bytes of the observation,
-//                       so the im2col operand is a sliding window of the raw bytes (0x6400 | byte is the fp16 of 1024 + byte)
-//       D1[128 x 80]  = A1[128 x 144] * B1[144 x 80]        banded weights: column (j, f) holds filter f at taps 3 (j + dj) + c
-//       C [agent][n]  = fp16(relu(D1 / 255 + cb[n]))        cb folds the bias, the -128 / 255 and the 1024 offset
-//       D2[128 x 32] += C[128 x 80] * W1_i[80 x 32]         Dense(32) accumulated over the 13 row blocks of its 1014 inputs
+//   per group of 128 agents (= UMMA M: one tensor-memory lane per agent; one persistent CTA per SM):
+//     for each of the 15 image rows r:   A_r[agent][k] = fp16(1024 + obs[agent][45 r + k]), k < 48  (0x6400 | byte IS that fp16; taps
+//                                         45..47 belong to the next row and meet zero weights) -- converted once, kept in a ring
+//     for each of the 13 output rows i of the convolution (image rows i..i+2 are the three operand blocks i, i+1, i+2):
+//       D1[128 x 80]  = sum_di A_(i+di)[128 x 48] * B1_di[48 x 80]   banded weights: column (j, f) holds filter f at taps 3 (j + dj) + c
+//       C [agent][n]  = fp16(relu(D1 / 255 + cb[n]))                cb folds the bias, the -128 / 255 and the 1024 offset
+//       D2[128 x 32] += C[128 x 80] * W1_i[80 x 32]                 Dense(32) accumulated over the 13 row blocks of its 1014 inputs
 //     D3[128 x 32] = fp16(relu(D2 + b1)) * W2;  features = relu(D3 + b2)
 //
-// Operands live in shared memory in the canonical K-major no-swizzle layout (8 x 16-byte core matrices: element (row, k) at
-// (k / 8) * rows * 16 + row * 16 + (k % 8) * 2), accumulators in tensor memory, all MMAs issued by one thread.
+// The A operands (image-row ring, C, the fc2 operand) and the accumulators live in tensor memory -- the lane that owns an agent
+// writes them with tcgen05.st -- the B operands (weights) in shared memory in the canonical K-major no-swizzle layout (8 x 16-byte
+// core matrices: element (n, k) at (k / 8) * rows * 16 + n * 16 + (k % 8) * 2); all MMAs are issued by one elected thread.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
