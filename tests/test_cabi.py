@@ -104,6 +104,18 @@ def test_argument_errors_need_no_gpu():
     # NULL handles are rejected, not dereferenced
     assert L.ssd_step(None, None, None, None, None, None, None) == -1
     assert L.ssd_num_apple_points(None) == -1 and L.ssd_destroy(None) == 0
+    # the policy entry points validate before they touch the device, too
+    ph = C.c_void_p()
+    w = [np.zeros(n, dtype=np.float32) for n in (162, 6, 1014 * 32, 32, 1024, 32)]
+    ptrs = [a.ctypes.data_as(C.c_void_p) for a in w]
+    assert L.ssd_policy_create(7, 0, None, *ptrs[1:], C.byref(ph)) == -1 and b"null" in L.ssd_last_error()
+    assert L.ssd_policy_create(5, 0, *ptrs, C.byref(ph)) == -3 and b"15x15" in L.ssd_last_error()   # SSD_ERR_UNSUPPORTED
+    assert L.ssd_policy_features(None, None, 0, None, None) == -1
+    assert L.ssd_policy_set_head(None, 128, 8, *([None] * 7)) == -1
+    assert L.ssd_policy_lstm_heads(None, *([None] * 8), 0, 0, 0, None) == -1
+    buf = C.c_void_p(4096)   # an aligned, never dereferenced address
+    assert L.ssd_policy_lstm_cell(buf, buf, buf, buf, buf, buf, 1, 12, None) == -1 and b"multiple of 8" in L.ssd_last_error()
+    L.ssd_policy_destroy(None)
 
 
 def test_product_does_not_touch_the_oracle():
