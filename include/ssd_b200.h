@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SSD_ABI_VERSION 1
+#define SSD_ABI_VERSION 2
 #define SSD_MAX_AGENTS 16
 
 #define SSD_KIND_HARVEST 0 /* social_dilemmas/envs/harvest.py:18  HarvestEnv */
@@ -98,7 +98,8 @@ const char* ssd_last_error(void);
 int ssd_abi_version(void);
 
 /* MapEnv.__init__ .. without the RNG-consuming setup_agents() (map_env.py:102): state is
- * the post-reset_map() grid with all agents at (0,0) until ssd_reset or ssd_set_state. */
+ * the post-reset_map() grid with all agents parked on the first 'P' spawn point of the map (cell (1,1) when the
+ * map has none) until ssd_reset or ssd_set_state places them. */
 int ssd_create(const SsdConfig* cfg, ssd_handle* out);
 int ssd_destroy(ssd_handle h);
 
@@ -116,7 +117,11 @@ int ssd_get_counter(ssd_handle h, uint32_t* t);
 
 /* State upload / download (parity, checkpoint/resume).  Pointers may be host or dev (UVA).
  * grid u8[B][H*W], pos i16[B][N][2], ori u8[B][N].  Reference fields: MapEnv.world_map
- * (map_env.py:85), Agent.pos / Agent.orientation (agent.py:37-38). */
+ * (map_env.py:85), Agent.pos / Agent.orientation (agent.py:37-38).
+ * ssd_set_state validates every position (0 <= row < H, 0 <= col < W) before it touches the state and returns
+ * SSD_ERR_INVALID otherwise (it synchronises `stream` to do so).  An agent placed on a '@' cell -- which the
+ * reference never does -- is accepted as PARKED: it keeps its place, never acts, is never painted or hit, so
+ * that no beam ever starts outside the wall enclosure. */
 int ssd_set_state(ssd_handle h, const uint8_t* grid, const int16_t* pos, const uint8_t* ori, void* stream);
 int ssd_get_state(ssd_handle h, uint8_t* grid, int16_t* pos, uint8_t* ori, void* stream);
 
@@ -125,6 +130,12 @@ int ssd_get_state(ssd_handle h, uint8_t* grid, int16_t* pos, uint8_t* ori, void*
  * mask dev u8[B] (NULL = all envs): only envs with mask != 0 are reset and rendered.
  * obs_out dev u8[B][N][V][V][3] or NULL. */
 int ssd_reset(ssd_handle h, const uint8_t* mask, uint8_t* obs_out, void* stream);
+
+/* MapEnv.reset of the listed environments only (RLlib resets sub-environments one at a time at the episode
+ * horizon, map_env.py:214-249 is per env): ONE launch over n_rows warps instead of a masked pass over all B.
+ * rows: host or dev i32[n_rows], each in 0..B-1 (a host list is range-checked; out-of-range device entries are
+ * skipped).  obs_out is the full dev u8[B][N][V][V][3] tensor (or NULL); only the listed rows are written. */
+int ssd_reset_rows(ssd_handle h, const int32_t* rows, int n_rows, uint8_t* obs_out, void* stream);
 
 /* MapEnv.step (map_env.py:152-212) for all B envs in one fused launch.
  * actions dev i8[B][N]; action_order dev u8[B][N] = iteration order of the action dict as agent
@@ -168,16 +179,18 @@ int ssd_render_map(ssd_handle h, uint8_t* rgb_out, void* stream);
 /* End-to-end step with HOST buffers: H2D actions, fused step, D2H observations and rewards,
  * pipelined in chunks over two internal streams; returns after everything landed.
  * actions_host i8[B][N], obs_host u8[B][N][V][V][3] (NULL to skip), reward_host i32[B][N].
- * Pinned host memory gives full PCIe bandwidth; pageable memory works but is slower. */
-int ssd_step_host(ssd_handle h, const int8_t* actions_host, uint8_t* obs_host, int32_t* reward_host);
+ * Pinned host memory gives full PCIe bandwidth; pageable memory works but is slower.
+ * The internal streams first wait for everything already queued on `stream` (NULL = legacy default stream), so
+ * the call is ordered after an asynchronous ssd_reset / ssd_set_state / ssd_step issued there. */
+int ssd_step_host(ssd_handle h, const int8_t* actions_host, uint8_t* obs_host, int32_t* reward_host, void* stream);
 
 /* ---- Policy-side consumer of the observation tensor -------------------------------------------------
  * The feature trunk of the reference's policy network, models/conv_to_fcnet_v2.py:36-66: Conv2D(6, 3x3, stride 1,
  * 'valid') -> ReLU -> flatten -> Dense(32) -> ReLU -> Dense(32) -> ReLU, applied to (obs - 128) / 255 (map_env.py:199)
  * of uint8 observations resident in HBM -- what ssd_step / ssd_rollout wrote -- in one fused tensor-core kernel
  * (fp16 operands, fp32 accumulation; nothing but the features returns to HBM).  The LSTM and the two heads that
- * follow (conv_to_fcnet_v2.py:68-92) are plain GEMMs on [M, 32] / [M, 128], left to the caller's BLAS, plus the
- * elementwise cell update ssd_policy_lstm_cell.
+ * follow (conv_to_fcnet_v2.py:68-92) are ssd_policy_lstm_heads below (one fused kernel); ssd_policy_lstm_cell is the
+ * elementwise cell update for callers that run the gate GEMMs of another cell size through their own BLAS.
  *
  * Weights are HOST fp32 arrays in the Keras layouts: conv_w [3][3][3][6] (kh, kw, in, out), conv_b [6],
  * fc1_w [1014][32] (inputs flattened (row, col, filter) as keras Flatten does), fc1_b [32], fc2_w [32][32], fc2_b [32].

@@ -8,7 +8,7 @@ from ._names import STAT_NAMES  # noqa: F401
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libssd_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_AGENTS = 16
 NUM_STATS = 8
 OPT_CHAIN_STEPS = 1
@@ -19,7 +19,7 @@ PHASE_MOVES, PHASE_CONSUME, PHASE_BEAMS, PHASE_SPAWN, PHASE_RENDER, PHASE_ALL = 
 SYMBOLS = ("ssd_last_error", "ssd_abi_version", "ssd_create", "ssd_destroy", "ssd_num_apple_points",
            "ssd_num_waste_points", "ssd_obs_bytes_per_env", "ssd_envs_per_cta",
            "ssd_algorithmic_bytes_per_env_step", "ssd_seed", "ssd_get_counter", "ssd_set_state",
-           "ssd_get_state", "ssd_reset", "ssd_step", "ssd_rollout", "ssd_step_phases", "ssd_get_beams", "ssd_render", "ssd_render_map", "ssd_step_host",
+           "ssd_get_state", "ssd_reset", "ssd_reset_rows", "ssd_step", "ssd_rollout", "ssd_step_phases", "ssd_get_beams", "ssd_render", "ssd_render_map", "ssd_step_host",
            "ssd_set_option", "ssd_stats", "ssd_launch_count", "ssd_philox_selftest",
            "ssd_policy_create", "ssd_policy_features", "ssd_policy_destroy", "ssd_policy_lstm_cell",
            "ssd_policy_set_head", "ssd_policy_lstm_heads")
@@ -71,13 +71,14 @@ def _load():
         "ssd_set_state": (i32, [vp, vp, vp, vp, vp]),
         "ssd_get_state": (i32, [vp, vp, vp, vp, vp]),
         "ssd_reset": (i32, [vp, vp, vp, vp]),
+        "ssd_reset_rows": (i32, [vp, vp, i32, vp, vp]),
         "ssd_step": (i32, [vp, vp, vp, C.POINTER(SsdTape), vp, vp, vp]),
         "ssd_rollout": (i32, [vp, i32, vp, vp, i32, vp, vp]),
         "ssd_step_phases": (i32, [vp, i32, vp, vp, C.POINTER(SsdTape), vp, vp, vp]),
         "ssd_get_beams": (i32, [vp, vp, vp]),
         "ssd_render": (i32, [vp, i32, vp, vp]),
         "ssd_render_map": (i32, [vp, vp, vp]),
-        "ssd_step_host": (i32, [vp, vp, vp, vp]),
+        "ssd_step_host": (i32, [vp, vp, vp, vp, vp]),
         "ssd_set_option": (i32, [vp, i32, i64]),
         "ssd_stats": (i32, [vp, vp, vp]),
         "ssd_launch_count": (i64, [vp]),

@@ -11,8 +11,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .config import EnvConfig, KIND_CLEANUP, KIND_HARVEST
-from .maps import CLEANUP_MAP, HARVEST_MAP
+from .config import make_config  # noqa: F401  (re-exported; lives in config.py so that CPU-only tools never load the CUDA library)
 
 
 def _ptr(t):
@@ -109,6 +108,19 @@ class BatchedSSDEnv(object):
         _lib.check(_lib.lib.ssd_reset(self._h, _ptr(m), _ptr(obs), self._stream()))
         return obs
 
+    def reset_rows(self, rows, out=None, render=True):
+        """MapEnv.reset of the listed envs only (ssd_reset_rows): one launch over len(rows) warps.  `rows` is a
+        sequence of ints or an int32 tensor; returns the full observation tensor (only those rows are rewritten)."""
+        obs = self._obs_buf(out) if render else None
+        if torch.is_tensor(rows):
+            r = rows.to(device=self.device, dtype=torch.int32).contiguous()
+            _lib.check(_lib.lib.ssd_reset_rows(self._h, _ptr(r), int(r.numel()), _ptr(obs), self._stream()))
+        else:
+            r = np.ascontiguousarray(rows, dtype=np.int32).reshape(-1)
+            _lib.check(_lib.lib.ssd_reset_rows(self._h, r.ctypes.data, int(r.size), _ptr(obs), self._stream()))
+            torch.cuda.current_stream(self.device).synchronize()  # the host list was copied asynchronously
+        return obs
+
     def step(self, actions, action_order=None, tape=None, out=None, reward_out=None, render=True, phases=None):
         """MapEnv.step (map_env.py:152-212).  Returns (obs, rewards); dones are always False in the
         reference (agent.py:174,209) and infos empty."""
@@ -189,7 +201,7 @@ class BatchedSSDEnv(object):
         if obs_host is not None:
             assert obs_host.dtype == np.uint8 and obs_host.flags.c_contiguous and obs_host.shape == self.obs_shape
         _lib.check(_lib.lib.ssd_step_host(self._h, a.ctypes.data, obs_host.ctypes.data if obs_host is not None else None,
-                                          reward_host.ctypes.data))
+                                          reward_host.ctypes.data, self._stream()))
         return obs_host, reward_host
 
     # ------------------------------------------------------------------ state I/O
@@ -244,15 +256,6 @@ class BatchedSSDEnv(object):
     @property
     def algorithmic_bytes_per_env_step(self):
         return int(_lib.lib.ssd_algorithmic_bytes_per_env_step(self._h))
-
-
-def make_config(name, num_agents=5, view_size=7, ascii_map=None):
-    name = name.lower()
-    if name == "harvest":
-        return EnvConfig(KIND_HARVEST, ascii_map or HARVEST_MAP, num_agents, view_size=view_size)
-    if name == "cleanup":
-        return EnvConfig(KIND_CLEANUP, ascii_map or CLEANUP_MAP, num_agents, view_size=view_size)
-    raise ValueError("unknown game %r" % name)
 
 
 def philox_selftest(ctr, key, device=0):

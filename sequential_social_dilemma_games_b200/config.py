@@ -8,7 +8,7 @@ possible waste count, so the device only ever compares doubles -- it never re-de
 """
 import numpy as np
 
-from .maps import validate_map
+from .maps import CLEANUP_MAP, HARVEST_MAP, validate_map
 
 KIND_HARVEST, KIND_CLEANUP, KIND_PLAIN = 0, 1, 2
 MAX_AGENTS = 16
@@ -129,3 +129,13 @@ class EnvConfig(object):
         for ch in keep:
             g[self.base_map == ord(ch)] = ord(ch)
         return g
+
+
+def make_config(name, num_agents=5, view_size=7, ascii_map=None):
+    """EnvConfig of 'harvest' / 'cleanup' with the reference's defaults (harvest.py:20, cleanup.py:32)."""
+    name = name.lower()
+    if name == "harvest":
+        return EnvConfig(KIND_HARVEST, ascii_map or HARVEST_MAP, num_agents, view_size=view_size)
+    if name == "cleanup":
+        return EnvConfig(KIND_CLEANUP, ascii_map or CLEANUP_MAP, num_agents, view_size=view_size)
+    raise ValueError("unknown game %r" % name)

@@ -10,7 +10,12 @@ namespace ssd {
 // the reference takes the LAST free entry of the shuffled list = the free entry with the largest
 // (key, index); spawn_rotation (:664-667) indexes ['LEFT','RIGHT','UP','DOWN'] with randint(4).
 __global__ void __launch_bounds__(128) ssd_reset_kernel(const ResetArgs a) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a.rows != nullptr) {  // ssd_reset_rows: one thread per listed env
+        if (e >= a.n_rows) return;
+        e = a.rows[e];
+        if (e < 0) return;
+    }
     if (e >= a.env_end) return;
     if (a.mask != nullptr && a.mask[e] == 0) return;
     const uint32_t env = static_cast<uint32_t>(a.env_id0 + static_cast<uint64_t>(e));
@@ -94,8 +99,19 @@ __global__ void pack_state_kernel(int kind, int B, int N, int H, int W, int Ws, 
         }
         grid[i] = cell;
     }
-    if (i < static_cast<size_t>(B) * N)
-        agents[i] = (pos_in[2 * i] & 255) | (pos_in[2 * i + 1] & 255) << 8 | static_cast<uint32_t>(ori_in[i] & 3) << 16;
+    if (i < static_cast<size_t>(B) * N) {  // positions were range-checked by check_positions_kernel
+        const int r = pos_in[2 * i], c = pos_in[2 * i + 1];
+        // An agent uploaded onto a wall cell (the adapters park a stand-in there when an env has no agents) is marked
+        // "parked": the step kernels never let it act or paint it, so no ray ever starts outside the wall enclosure.
+        const uint32_t parked = grid_in[(i / N) * H * W + r * W + c] == '@';
+        agents[i] = (r & 255) | (c & 255) << 8 | static_cast<uint32_t>(ori_in[i] & 3) << 16 | parked << 24;
+    }
+}
+__global__ void check_positions_kernel(int B, int N, int H, int W, const int16_t* pos_in, int* bad) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= static_cast<size_t>(B) * N) return;
+    const int r = pos_in[2 * i], c = pos_in[2 * i + 1];
+    if (r < 0 || r >= H || c < 0 || c >= W) atomicAdd(bad, 1);
 }
 __global__ void unpack_state_kernel(int B, int N, int H, int W, int Ws, int env_bytes, const uint8_t* grid, const uint32_t* agents,
                                     uint8_t* grid_out, int16_t* pos_out, uint8_t* ori_out) {
@@ -124,7 +140,7 @@ __global__ void render_map_kernel(int B, int N, int H, int W, int Ws, int env_by
     uint8_t cell = grid[b * env_bytes + r * Ws + c] & 0x7F;
     for (int ag = 0; ag < N; ++ag) {
         const uint32_t w = agents[b * N + ag];
-        if ((w & 255u) == r && ((w >> 8) & 255u) == c) cell = agent_cell(ag);
+        if ((w & 255u) == r && ((w >> 8) & 255u) == c && !((w >> 24) & 1u)) cell = agent_cell(ag);
     }
     const uint32_t rgb = color[cell];
     out[3 * i] = rgb & 255; out[3 * i + 1] = (rgb >> 8) & 255; out[3 * i + 2] = (rgb >> 16) & 255;
@@ -137,8 +153,14 @@ __global__ void philox_selftest_kernel(const uint32_t* ck, uint32_t* out) {
 
 // ====================================================================== launchers
 cudaError_t launch_reset(const ResetArgs& a, cudaStream_t stream) {
-    if (a.env_end <= 0) return cudaSuccess;
-    ssd_reset_kernel<<<(a.env_end + 127) / 128, 128, 0, stream>>>(a);
+    const int n = a.rows != nullptr ? a.n_rows : a.env_end;
+    if (n <= 0) return cudaSuccess;
+    ssd_reset_kernel<<<(n + 127) / 128, 128, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t launch_check_positions(int B, int N, int H, int W, const int16_t* pos_in, int* bad, cudaStream_t stream) {
+    const size_t n = static_cast<size_t>(B) * N;
+    check_positions_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(B, N, H, W, pos_in, bad);
     return cudaGetLastError();
 }
 

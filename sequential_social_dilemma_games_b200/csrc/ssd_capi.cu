@@ -63,7 +63,11 @@ struct SsdEnv {
     uint8_t* d_init_grid = nullptr;
     uint8_t* d_grid = nullptr; uint32_t* d_agents = nullptr; uint8_t* d_beam_buf = nullptr;
     unsigned long long* d_stats = nullptr;
+    int* d_bad = nullptr;  // ssd_set_state: number of agent positions outside the map
+    int32_t* d_rows = nullptr; int rows_cap = 0;  // ssd_reset_rows: device copy of a host row list
     // ssd_step_host plumbing
+    bool host_ready = false;
+    cudaEvent_t host_ev = nullptr;
     cudaStream_t hs[2] = {nullptr, nullptr};
     int8_t* d_act_stage = nullptr; uint8_t* d_obs_stage = nullptr; int32_t* d_rew_stage = nullptr;
     // staging for host-pointer set/get state
@@ -110,7 +114,7 @@ ssd::SmemLayout make_layout(const SsdEnv& h, int threads, bool fast = false) {
     const uint32_t u_moves = epw * sizeof(ssd::MoveScratch);
     L.u_words = std::max(u_render, std::max(u_spawn, u_moves)) / 4;
     w += 4 * L.u_words;
-    if (const char* x = getenv("SSD_EXTRA_SMEM")) w += up16(static_cast<uint32_t>(atoi(x)));  // occupancy experiments
+    if (const char* x = ssd::knob("SSD_EXTRA_SMEM")) w += up16(static_cast<uint32_t>(atoi(x)));  // occupancy experiments
     L.warp_stride = w;
     L.total = off + (threads / 32) * w;
     return L;
@@ -123,7 +127,7 @@ void fill_args(SsdEnv* h, ssd::StepArgs& a) {
     a.beam_len = c.beam_len; a.Ws = h->Ws; a.env_bytes = h->env_bytes; a.pad_bytes = h->pad_bytes;
     a.n_apple = h->n_apple; a.n_waste = h->n_waste; a.area = c.potential_waste_area;
     a.harvest_nz = h->harvest_nz;
-    { static const int dbg = getenv("SSD_DEBUG_SKIP") ? atoi(getenv("SSD_DEBUG_SKIP")) : 0; a.debug = dbg; }
+    { static const int dbg = ssd::knob("SSD_DEBUG_SKIP") ? atoi(ssd::knob("SSD_DEBUG_SKIP")) : 0; a.debug = dbg; }
     a.obs_env = h->obs_env;
     a.G = h->cfg.num_agents <= 8 ? 8 : 16; a.env_begin = 0; a.env_end = h->B;
     a.phases = SSD_PHASE_ALL; a.rotate = 1; a.spawn_stream = ssd::STREAM_SPAWN;
@@ -255,7 +259,7 @@ int ssd_create(const SsdConfig* cfg, ssd_handle* out) {
 
     // CTA shape: every warp owns 32/G envs; SSD_THREADS (64, 128 or 256) overrides the CTA size for tuning.
     const int smem_max = static_cast<int>(prop.sharedMemPerBlockOptin);
-    auto env_int = [](const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; };
+    auto env_int = [](const char* name, int dflt) { const char* v = ssd::knob(name); return v && *v ? atoi(v) : dflt; };
     int threads = env_int("SSD_THREADS", 128);
     if (threads != 32 && threads != 64 && threads != 128 && threads != 256) { delete h; return fail(SSD_ERR_INVALID, "SSD_THREADS must be 32, 64, 128 or 256"); }
     if (cfg->envs_per_cta != 0) {  // explicit request: must be a whole number of warps
@@ -287,6 +291,8 @@ int ssd_create(const SsdConfig* cfg, ssd_handle* out) {
     bad |= h->alloc(&h->d_beam_buf, static_cast<size_t>(h->B_pad) * 64);
     bad |= h->alloc(&h->d_stats, static_cast<size_t>(SSD_NUM_STATS));
     bad |= h->alloc(&h->chain.done, static_cast<size_t>(h->B_pad / 2 + 1));  // one word per task (4 or 2 envs)
+    bad |= h->alloc(&h->d_bad, 1);
+    h->chain.cta_slots = prop.multiProcessorCount * 8;  // resident CTAs at the specialised kernel's shape (8 per SM)
     if (bad) { const char* m = cudaGetErrorString(cudaGetLastError()); ssd_destroy(h); return fail(SSD_ERR_CUDA, "device allocation failed: %s", m); }
     // initial state: post-reset_map grid, agents parked on the first spawn point (or cell 1,1)
     {
@@ -312,6 +318,7 @@ int ssd_destroy(ssd_handle h) {
     if (!h) return SSD_OK;
     cudaSetDevice(h->cfg.device);
     for (int i = 0; i < 2; ++i) if (h->hs[i]) cudaStreamDestroy(h->hs[i]);
+    if (h->host_ev) cudaEventDestroy(h->host_ev);
     for (void* p : h->allocs) cudaFree(p);
     delete h;
     return SSD_OK;
@@ -361,6 +368,15 @@ int ssd_set_state(ssd_handle h, const uint8_t* grid, const int16_t* pos, const u
         CUDA_TRY(cudaMemcpyAsync(h->d_io_ori, ori, np, cudaMemcpyDefault, st));
         grid = h->d_io_grid; pos = h->d_io_pos; ori = h->d_io_ori;
     }
+    {   // positions index the shared-memory tiles unchecked inside the kernels: refuse anything outside the map up front
+        int bad = 0;
+        CUDA_TRY(cudaMemsetAsync(h->d_bad, 0, sizeof(int), st));
+        CUDA_TRY(ssd::launch_check_positions(h->B, N, h->cfg.height, h->cfg.width, pos, h->d_bad, st));
+        CUDA_TRY(cudaMemcpyAsync(&bad, h->d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        h->launches++;
+        if (bad) return fail(SSD_ERR_INVALID, "%d agent position(s) outside the %dx%d map; the state was not changed", bad, h->cfg.height, h->cfg.width);
+    }
     CUDA_TRY(ssd::launch_pack_state(h->cfg.kind, h->B, N, h->cfg.height, h->cfg.width, h->Ws, h->env_bytes, grid, pos, ori, h->d_grid, h->d_agents, st));
     h->launches++;
     return SSD_OK;
@@ -392,8 +408,7 @@ int ssd_get_state(ssd_handle h, uint8_t* grid, int16_t* pos, uint8_t* ori, void*
     return SSD_OK;
 }
 
-int ssd_reset(ssd_handle h, const uint8_t* mask, uint8_t* obs_out, void* stream) {
-    if (check_handle(h)) return SSD_ERR_INVALID;
+static int reset_impl(ssd_handle h, const uint8_t* mask, const int32_t* rows, int n_rows, uint8_t* obs_out, void* stream) {
     h->chain.valid = false;
     if (h->n_spawn == 0) return fail(SSD_ERR_INVALID, "the map has no 'P' spawn points");
     if (h->distinct_spawn < h->cfg.num_agents)  // map_env.py:661
@@ -404,15 +419,39 @@ int ssd_reset(ssd_handle h, const uint8_t* mask, uint8_t* obs_out, void* stream)
     r.N = h->cfg.num_agents; r.n_spawn = h->n_spawn; r.env_bytes = h->env_bytes; r.env_end = h->B;
     r.key0 = static_cast<uint32_t>(h->seed); r.key1 = static_cast<uint32_t>(h->seed >> 32); r.t = h->t;
     r.env_id0 = h->cfg.env_id_offset;
-    r.spawn_key = h->d_spawn; r.init_grid = h->d_init_grid; r.mask = mask; r.grid = h->d_grid; r.agents = h->d_agents;
+    r.spawn_key = h->d_spawn; r.init_grid = h->d_init_grid; r.mask = mask; r.rows = rows; r.n_rows = n_rows; r.grid = h->d_grid; r.agents = h->d_agents;
     CUDA_TRY(ssd::launch_reset(r, st));
     ssd::StepArgs a;
     fill_args(h, a);
     a.phases = SSD_PHASE_SPAWN | (obs_out ? SSD_PHASE_RENDER : 0);  // custom_map_update + un-rotated render (map_env.py:230-248)
-    a.rotate = 0; a.spawn_stream = ssd::STREAM_RSPAWN; a.mask = mask; a.obs = obs_out;
+    a.rotate = 0; a.spawn_stream = ssd::STREAM_RSPAWN; a.mask = mask; a.rows = rows; a.n_rows = n_rows; a.obs = obs_out;
     CUDA_TRY(ssd::launch_step(a, h->threads, st));
     h->launches += 2;
     return SSD_OK;
+}
+
+int ssd_reset(ssd_handle h, const uint8_t* mask, uint8_t* obs_out, void* stream) {
+    if (check_handle(h)) return SSD_ERR_INVALID;
+    return reset_impl(h, mask, nullptr, 0, obs_out, stream);
+}
+
+int ssd_reset_rows(ssd_handle h, const int32_t* rows, int n_rows, uint8_t* obs_out, void* stream) {
+    if (check_handle(h)) return SSD_ERR_INVALID;
+    if (n_rows < 0 || (n_rows > 0 && !rows)) return fail(SSD_ERR_INVALID, "rows / n_rows");
+    if (n_rows == 0) return SSD_OK;
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    if (!is_device_ptr(rows)) {  // a host list: range-check it here and stage it on the device
+        for (int i = 0; i < n_rows; ++i)
+            if (rows[i] < 0 || rows[i] >= h->B) return fail(SSD_ERR_INVALID, "row %d outside 0..%d", rows[i], h->B - 1);
+        if (n_rows > h->rows_cap) {
+            int cap = n_rows < 256 ? 256 : n_rows;
+            if (h->alloc(&h->d_rows, static_cast<size_t>(cap))) return fail(SSD_ERR_CUDA, "staging allocation failed");
+            h->rows_cap = cap;
+        }
+        CUDA_TRY(cudaMemcpyAsync(h->d_rows, rows, static_cast<size_t>(n_rows) * sizeof(int32_t), cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)));
+        rows = h->d_rows;
+    }
+    return reset_impl(h, nullptr, rows, n_rows, obs_out, stream);
 }
 
 int ssd_step_phases(ssd_handle h, int phases, const int8_t* actions, const uint8_t* action_order, const SsdTape* tape,
@@ -500,19 +539,27 @@ int ssd_render_map(ssd_handle h, uint8_t* rgb_out, void* stream) {
     return SSD_OK;
 }
 
-int ssd_step_host(ssd_handle h, const int8_t* actions_host, uint8_t* obs_host, int32_t* reward_host) {
+int ssd_step_host(ssd_handle h, const int8_t* actions_host, uint8_t* obs_host, int32_t* reward_host, void* stream) {
     if (check_handle(h)) return SSD_ERR_INVALID;
     h->chain.valid = false;
     if (!actions_host || !reward_host) return fail(SSD_ERR_INVALID, "actions_host and reward_host are required");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     const int N = h->cfg.num_agents, B = h->B, E = h->E;
-    if (!h->hs[0]) {
-        CUDA_TRY(cudaStreamCreateWithFlags(&h->hs[0], cudaStreamNonBlocking));
-        CUDA_TRY(cudaStreamCreateWithFlags(&h->hs[1], cudaStreamNonBlocking));
-        if (h->alloc(&h->d_act_stage, static_cast<size_t>(h->B_pad) * N) || h->alloc(&h->d_rew_stage, static_cast<size_t>(h->B_pad) * N) ||
-            h->alloc(&h->d_obs_stage, static_cast<size_t>(h->B_pad) * h->obs_env))
+    if (!h->host_ready) {
+        if (!h->hs[0]) CUDA_TRY(cudaStreamCreateWithFlags(&h->hs[0], cudaStreamNonBlocking));
+        if (!h->hs[1]) CUDA_TRY(cudaStreamCreateWithFlags(&h->hs[1], cudaStreamNonBlocking));
+        if (!h->host_ev) CUDA_TRY(cudaEventCreateWithFlags(&h->host_ev, cudaEventDisableTiming));
+        if ((!h->d_act_stage && h->alloc(&h->d_act_stage, static_cast<size_t>(h->B_pad) * N)) ||
+            (!h->d_rew_stage && h->alloc(&h->d_rew_stage, static_cast<size_t>(h->B_pad) * N)) ||
+            (!h->d_obs_stage && h->alloc(&h->d_obs_stage, static_cast<size_t>(h->B_pad) * h->obs_env)))
             return fail(SSD_ERR_CUDA, "staging allocation failed");
+        h->host_ready = true;
     }
+    // The chunks run on two internal non-blocking streams: make them wait for whatever the caller already queued on
+    // `stream` (an asynchronous ssd_reset / ssd_set_state / ssd_step writes the state these kernels read).
+    CUDA_TRY(cudaEventRecord(h->host_ev, static_cast<cudaStream_t>(stream)));
+    CUDA_TRY(cudaStreamWaitEvent(h->hs[0], h->host_ev, 0));
+    CUDA_TRY(cudaStreamWaitEvent(h->hs[1], h->host_ev, 0));
     // chunks of whole CTAs, ~8 per step, alternating between two streams so that the D2H copy of
     // chunk i overlaps the kernel of chunk i+1
     int chunk = ((B + 7) / 8 + E - 1) / E * E;

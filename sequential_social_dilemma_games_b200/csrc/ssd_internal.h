@@ -1,6 +1,7 @@
 // Internal definitions shared by the kernels (ssd_step.cu) and the C-ABI host layer (ssd_capi.cu).
 #pragma once
 #include <cstdint>
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 #include "../../include/ssd_b200.h"
@@ -52,6 +53,14 @@ __host__ __device__ constexpr uint8_t CB(uint8_t code) { return static_cast<uint
 #define SSD_SKIP(dbg, bit) (((dbg) & (bit)) != 0)
 #else
 #define SSD_SKIP(dbg, bit) false
+#endif
+// Environment-variable knobs of the tuning scripts under profiles/ (SSD_THREADS, SSD_EXTRA_SMEM, SSD_DEBUG_SKIP, SSD_NO_FAST,
+// SSD_CHAIN_ALWAYS, SSD_NO_PDL, SSD_EPW).  A production build never reads the environment: knob() is the constant nullptr unless
+// the library is built with -DSSD_PROFILING_KNOBS.
+#ifdef SSD_PROFILING_KNOBS
+inline const char* knob(const char* name) { return getenv(name); }
+#else
+inline const char* knob(const char*) { return nullptr; }
 #endif
 
 constexpr uint8_t kFlag = 0x80;
@@ -137,10 +146,11 @@ struct StepArgs {
     const uint64_t* waste_thr;   const double* waste_p;    // [area+1]
     // ---- state (device)
     uint8_t* grid;        // [B_pad][env_bytes]
-    uint32_t* agents;     // [B_pad][N] row | col<<8 | ori<<16
+    uint32_t* agents;     // [B_pad][N] row | col<<8 | ori<<16 | parked<<24 (parked: uploaded onto a '@' cell; never acts, never painted)
     uint8_t* beam_buf;    // [B_pad][64] raylen + firech between phase-split calls
     // ---- I/O (device)
     const int8_t* actions; const uint8_t* order; const uint8_t* mask;
+    const int32_t* rows; int n_rows;  // general kernel: step only these envs, one warp per listed row (ssd_reset_rows)
     const uint8_t* tape_move; const double* tape_u; int u_stride; const uint16_t* tape_waste; int32_t* n_draws_out;
     uint8_t* obs; int32_t* rew;
     unsigned long long* stats;
@@ -161,6 +171,7 @@ struct ChainState {
     int env_begin = 0, env_end = 0;
     uint32_t epoch = 0;
     uint32_t* done = nullptr;
+    int cta_slots = 0;          // resident CTAs of the handle's GPU at the step kernel's CTA shape (set by ssd_create)
 };
 
 struct ResetArgs {
@@ -170,6 +181,7 @@ struct ResetArgs {
     const uint16_t* spawn_key;  // [n_spawn] row<<8|col, canonical order
     const uint8_t* init_grid;   // [env_bytes]
     const uint8_t* mask;
+    const int32_t* rows; int n_rows;  // reset only these envs (ssd_reset_rows); NULL: all envs below env_end
     uint8_t* grid; uint32_t* agents;
 };
 
@@ -181,6 +193,8 @@ cudaError_t launch_step(const StepArgs& a, int threads, cudaStream_t stream, Cha
 cudaError_t launch_reset(const ResetArgs& a, cudaStream_t stream);
 cudaError_t launch_pack_state(int kind, int B, int N, int H, int W, int Ws, int env_bytes, const uint8_t* grid_in, const int16_t* pos_in,
                               const uint8_t* ori_in, uint8_t* grid, uint32_t* agents, cudaStream_t stream);
+// counts the agents whose (row, col) lies outside the map into *bad (device int, zeroed by the caller)
+cudaError_t launch_check_positions(int B, int N, int H, int W, const int16_t* pos_in, int* bad, cudaStream_t stream);
 cudaError_t launch_unpack_state(int B, int N, int H, int W, int Ws, int env_bytes, const uint8_t* grid, const uint32_t* agents,
                                 uint8_t* grid_out, int16_t* pos_out, uint8_t* ori_out, cudaStream_t stream);
 cudaError_t launch_render_map(int B, int N, int H, int W, int Ws, int env_bytes, const uint8_t* grid, const uint32_t* agents,

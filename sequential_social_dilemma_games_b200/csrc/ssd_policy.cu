@@ -526,6 +526,7 @@ int ssd_policy_features(ssd_policy_t p, const uint8_t* obs, int64_t num_agents, 
     if (reinterpret_cast<uintptr_t>(obs) % 16 != 0 || reinterpret_cast<uintptr_t>(features) % 16 != 0)
         return ssd::set_error(SSD_ERR_INVALID, "obs and features must be 16-byte aligned");
     if (num_agents == 0) return SSD_OK;
+    if (cudaSetDevice(p->device) != cudaSuccess) return ssd::set_error(SSD_ERR_CUDA, "cudaSetDevice failed");  // the blob and the stream live there
     const long long groups = (num_agents + GA - 1) / GA;
     const int grid = static_cast<int>(groups < p->sms ? groups : p->sms);
     policy_features_kernel<<<grid, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(obs, num_agents, p->d_blob, features);

@@ -288,6 +288,7 @@ int ssd_policy_lstm_heads(ssd_policy_t p, const float* features, const float* h_
     for (const void* q : ptrs)
         if (reinterpret_cast<uintptr_t>(q) % 16 != 0) return ssd::set_error(SSD_ERR_INVALID, "features and state pointers must be 16-byte aligned");
     if (num_agents == 0) return SSD_OK;
+    if (cudaSetDevice(p->device) != cudaSuccess) return ssd::set_error(SSD_ERR_CUDA, "cudaSetDevice failed");  // the blob and the stream live there
     const long long groups = (num_agents + GA - 1) / GA;
     const int grid = static_cast<int>(groups < p->sms ? groups : p->sms);
     lstm_heads_kernel<<<grid, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(

@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
         me.key = 0x0101; me.ori = 0; me.act = -1; me.rew = 0;
         if (valid) {
             const uint32_t w = __ldcg(a.agents + gi);  // L2: a chained predecessor may just have written it
-            me.act = a.actions[gi];
+            me.act = (w >> 24) & 1u ? -2 : a.actions[gi];  // -2: parked on a wall cell by ssd_set_state, never acts
             me.key = (w & 255) << 8 | ((w >> 8) & 255);
             me.ori = (w >> 16) & 3;
             S.order[al] = a.order != nullptr ? a.order[gi] : static_cast<uint8_t>(al);  // action-dict order (NULL: agent order)
@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
         // ---- phase C: overlay (get_map_with_agents map_env.py:280-302), view geometry, packed rows
         {
             const uint32_t same = __match_any_sync(0xffffffffu, valid ? (me.key | static_cast<uint32_t>(gbase) << 16) : (0x80000000u | lane));
-            if (valid && (31 - __clz(same)) == lane) g[my_idx] = agent_cell(al);  // the last agent on a cell wins
+            if (valid && (31 - __clz(same)) == lane && me.act != -2) g[my_idx] = agent_cell(al);  // the last agent on a cell wins
             __syncwarp();
             if (KIND == SSD_KIND_HARVEST && fmask) {  // all beams are 'F': the painting order is irrelevant
                 if ((fmask >> lane) & 1u) fire_list[__popc(fmask & lanemask_lt())] = fire_ent;  // the union was reused by the spawn pass
@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
                                 a.obs + static_cast<size_t>(we) * a.obs_env, EPW * N * VT, a.debug);
         }
         if (valid) {  // agent words and rewards last: no ordinary global store is in flight when the row loop fences
-            a.agents[gi] = (me.key >> 8) | (me.key & 255) << 8 | static_cast<uint32_t>(me.ori) << 16;
+            if (me.act != -2) a.agents[gi] = (me.key >> 8) | (me.key & 255) << 8 | static_cast<uint32_t>(me.ori) << 16;
             a.rew[gi] = me.rew;
         }
         if (a.publish) {  // everything this task wrote (grid, agent words, rewards, observation rows) is visible before the word is
@@ -430,8 +430,8 @@ cudaError_t launch_step(const StepArgs& a, int threads, cudaStream_t stream, Cha
     const bool fast_rows = (((32 / a.G) * a.obs_env) % 4 == 0) && (reinterpret_cast<uintptr_t>(a.obs) % 4 == 0);
     const bool tape = a.tape_u != nullptr || a.tape_move != nullptr;
     // a production step: everything the specialised kernel assumes (see ssd_step_fast_kernel)
-    static const bool no_fast = getenv("SSD_NO_FAST") != nullptr;
-    const bool full = !no_fast && !(chain && chain->general_only) && a.phases == SSD_PHASE_ALL && a.mask == nullptr && !a.use_beam_buf &&
+    static const bool no_fast = knob("SSD_NO_FAST") != nullptr;
+    const bool full = !no_fast && !(chain && chain->general_only) && a.phases == SSD_PHASE_ALL && a.mask == nullptr && a.rows == nullptr && !a.use_beam_buf &&
                       !a.rew_accumulate && a.obs != nullptr && a.rew != nullptr && a.actions != nullptr && fast_rows &&
                       (a.V == 11 || a.V == 15 || a.V == 21) && a.env_begin % (32 / a.G) == 0;
     if (!full) {
@@ -447,16 +447,10 @@ cudaError_t launch_step(const StepArgs& a, int threads, cudaStream_t stream, Cha
     // (profiles/r01h_sweep.md): chain between 1.5 and 12 waves.
     bool chain_here = false;
     if (chain && chain->enabled && chain->done != nullptr) {
-        static int slots = 0;  // resident CTAs of the whole GPU at this CTA shape (8 per SM on B200)
-        if (slots == 0) {
-            int dev = 0, sms = 148;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-            slots = sms * 8;
-        }
+        const int slots = chain->cta_slots > 0 ? chain->cta_slots : 148 * 8;  // resident CTAs of this handle's GPU (8 per SM on B200)
         const int ctas = (f.env_end - f.env_begin + (threads / 32) * epw - 1) / ((threads / 32) * epw);
         chain_here = 2 * ctas >= 3 * slots && ctas <= 12 * slots;
-        static const bool chain_always = getenv("SSD_CHAIN_ALWAYS") != nullptr;  // experiments
+        static const bool chain_always = knob("SSD_CHAIN_ALWAYS") != nullptr;  // experiments
         if (chain_always) chain_here = true;
     }
     if (chain_here) {
@@ -471,7 +465,7 @@ cudaError_t launch_step(const StepArgs& a, int threads, cudaStream_t stream, Cha
     } else if (chain) {
         chain->valid = false;
     }
-    static const bool no_pdl = getenv("SSD_NO_PDL") != nullptr;  // experiments
+    static const bool no_pdl = knob("SSD_NO_PDL") != nullptr;  // experiments
     f.pdl_wait = !f.dep_wait && !no_pdl;
     cudaError_t e = cudaSuccess;
 #define SSD_FAST(KIND_)                                                                                                     \

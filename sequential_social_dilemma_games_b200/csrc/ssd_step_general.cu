@@ -34,7 +34,14 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_kernel(const __grid_cons
     uint8_t* tiles = wbase + a.L.w_tiles;
     EnvScratch* envs = reinterpret_cast<EnvScratch*>(wbase + a.L.w_env);
     const int tile_pitch = a.env_bytes + a.pad_bytes;
-    const int we = a.env_begin + (blockIdx.x * nwarps + warp) * EPW;  // first local env of this warp
+    // a.rows (ssd_reset_rows): one warp per listed env; it loads the group of EPW envs around it and steps that one only
+    int we = a.env_begin + (blockIdx.x * nwarps + warp) * EPW;  // first local env of this warp
+    int row = -1;
+    if (a.rows != nullptr) {
+        const int wi = blockIdx.x * nwarps + warp;
+        row = wi < a.n_rows ? a.rows[wi] : -1;
+        we = (row >= 0 && row < a.env_end) ? row / EPW * EPW : a.env_end;
+    }
     const int nvalid = max(0, min(EPW, a.env_end - we));
     Counters cnt = {0, 0, 0, 0, 0, 0, 0};
 
@@ -58,7 +65,7 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_kernel(const __grid_cons
         EnvScratch& S = envs[j];
         uint8_t* g = tiles + a.pad_bytes + j * tile_pitch;
         const int e = we + j;
-        const bool active = j < nvalid && (a.mask == nullptr || a.mask[e] != 0);
+        const bool active = j < nvalid && (a.mask == nullptr || a.mask[e] != 0) && (a.rows == nullptr || e == row);
         const bool valid = al < N;
         const size_t gi = static_cast<size_t>(e) * N + (valid ? al : 0);
         PhiloxKey pk;
@@ -66,11 +73,13 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_kernel(const __grid_cons
         pk.env = static_cast<uint32_t>(a.env_id0 + static_cast<uint64_t>(e));
         AgentLane me;
         me.key = 0x0101; me.ori = 0; me.act = -1; me.rew = 0;
+        bool parked = false;  // uploaded onto a wall cell by ssd_set_state: never acts, never painted
         if (valid) {
             const uint32_t w = a.agents[gi];
             me.key = (w & 255) << 8 | ((w >> 8) & 255);
             me.ori = (w >> 16) & 3;
-            if (active && a.actions) me.act = a.actions[gi];
+            parked = (w >> 24) & 1u;
+            if (active && a.actions && !parked) me.act = a.actions[gi];
             if (active && a.rew_accumulate && a.rew) me.rew = a.rew[gi];
             S.order[al] = (active && a.order) ? a.order[gi] : static_cast<uint8_t>(al);
             S.rew[al] = 0;
@@ -123,19 +132,23 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_kernel(const __grid_cons
         if (valid && active) {
             me.rew += S.rew[al];  // -50 per hit taken
             if (phases & (SSD_PHASE_MOVES | SSD_PHASE_CONSUME | SSD_PHASE_BEAMS)) {
-                a.agents[gi] = (me.key >> 8) | (me.key & 255) << 8 | static_cast<uint32_t>(me.ori) << 16;
+                a.agents[gi] = (me.key >> 8) | (me.key & 255) << 8 | static_cast<uint32_t>(me.ori) << 16 | static_cast<uint32_t>(parked) << 24;
                 if (a.rew) a.rew[gi] = me.rew;
             }
         }
         // beams recorded by an earlier phase call of this step (phase-split mode only)
         if (a.use_beam_buf) {
-            const bool load = (phases & SSD_PHASE_RENDER) && !(phases & SSD_PHASE_BEAMS);
+            // a call that moves the agents without a beam phase starts a NEW step whose beams (if any) come from the caller's own
+            // custom_action hook: forget what an earlier step's device beam phase recorded, or a later RENDER call paints it
+            const bool fresh = (phases & SSD_PHASE_MOVES) && !(phases & SSD_PHASE_BEAMS);
+            const bool load = !fresh && (phases & SSD_PHASE_RENDER) && !(phases & SSD_PHASE_BEAMS);
             const bool store = (phases & SSD_PHASE_BEAMS) && !(phases & SSD_PHASE_RENDER);
             for (int q = 0; q < EPW; ++q) {
                 if (!envs[q].active) continue;
                 for (int i = lane; i < 64; i += 32) {
                     uint8_t* p = i < 48 ? &envs[q].raylen[i] : &envs[q].firech[i - 48];
                     uint8_t* gp = a.beam_buf + static_cast<size_t>(we + q) * 64 + i;
+                    if (fresh) { *gp = 0; *p = 0; }
                     if (load) *p = *gp;
                     if (store) *gp = *p;
                 }
@@ -179,7 +192,7 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_kernel(const __grid_cons
             {
                 const uint32_t key = valid ? S.pos[al] : 0x0101u;
                 const uint32_t same = __match_any_sync(0xffffffffu, valid ? (key | static_cast<uint32_t>(gbase) << 16) : (0x80000000u | lane));
-                if (valid && (31 - __clz(same)) == lane) g[tile_idx(a, key)] = agent_cell(al);
+                if (valid && (31 - __clz(same)) == lane && !parked) g[tile_idx(a, key)] = agent_cell(al);
                 __syncwarp();
                 if (KIND != SSD_KIND_PLAIN) {
                     for (int k = 0; k < N; ++k) {
@@ -204,7 +217,7 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_kernel(const __grid_cons
             for (int i = lane; i < EPW * N; i += 32) s_view[i] = view_param(a, envs[i / N], a.pad_bytes + (i / N) * tile_pitch, i % N);
             __syncwarp();
             uint8_t* dst = a.obs + static_cast<size_t>(we) * a.obs_env;
-            const bool all_active = (nvalid == EPW) && (a.mask == nullptr);
+            const bool all_active = (nvalid == EPW) && (a.mask == nullptr) && (a.rows == nullptr);
             if constexpr (VT > 0) {
                 if (all_active) render_rows<VT>(s_view, tiles, s_color, reinterpret_cast<uint32_t*>(wbase + a.L.w_union + a.L.u_stage), dst, EPW * N * VT);
                 else render_generic(a, envs, s_view, tiles, s_color, dst, nvalid);
@@ -238,7 +251,8 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_kernel(const __grid_cons
 template <int KIND, bool TAPE>
 static cudaError_t launch_v(const StepArgs& a, int threads, cudaStream_t stream, bool fast_rows) {
     const int envs_per_cta = (threads / 32) * (32 / a.G);
-    const int ctas = (a.env_end - a.env_begin + envs_per_cta - 1) / envs_per_cta;
+    const int ctas = a.rows != nullptr ? (a.n_rows + threads / 32 - 1) / (threads / 32)  // one warp per listed env
+                                       : (a.env_end - a.env_begin + envs_per_cta - 1) / envs_per_cta;
     if (ctas <= 0) return cudaSuccess;
     const int vt = fast_rows ? a.V : 0;
 #define SSD_LAUNCH(VT_)                                                                                         \

@@ -68,9 +68,7 @@ class SSDVectorEnv(object):
         return [self._wrap(obs, b) for b in range(self.num_envs)]
 
     def reset_at(self, index):
-        mask = torch.zeros(self.num_envs, dtype=torch.uint8, device=self.engine.device)
-        mask[index] = 1
-        obs = self.engine.reset(mask=mask)[index:index + 1].cpu().numpy()
+        obs = self.engine.reset_rows([int(index)])[index:index + 1].cpu().numpy()  # one warp, not a pass over all rows
         self._t[index] = 0
         return self._wrap(obs, 0)
 

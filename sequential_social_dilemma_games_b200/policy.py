@@ -63,6 +63,8 @@ class ConvToFCNet(object):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise _lib.SsdError("the policy trunk runs on a CUDA device only")
+        if self.device.index is None:  # 'cuda' means the current device, not device 0
+            self.device = torch.device("cuda", torch.cuda.current_device())
         w = {k: np.ascontiguousarray(v, dtype=np.float32) for k, v in weights.items()}
         for name, shape in (("conv_w", (3, 3, 3, CONV_FILTERS)), ("conv_b", (CONV_FILTERS,)), ("fc1_w", (FLAT, FEATURES)),
                             ("fc1_b", (FEATURES,)), ("fc2_w", (FEATURES, FEATURES)), ("fc2_b", (FEATURES,))):
@@ -71,7 +73,7 @@ class ConvToFCNet(object):
         self.weights = w
         self._h = C.c_void_p()
         ptr = lambda a: a.ctypes.data_as(C.c_void_p)
-        _lib.check(_lib.lib.ssd_policy_create(VIEW_RADIUS, self.device.index or 0, ptr(w["conv_w"]), ptr(w["conv_b"]), ptr(w["fc1_w"]),
+        _lib.check(_lib.lib.ssd_policy_create(VIEW_RADIUS, self.device.index, ptr(w["conv_w"]), ptr(w["conv_b"]), ptr(w["fc1_w"]),
                                               ptr(w["fc1_b"]), ptr(w["fc2_w"]), ptr(w["fc2_b"]), C.byref(self._h)))
         self.cell_size = w["lstm_u"].shape[0] if "lstm_u" in w else 0
         self.num_outputs = w["logits_w"].shape[1] if "logits_w" in w else 0

@@ -16,6 +16,12 @@ Two kinds of fixtures:
 Every fixture stores the initial state, the actions, and after EVERY step the reference's
 grid, positions, orientations, rewards and uint8 observations (the float64 observation is
 (u8 - 128.0) / 255.0 exactly; ref_harness.obs_u8 asserts that).
+
+The two 64-env fixtures (BASELINE.json configs[1] and configs[3]) are "seeded tapes": instead
+of ~10 MB of incompressible uniform doubles and shuffled waste orders they store the MT19937 states of
+np.random / random right after reset(); tests/golden_util.py regenerates the tape from them (the draw
+counts per step are stored, and this script asserts that the regenerated tape equals the recorded one).
+Observations are kept every `obs_every`-th step, everything else every step.
 """
 import os
 import random
@@ -55,7 +61,7 @@ def gen_actions(rng, cfg, t, steps, N, p_clean, p_fire, p_absent, shuffle_order)
 
 
 def record(name, kind, amap, N, n_envs, steps, view=7, mode="tape", p_clean=0.0, p_fire=0.0,
-           p_absent=0.0, shuffle_order=False, seed0=0, reset_at=()):
+           p_absent=0.0, shuffle_order=False, seed0=0, reset_at=(), seeded=False, obs_every=1):
     ref = rh.load_reference()
     cfg = EnvConfig(kind, amap, N, view_size=view)
     B, T, V, H, W = n_envs, steps, cfg.view_width, cfg.height, cfg.width
@@ -105,6 +111,15 @@ def record(name, kind, amap, N, n_envs, steps, view=7, mode="tape", p_clean=0.0,
             obs = env.reset()
             out["init_grid"][b], out["init_pos"][b], out["init_ori"][b] = rh.extract_state(env)
             store_obs(out["init_obs"][b], obs)
+            if seeded:
+                st = np.random.get_state()
+                assert st[0] == 'MT19937' and st[3] == 0
+                out.setdefault("np_state", np.zeros((B, 625), np.uint32))[b] = list(st[1]) + [st[2]]
+                ps = random.getstate()
+                assert ps[0] == 3 and ps[2] is None
+                out.setdefault("py_state", np.zeros((B, 625), np.uint32))[b] = ps[1]
+                if nw:
+                    out.setdefault("waste_init", np.zeros((B, nw), np.uint16))[b] = [int(r) * W + int(c) for r, c in env.waste_points]
             for t in range(T):
                 if t in reset_at:
                     assert mode == "philox"
@@ -143,6 +158,22 @@ def record(name, kind, amap, N, n_envs, steps, view=7, mode="tape", p_clean=0.0,
                     events["apple_prob_steps"] += env.current_apple_spawn_prob > 0
     if mode == "tape":
         out["u_flat"] = np.array([x for t in range(T) for b in range(B) for x in u_chunks[t][b]], np.float64)
+    if seeded:  # keep the generator states, drop what they regenerate (after checking that they do)
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import golden_util
+        u_re, w_re = golden_util.regenerate_tape(out)
+        off = 0
+        for t in range(T):
+            for b in range(B):
+                n = int(out["n_draws"][t, b])
+                assert np.array_equal(u_re[t, b, :n], out["u_flat"][off:off + n]), (name, t, b)
+                off += n
+        sh = out["waste_shuffled"].astype(bool)  # steps without a waste pass recorded the canonical order as a placeholder
+        assert np.array_equal(w_re[sh], out["waste_order"][sh]), name
+        del out["u_flat"], out["waste_order"]
+    if obs_every > 1:
+        keep = np.array(sorted(set(range(0, T, obs_every)) | {T - 1}), np.int32)
+        out["obs_steps"], out["obs"] = keep, out["obs"][keep]
     path = os.path.join(OUT, name + ".npz")
     np.savez_compressed(path, **out)
     print("%-28s %7.1f KB  %s" % (name, os.path.getsize(path) / 1024.0, events))
@@ -150,6 +181,11 @@ def record(name, kind, amap, N, n_envs, steps, view=7, mode="tape", p_clean=0.0,
 
 def main():
     tiled = tile_map(CLEANUP_MAP)
+    only = sys.argv[1:]
+    if only:  # python tests/golden/make_golden.py cleanup_tape64 ...: regenerate the named fixtures only
+        global record
+        _rec = record
+        record = lambda name, *a, **k: _rec(name, *a, **k) if name in only else None
     record("harvest_tape", KIND_HARVEST, HARVEST_MAP, 5, 8, 150, p_fire=0.1)
     record("cleanup_tape", KIND_CLEANUP, CLEANUP_MAP, 5, 8, 250, p_clean=0.4, p_fire=0.05)
     record("cleanup10_tiled_tape", KIND_CLEANUP, tiled, 10, 4, 80, p_clean=0.3, p_fire=0.25, seed0=50)
@@ -158,6 +194,11 @@ def main():
     record("harvest_r10_tape", KIND_HARVEST, HARVEST_MAP, 5, 2, 40, view=10, p_fire=0.15, seed0=32)
     record("cleanup_order_tape", KIND_CLEANUP, CLEANUP_MAP, 5, 4, 120, p_clean=0.4, p_fire=0.1,
            p_absent=0.15, shuffle_order=True, seed0=40)
+    # BASELINE.json configs[1] / SURVEY 8d config 2: 64 distinct reference envs x 200 steps (tiled to 4096 slots by the test);
+    # CLEAN-biased for the first 120 steps so that the waste density falls below the depletion threshold
+    record("cleanup_tape64", KIND_CLEANUP, CLEANUP_MAP, 5, 64, 200, p_clean=0.35, p_fire=0.05, seed0=100, seeded=True, obs_every=5)
+    # BASELINE.json configs[3] / SURVEY 8d config 4: 64 reference envs on the 2x2-tiled map, 10 agents, P(FIRE) = P(CLEAN) = 0.25
+    record("cleanup10_tiled_tape64", KIND_CLEANUP, tiled, 10, 64, 80, p_clean=0.25, p_fire=0.25, seed0=200, seeded=True, obs_every=8)
     record("harvest_philox", KIND_HARVEST, HARVEST_MAP, 5, 4, 100, mode="philox", p_fire=0.1, reset_at=(50,))
     record("cleanup_philox", KIND_CLEANUP, CLEANUP_MAP, 5, 4, 160, mode="philox", p_clean=0.5, reset_at=(130,))
     record("cleanup10_tiled_philox", KIND_CLEANUP, tiled, 10, 2, 90, mode="philox", p_clean=0.65, p_fire=0.1, seed0=3)

@@ -102,20 +102,38 @@ def test_philox_golden(name, explicit_order):
             assert np.array_equal(obs.cpu().numpy()[0], fx["obs"][t, b]), (name, b, t)
 
 
-def test_config2_cleanup_4096_tape():
-    """BASELINE.json configs[1]: CleanupEnv, 5 agents, 4096 batched envs, bit-exact vs the reference
-    under replayed RNG: the 8 reference trajectories of cleanup_tape are tiled over 4096 slots."""
-    fx = Fixture("cleanup_tape")
-    B = 4096
+def _replay_tiled(name, B, check_every):
+    fx = Fixture(name)
     sel = np.arange(B) % fx.B
     env = _env(fx.cfg, B)
     env.set_state(fx["init_grid"][sel], fx["init_pos"][sel], fx["init_ori"][sel])
+    assert np.array_equal(env.render(rotate=False).cpu().numpy(), fx["init_obs"][sel])
     for t in range(fx.T):
         obs, rew = env.step(fx["actions"][t][sel], action_order=_order(fx, t, sel), tape=fx.tape(t, sel))  # agent order: specialised kernel
-        if t % 10 == 0 or t == fx.T - 1:
-            _assert_state(env, fx["grid"][t][sel], fx["pos"][t][sel], fx["ori"][t][sel], ("cfg2", t))
-            assert np.array_equal(obs.cpu().numpy(), fx["obs"][t][sel]), ("cfg2", t)
-        assert np.array_equal(rew.cpu().numpy(), fx["reward"][t][sel]), ("cfg2", t)
+        if t % check_every == 0 or t == fx.T - 1:
+            _assert_state(env, fx["grid"][t][sel], fx["pos"][t][sel], fx["ori"][t][sel], (name, t))
+        if fx.has_obs(t):
+            assert np.array_equal(obs.cpu().numpy(), fx.obs_at(t)[sel]), (name, t)
+        assert np.array_equal(rew.cpu().numpy(), fx["reward"][t][sel]), (name, t)
+    st = env.stats()
+    assert st["env_steps"] == fx.T * B and st["reward_sum"] == int(fx["reward"][:, sel].sum())
+    return fx
+
+
+def test_config2_cleanup_4096_tape():
+    """BASELINE.json configs[1] as SURVEY.md 8d specifies it: CleanupEnv, 5 agents, 4096 batched envs on one GPU, bit-exact
+    vs the reference under replayed RNG -- 64 DISTINCT reference envs (seeds 100..163) x 200 steps, CLEAN-biased so that the
+    waste and fractional-apple paths execute, tiled over the 4096 slots; rewards every step, state every 5th, observations
+    on the steps the fixture keeps (every 5th)."""
+    fx = _replay_tiled("cleanup_tape64", 4096, 5)
+    assert fx.B == 64 and fx.T >= 200
+
+
+def test_config4_cleanup10_tiled_64_reference_envs():
+    """BASELINE.json configs[3] parity spot-check: 64 reference envs on the 2x2-tiled Cleanup map,
+    10 agents (agent-9 renders as '1'), P(FIRE) = P(CLEAN) = 0.25, replayed on the device in 1024 slots."""
+    fx = _replay_tiled("cleanup10_tiled_tape64", 1024, 4)
+    assert fx.B == 64 and fx.N == 10
 
 
 def _random_actions(rng, cfg, B, p_clean=0.0):

@@ -110,3 +110,42 @@ def test_two_rank_stats_reduction_gloo():
     assert t0 == t1 and s0 == s1 == 2.0
     assert span0 == (0, 501) and span1 == (501, 1001)
     assert t0["env_steps"] == 10010 and t0["apples_eaten"] == sum(range(1001)) and t0["reward_sum"] == -501
+
+
+def test_policy_ref_hand_vector():
+    """oracle/policy_ref.py (the float64 checker of the policy kernels, restating models/conv_to_fcnet_v2.py:36-92 and the
+    tf.keras 2.0 LSTMCell) on a vector that can be computed by hand: all pixels 255 -> x = 127/255 =: a; every conv tap
+    1/27 -> relu(conv) = a; fc1 = 1/1014, fc2 = 1/32 -> features = a; LSTM kernels 0 and bias (i, f, c~, o) = (0, 0, 20, 0)
+    -> i = o = 1/2, tanh(20) = 1 to 1e-17, c' = 1/2, h' = tanh(1/2) / 2; logits column j = j / 128 -> j * h', value = -h'."""
+    from oracle import policy_ref
+    u, A = 128, 4
+    w = {"conv_w": np.full((3, 3, 3, 6), 1 / 27.0), "conv_b": np.zeros(6), "fc1_w": np.full((1014, 32), 1 / 1014.0),
+         "fc1_b": np.zeros(32), "fc2_w": np.full((32, 32), 1 / 32.0), "fc2_b": np.zeros(32),
+         "lstm_w": np.zeros((32, 4 * u)), "lstm_u": np.zeros((u, 4 * u)),
+         "lstm_b": np.concatenate([np.zeros(2 * u), np.full(u, 20.0), np.zeros(u)]),
+         "logits_w": np.tile(np.arange(A) / 128.0, (u, 1)), "logits_b": np.zeros(A),
+         "value_w": np.full((u, 1), -1 / 128.0), "value_b": np.zeros(1)}
+    obs = np.full((2, 15, 15, 3), 255, np.uint8)
+    a = 127.0 / 255.0
+    assert np.allclose(policy_ref.features(w, obs), a, rtol=0, atol=1e-13)
+    logits, value, h, c = policy_ref.forward(w, obs, np.zeros((2, u)), np.zeros((2, u)))
+    hh = 0.5 * np.tanh(0.5)                       # 0.23105857863000490
+    assert abs(hh - 0.2310585786300049) < 1e-15
+    assert np.allclose(c, 0.5, rtol=0, atol=1e-12) and np.allclose(h, hh, rtol=0, atol=1e-12)
+    assert np.allclose(logits, np.arange(A) * hh, rtol=0, atol=1e-12) and np.allclose(value, -hh, rtol=0, atol=1e-12)
+    # second step from that state, gates now see h through a recurrent kernel: u_f = 1/128 on every unit -> z_f = h' * 1 = hh
+    w["lstm_u"][:, u:2 * u] = 1 / 128.0
+    _, _, h2, c2 = policy_ref.forward(w, obs, h, c)
+    f = 1 / (1 + np.exp(-hh))
+    assert np.allclose(c2, f * 0.5 + 0.5, rtol=0, atol=1e-12) and np.allclose(h2, 0.5 * np.tanh(f * 0.5 + 0.5), rtol=0, atol=1e-12)
+    # an asymmetric conv check: one tap only -> the conv output is that shifted pixel (kernel layout [kh, kw, in, out])
+    w2 = dict(w, conv_w=np.zeros((3, 3, 3, 6)))
+    w2["conv_w"][2, 0, 1, 4] = 1.0                # filter 4 reads channel 1 at (i + 2, j + 0)
+    rng = np.random.RandomState(0)
+    ob = rng.randint(0, 256, size=(1, 15, 15, 3)).astype(np.uint8)
+    x = (ob.astype(np.float64) - 128.0) / 255.0
+    want = np.zeros((13, 13, 6))
+    want[:, :, 4] = np.maximum(x[0, 2:15, 0:13, 1], 0)
+    fc_in = want.reshape(-1)                      # keras Flatten order (row, col, filter)
+    got = policy_ref.features(dict(w2, fc1_w=np.eye(1014)[:, :32] * 1.0, fc2_w=np.eye(32)), ob)
+    assert np.allclose(got[0], fc_in[:32], rtol=0, atol=1e-15)

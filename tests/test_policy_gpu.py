@@ -1,13 +1,18 @@
-"""The fused policy trunk (csrc/ssd_policy.cu) against a plain PyTorch fp32 reference of the same layers
-(models/conv_to_fcnet_v2.py:36-66 on (obs - 128) / 255).  The kernel multiplies fp16 operands (weights and activations
-rounded to 11 significant bits) and accumulates in fp32, so the comparison is to a stated tolerance, not bit-exact."""
+"""The fused policy kernels (csrc/ssd_policy.cu, ssd_policy_head.cu) against two independent checkers of the same
+layers (models/conv_to_fcnet_v2.py:36-92 on (obs - 128) / 255): oracle/policy_ref.py, a float64 numpy restatement pinned by a
+hand-computed vector (tests/test_host_logic.py), and a plain PyTorch fp32 implementation.  The kernels multiply fp16
+operands (weights and activations rounded to 11 significant bits), accumulate in fp32 and use tanh.approx in the LSTM, so the
+comparison is to a stated tolerance, not bit-exact: measured max abs errors are 2-3e-4 on the trunk features (values O(1))
+and below 1e-3 on logits / value / state after three recurrent steps; the asserted bounds are 2e-3 and 5e-3."""
 import numpy as np
 import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
 
-ATOL, RTOL = 2e-2, 2e-2   # fp16 operand rounding through three layers; features are O(1)
+TRUNK_TOL = 2e-3    # max abs error of the trunk features (fp16 operand rounding through three layers; features are O(1))
+FWD_TOL = 5e-3      # max abs error of logits / value / h / c over three recurrent steps (adds tanh.approx and fp16 h)
+ATOL, RTOL = TRUNK_TOL, 0.0
 
 
 def _reference_features(w, obs):
@@ -35,7 +40,12 @@ def test_trunk_matches_fp32_reference_random_pixels(m):
     assert got.shape == (m, 32)
     assert torch.isfinite(got).all()
     err = (got - want).abs().max().item()
-    assert torch.allclose(got, want, atol=ATOL, rtol=RTOL), "max abs err %g (ref max %g)" % (err, want.abs().max().item())
+    assert err < TRUNK_TOL, "max abs err %g vs torch fp32 (ref max %g)" % (err, want.abs().max().item())
+    from oracle import policy_ref
+    want64 = policy_ref.features(w, obs.cpu().numpy())           # float64 numpy oracle
+    err64 = np.abs(got.cpu().numpy().astype(np.float64) - want64).max()
+    assert err64 < TRUNK_TOL, "max abs err %g vs the float64 oracle" % err64
+    assert np.abs(want.cpu().numpy() - want64).max() < 1e-4       # the two checkers agree far below the kernel's tolerance
     assert want.abs().max().item() > 0.1   # the comparison is not vacuous
 
 
@@ -63,6 +73,8 @@ def test_forward_matches_fp32_reference_over_steps():
     assert h.shape == (8, 8, 128, 16)
     hr, cr = torch.zeros((m, 128), device="cuda"), torch.zeros((m, 128), device="cuda")
     hu, cu = hr.clone(), cr.clone()
+    from oracle import policy_ref
+    h64, c64 = np.zeros((m, 128)), np.zeros((m, 128))
     assert torch.equal(net.state_rows(net.state_from_rows(torch.arange(m * 128.0, device="cuda").reshape(m, 128)), m),
                        torch.arange(m * 128.0, device="cuda").reshape(m, 128))
     for _ in range(3):
@@ -71,9 +83,12 @@ def test_forward_matches_fp32_reference_over_steps():
         l2, v2, h2, c2 = net.forward_unfused(obs, hu, cu)       # library GEMMs + one-pass cell update
         hu, cu = h2, c2
         lr, vr, hr, cr = _reference_forward(w, obs, hr, cr)
+        l64, v64, h64, c64 = policy_ref.forward(w, obs.cpu().numpy(), h64, c64)   # float64 numpy oracle carried alongside
         assert logits.shape == (m, 9) and value.shape == (m,)
-        for got, want in ((logits, lr), (value, vr), (net.state_rows(h, m), hr), (net.state_rows(c, m), cr)):
-            assert torch.allclose(got, want, atol=2e-2, rtol=2e-2), (got - want).abs().max().item()   # fp16 operands, fp32 accumulation
+        for got, want, w64 in ((logits, lr, l64), (value, vr, v64), (net.state_rows(h, m), hr, h64), (net.state_rows(c, m), cr, c64)):
+            assert (got - want).abs().max().item() < FWD_TOL, (got - want).abs().max().item()   # fp16 operands, fp32 accumulation, tanh.approx
+            assert np.abs(got.cpu().numpy().astype(np.float64) - w64).max() < FWD_TOL
+            assert np.abs(want.cpu().numpy().astype(np.float64) - w64).max() < 2e-4           # torch fp32 vs float64: the checkers agree
         for got, want in ((l2, lr), (v2, vr), (h2, hr), (c2, cr)):
             assert torch.allclose(got, want, atol=3e-2, rtol=3e-2), (got - want).abs().max().item()   # bf16 operands: 8 significant bits
     net.close()
@@ -120,7 +135,7 @@ def test_trunk_on_env_observations_and_rollout_loop():
         flat = obs.reshape(-1, 15, 15, 3)
         got = net.features(flat)
         want = _reference_features(w, flat)
-        assert torch.allclose(got, want, atol=ATOL, rtol=RTOL), (got - want).abs().max().item()
+        assert (got - want).abs().max().item() < TRUNK_TOL, (got - want).abs().max().item()
         a, value, h, c = net.act(flat, h, c, generator=gen)
         assert a.dtype == torch.int8 and int(a.min()) >= 0 and int(a.max()) < 8
         obs, rew = env.step(a.reshape(300, 5))
