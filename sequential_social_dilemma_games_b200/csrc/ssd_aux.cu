@@ -44,6 +44,8 @@ __global__ void __launch_bounds__(128) ssd_reset_kernel(const ResetArgs a) {
     const uint4* src = reinterpret_cast<const uint4*>(a.init_grid);
     uint4* dst = reinterpret_cast<uint4*>(a.grid + static_cast<size_t>(e) * a.env_bytes);
     for (int i = 0; i < a.env_bytes / 16; ++i) dst[i] = src[i];
+    if (a.orch != nullptr)  // every apple point holds an apple again: empty orchard bitmaps
+        for (int i = 0; i < a.orch_stride; ++i) a.orch[static_cast<size_t>(e) * a.orch_stride + i] = i == 0 ? a.orch_word0 : 0u;
 }
 
 // ====================================================================== state pack / unpack, selftest
@@ -107,6 +109,27 @@ __global__ void pack_state_kernel(int kind, int B, int N, int H, int W, int Ws, 
         agents[i] = (r & 255) | (c & 255) << 8 | static_cast<uint32_t>(ori_in[i] & 3) << 16 | parked << 24;
     }
 }
+// Orchard bitmaps of one env from its grid (ssd_internal.h, StepArgs::orch): one warp per env.
+__global__ void build_orch_kernel(int kind, int B, int n_apple, int nW, int orch_stride, int harvest_nz, int env_bytes, const uint16_t* apple_cell,
+                                  const uint8_t* grid, uint32_t* orch) {
+    const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (e >= B) return;
+    const uint8_t* g = grid + static_cast<size_t>(e) * env_bytes;
+    if (kind == SSD_KIND_CLEANUP) {  // word 0: the number of 'H' cells
+        int nh = 0;
+        for (int i = lane; i < env_bytes; i += 32) nh += (g[i] & 0x7F) == CB(C_WASTE);
+        nh = __reduce_add_sync(0xffffffffu, nh);
+        if (lane == 0) orch[static_cast<size_t>(e) * orch_stride] = static_cast<uint32_t>(nh);
+        return;
+    }
+    for (int w = 0; w < nW; ++w) {
+        const int i = 32 * w + lane;
+        const uint8_t c = i < n_apple ? g[apple_cell[i]] : 0;
+        const bool emp = i < n_apple && (c & kCodeMask) == CB(C_EMPTY);
+        const uint32_t me = __ballot_sync(0xffffffffu, emp), mn = __ballot_sync(0xffffffffu, emp && ((harvest_nz >> (c & 3)) & 1));
+        if (lane == 0) { orch[static_cast<size_t>(e) * orch_stride + w] = me; orch[static_cast<size_t>(e) * orch_stride + nW + w] = mn; }
+    }
+}
 __global__ void check_positions_kernel(int B, int N, int H, int W, const int16_t* pos_in, int* bad) {
     const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= static_cast<size_t>(B) * N) return;
@@ -156,6 +179,12 @@ cudaError_t launch_reset(const ResetArgs& a, cudaStream_t stream) {
     const int n = a.rows != nullptr ? a.n_rows : a.env_end;
     if (n <= 0) return cudaSuccess;
     ssd_reset_kernel<<<(n + 127) / 128, 128, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t launch_build_orch(int kind, int B, int n_apple, int nW, int orch_stride, int harvest_nz, int env_bytes, const uint16_t* apple_cell,
+                              const uint8_t* grid, uint32_t* orch, cudaStream_t stream) {
+    if (B <= 0 || orch_stride <= 0) return cudaSuccess;
+    build_orch_kernel<<<(B + 3) / 4, 128, 0, stream>>>(kind, B, n_apple, nW, orch_stride, harvest_nz, env_bytes, apple_cell, grid, orch);
     return cudaGetLastError();
 }
 cudaError_t launch_check_positions(int B, int N, int H, int W, const int16_t* pos_in, int* bad, cudaStream_t stream) {

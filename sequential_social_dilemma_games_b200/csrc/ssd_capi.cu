@@ -62,6 +62,9 @@ struct SsdEnv {
     uint64_t* d_athr = nullptr; double* d_ap = nullptr; uint64_t* d_wthr = nullptr; double* d_wp = nullptr;
     uint8_t* d_init_grid = nullptr;
     uint8_t* d_grid = nullptr; uint32_t* d_agents = nullptr; uint8_t* d_beam_buf = nullptr;
+    uint32_t* d_orch = nullptr; uint32_t* d_pt_mask = nullptr; uint16_t* d_pt_pre = nullptr;
+    int nW = 0, orch_stride = 0, use_orch = 0;
+    uint32_t init_waste = 0;  // 'H' cells of the reset grid (Cleanup)
     unsigned long long* d_stats = nullptr;
     int* d_bad = nullptr;  // ssd_set_state: number of agent positions outside the map
     int32_t* d_rows = nullptr; int rows_cap = 0;  // ssd_reset_rows: device copy of a host row list
@@ -102,18 +105,28 @@ ssd::SmemLayout make_layout(const SsdEnv& h, int threads, bool fast = false) {
     const uint32_t G = h.cfg.num_agents <= 8 ? 8 : 16, epw = 32 / G;
     uint32_t off = 0;
     L.apple = off; off += up16(((h.n_apple + 63) & ~63) * 2);  // padded to two whole warps
+    const uint32_t orch_bytes = (fast && h.use_orch) ? epw * h.orch_stride * 4u : 0u;
+    if (orch_bytes) {  // cell -> apple-point tables of the orchard bitmaps
+        const uint32_t ncw = (h.env_bytes + 31) / 32;
+        L.pt_mask = off; off += up16(ncw * 4);
+        L.pt_pre = off; off += up16(ncw * 2);
+    }
     L.warp0 = off;
     uint32_t w = 0;
     L.w_mbar = w; w += 16;
     L.w_tiles = w; w += epw * (h.env_bytes + h.pad_bytes) + h.pad_bytes;
-    L.w_env = w; w += epw * (fast ? 10u * G : sizeof(ssd::EnvScratch));  // FastScratchT<G> is 10 bytes per lane
+    L.w_env = w; w += epw * (fast ? 10u * G + 16u : sizeof(ssd::EnvScratch));  // FastScratchT<G> is 10 bytes per lane + 16
     L.w_union = w;
     L.u_stage = up16(epw * h.cfg.num_agents * 8);                          // view params first
     const uint32_t u_render = L.u_stage + up16(32u * 3u * h.V) + 32;       // + staging of 32 view rows, spill and dummy words
     const uint32_t u_spawn = up16(std::max(std::max(h.n_apple * 4, h.n_waste * 4), h.cfg.kind == SSD_KIND_CLEANUP ? 512 : 0)); // need-list / waste keys / 32 Philox blocks
     const uint32_t u_moves = epw * sizeof(ssd::MoveScratch);
-    L.u_words = std::max(u_render, std::max(u_spawn, u_moves)) / 4;
-    w += 4 * L.u_words;
+    // the orchard bitmaps sit behind whatever phases A and B keep in the union (they are stored back before phase C reuses it)
+    const uint32_t u_ab = up16(std::max(u_spawn, std::max(u_moves, 32u * 4u)));  // need-list / move scratch / fire list
+    L.u_orch = u_ab;
+    const uint32_t union_bytes = std::max(u_render, u_ab + orch_bytes);
+    L.u_words = (orch_bytes ? u_ab : union_bytes) / 4;  // capacity of the candidate list
+    w += union_bytes;
     if (const char* x = ssd::knob("SSD_EXTRA_SMEM")) w += up16(static_cast<uint32_t>(atoi(x)));  // occupancy experiments
     L.warp_stride = w;
     L.total = off + (threads / 32) * w;
@@ -127,6 +140,8 @@ void fill_args(SsdEnv* h, ssd::StepArgs& a) {
     a.beam_len = c.beam_len; a.Ws = h->Ws; a.env_bytes = h->env_bytes; a.pad_bytes = h->pad_bytes;
     a.n_apple = h->n_apple; a.n_waste = h->n_waste; a.area = c.potential_waste_area;
     a.harvest_nz = h->harvest_nz;
+    a.nW = h->nW; a.orch_stride = h->orch_stride; a.use_orch = h->use_orch;
+    a.orch = h->d_orch; a.pt_mask = h->d_pt_mask; a.pt_pre = h->d_pt_pre;
     { static const int dbg = ssd::knob("SSD_DEBUG_SKIP") ? atoi(ssd::knob("SSD_DEBUG_SKIP")) : 0; a.debug = dbg; }
     a.obs_env = h->obs_env;
     a.G = h->cfg.num_agents <= 8 ? 8 : 16; a.env_begin = 0; a.env_end = h->B;
@@ -257,6 +272,22 @@ int ssd_create(const SsdConfig* cfg, ssd_handle* out) {
         ap.push_back(pa); athr.push_back(threshold53(pa)); wp.push_back(pw); wthr.push_back(threshold53(pw));
     }
 
+    // Harvest orchard bitmaps (ssd_internal.h): two bitmaps over the apple points per env; the specialised kernel scans them
+    // when all the words of a warp's envs fit one pass of 32 lanes
+    std::vector<uint32_t> pt_mask((h->env_bytes + 31) / 32, 0);
+    std::vector<uint16_t> pt_pre((h->env_bytes + 31) / 32, 0);
+    if (cfg->kind == SSD_KIND_HARVEST && h->n_apple > 0) {
+        h->nW = (h->n_apple + 31) / 32;
+        h->orch_stride = (2 * h->nW + 3) & ~3;
+        h->use_orch = (N <= 8 ? 4 : 2) * h->nW <= 32 && !ssd::knob("SSD_NO_ORCH");
+        for (uint16_t c : apple) pt_mask[c >> 5] |= 1u << (c & 31);
+        for (size_t w2 = 1; w2 < pt_mask.size(); ++w2) pt_pre[w2] = static_cast<uint16_t>(pt_pre[w2 - 1] + __builtin_popcount(pt_mask[w2 - 1]));
+    }
+    if (cfg->kind == SSD_KIND_CLEANUP) {  // word 0 of an env's record: its number of 'H' cells
+        h->orch_stride = 4;
+        for (uint8_t c : init_grid) h->init_waste += c == ssd::CB(ssd::C_WASTE);
+    }
+
     // CTA shape: every warp owns 32/G envs; SSD_THREADS (64, 128 or 256) overrides the CTA size for tuning.
     const int smem_max = static_cast<int>(prop.sharedMemPerBlockOptin);
     auto env_int = [](const char* name, int dflt) { const char* v = ssd::knob(name); return v && *v ? atoi(v) : dflt; };
@@ -289,6 +320,8 @@ int ssd_create(const SsdConfig* cfg, ssd_handle* out) {
     bad |= h->alloc(&h->d_grid, static_cast<size_t>(h->B_pad) * h->env_bytes);
     bad |= h->alloc(&h->d_agents, static_cast<size_t>(h->B_pad) * N);
     bad |= h->alloc(&h->d_beam_buf, static_cast<size_t>(h->B_pad) * 64);
+    bad |= h->alloc(&h->d_orch, static_cast<size_t>(h->B_pad) * std::max(h->orch_stride, 4));
+    bad |= h->upload(&h->d_pt_mask, pt_mask); bad |= h->upload(&h->d_pt_pre, pt_pre);
     bad |= h->alloc(&h->d_stats, static_cast<size_t>(SSD_NUM_STATS));
     bad |= h->alloc(&h->chain.done, static_cast<size_t>(h->B_pad / 2 + 1));  // one word per task (4 or 2 envs)
     bad |= h->alloc(&h->d_bad, 1);
@@ -305,6 +338,13 @@ int ssd_create(const SsdConfig* cfg, ssd_handle* out) {
         cudaError_t e3 = cudaMemset(h->d_stats, 0, SSD_NUM_STATS * sizeof(unsigned long long));
         cudaError_t e4 = cudaMemset(h->d_beam_buf, 0, static_cast<size_t>(h->B_pad) * 64);
         if (e4 == cudaSuccess) e4 = cudaMemset(h->chain.done, 0, (static_cast<size_t>(h->B_pad) / 2 + 1) * sizeof(uint32_t));
+        // every apple point holds an apple after reset_map (harvest.py:57-60): both orchard bitmaps are empty
+        if (e4 == cudaSuccess) e4 = cudaMemset(h->d_orch, 0, static_cast<size_t>(h->B_pad) * std::max(h->orch_stride, 4) * sizeof(uint32_t));
+        if (e4 == cudaSuccess && cfg->kind == SSD_KIND_CLEANUP) {
+            std::vector<uint32_t> o(static_cast<size_t>(h->B_pad) * 4, 0u);
+            for (int b = 0; b < h->B_pad; ++b) o[static_cast<size_t>(b) * 4] = h->init_waste;
+            e4 = cudaMemcpy(h->d_orch, o.data(), o.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
+        }
         if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess) {
             ssd_destroy(h);
             return fail(SSD_ERR_CUDA, "state initialisation failed");
@@ -379,6 +419,10 @@ int ssd_set_state(ssd_handle h, const uint8_t* grid, const int16_t* pos, const u
     }
     CUDA_TRY(ssd::launch_pack_state(h->cfg.kind, h->B, N, h->cfg.height, h->cfg.width, h->Ws, h->env_bytes, grid, pos, ori, h->d_grid, h->d_agents, st));
     h->launches++;
+    if (h->orch_stride > 0) {
+        CUDA_TRY(ssd::launch_build_orch(h->cfg.kind, h->B, h->n_apple, h->nW, h->orch_stride, h->harvest_nz, h->env_bytes, h->d_apple, h->d_grid, h->d_orch, st));
+        h->launches++;
+    }
     return SSD_OK;
 }
 
@@ -420,6 +464,7 @@ static int reset_impl(ssd_handle h, const uint8_t* mask, const int32_t* rows, in
     r.key0 = static_cast<uint32_t>(h->seed); r.key1 = static_cast<uint32_t>(h->seed >> 32); r.t = h->t;
     r.env_id0 = h->cfg.env_id_offset;
     r.spawn_key = h->d_spawn; r.init_grid = h->d_init_grid; r.mask = mask; r.rows = rows; r.n_rows = n_rows; r.grid = h->d_grid; r.agents = h->d_agents;
+    r.orch = h->orch_stride > 0 ? h->d_orch : nullptr; r.orch_stride = h->orch_stride; r.orch_word0 = h->init_waste;
     CUDA_TRY(ssd::launch_reset(r, st));
     ssd::StepArgs a;
     fill_args(h, a);
@@ -459,7 +504,7 @@ int ssd_step_phases(ssd_handle h, int phases, const int8_t* actions, const uint8
     if (check_handle(h)) return SSD_ERR_INVALID;
     if ((phases & ~SSD_PHASE_ALL) || phases == 0) return fail(SSD_ERR_INVALID, "bad phase mask %d", phases);
     if ((phases & (SSD_PHASE_MOVES | SSD_PHASE_BEAMS)) && !actions) return fail(SSD_ERR_INVALID, "actions are required");
-    if (tape && h->cfg.kind == SSD_KIND_CLEANUP && !tape->waste_order && (phases & SSD_PHASE_SPAWN))
+    if (tape && h->cfg.kind == SSD_KIND_CLEANUP && h->n_waste > 0 && !tape->waste_order && (phases & SSD_PHASE_SPAWN))
         return fail(SSD_ERR_INVALID, "tape.waste_order is required for Cleanup");
     if (tape && (!tape->move_order || !tape->uniforms)) return fail(SSD_ERR_INVALID, "tape.move_order and tape.uniforms are required");
     CUDA_TRY(cudaSetDevice(h->cfg.device));

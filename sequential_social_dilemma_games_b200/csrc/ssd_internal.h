@@ -91,8 +91,10 @@ struct FastScratchT {
     int32_t rew[G];   // 32-bit: rays of different shooters add their -50 with shared-memory atomics
     uint8_t raylen[3 * G];
     uint8_t order[G];
+    int32_t hcount;   // Cleanup: running number of 'H' cells of the env (StepArgs::orch word 0)
+    int32_t pad[3];
 };
-static_assert(sizeof(FastScratchT<8>) == 80 && sizeof(FastScratchT<16>) == 160, "FastScratchT is 10 bytes per lane");
+static_assert(sizeof(FastScratchT<8>) == 96 && sizeof(FastScratchT<16>) == 176, "FastScratchT is 10 bytes per lane + 16");
 
 // Scratch of the literal update_moves emulation (moves_slow); lives in the per-warp phase union.
 struct MoveScratch {
@@ -108,6 +110,8 @@ static_assert(sizeof(MoveScratch) % 16 == 0, "MoveScratch must stay 16-byte size
 //   moves:  MoveScratch per env        spawn: need-list / waste keys        render: view params + staging
 struct SmemLayout {
     uint32_t apple;                                  // CTA-shared table
+    uint32_t pt_mask, pt_pre;                        // CTA-shared cell -> apple-point tables (orchard bitmaps, specialised Harvest kernel)
+    uint32_t u_orch;                                 // orchard bitmaps of the warp's envs: the tail of the union, live in phases A and B
     uint32_t warp0, warp_stride;                     // first warp region, bytes per warp
     uint32_t w_mbar, w_tiles, w_env, w_union;        // offsets inside a warp region
     uint32_t u_stage;                                // staging buffer inside the union (after the view params)
@@ -123,6 +127,9 @@ struct StepArgs {
     int pad_bytes;        // zero bytes between / around the tiles in shared memory
     int n_apple, n_waste, area;
     int harvest_nz;       // bit n: SPAWN_PROB[n] != 0 (harvest.py:13)
+    int nW;               // Harvest: 32-bit words per orchard bitmap = ceil(n_apple / 32)
+    int orch_stride;      // 32-bit words of orchard bitmaps per env in HBM and in shared memory (2 * nW rounded up to 16 bytes)
+    int use_orch;         // the specialised kernel scans the bitmaps instead of the apple points (all the warp's words fit one pass)
     int debug;            // SSD_DEBUG_SKIP bits; only read by builds with -DSSD_PROFILING_KNOBS (profiles/skip_sweep.py)
     int obs_env;          // N*V*V*3 bytes
     // ---- launch description
@@ -148,6 +155,13 @@ struct StepArgs {
     uint8_t* grid;        // [B_pad][env_bytes]
     uint32_t* agents;     // [B_pad][N] row | col<<8 | ori<<16 | parked<<24 (parked: uploaded onto a '@' cell; never acts, never painted)
     uint8_t* beam_buf;    // [B_pad][64] raylen + firech between phase-split calls
+    // Harvest orchard bitmaps, [B_pad][orch_stride] words: bit p of word p/32 of `emp` (words 0..nW-1) = apple point p holds no
+    // apple; of `need` (words nW..2nW-1) = it holds none AND SPAWN_PROB[cached neighbour count] != 0, i.e. it is a candidate of
+    // spawn_apples (harvest.py:87-101).  Kept exact by every kernel that changes a grid.
+    // Cleanup: [B_pad][4] words, word 0 = number of 'H' cells of the env's grid (compute_permitted_area, cleanup.py:173-179).
+    uint32_t* orch;
+    const uint32_t* pt_mask;    // [ceil(env_bytes/32)] bit c%32 of word c/32: tile cell c is an apple point
+    const uint16_t* pt_pre;     // [ceil(env_bytes/32)] number of apple points in the words before
     // ---- I/O (device)
     const int8_t* actions; const uint8_t* order; const uint8_t* mask;
     const int32_t* rows; int n_rows;  // general kernel: step only these envs, one warp per listed row (ssd_reset_rows)
@@ -183,6 +197,8 @@ struct ResetArgs {
     const uint8_t* mask;
     const int32_t* rows; int n_rows;  // reset only these envs (ssd_reset_rows); NULL: all envs below env_end
     uint8_t* grid; uint32_t* agents;
+    uint32_t* orch; int orch_stride;  // Harvest orchard bitmaps: all zero after reset_map (every point holds an apple) ...
+    uint32_t orch_word0;              // ... Cleanup: word 0 = number of 'H' cells of the reset grid
 };
 
 // Launchers.  launch_step (ssd_step_fast.cu) decides which kernel steps what; launch_general (ssd_step_general.cu) is
@@ -193,6 +209,9 @@ cudaError_t launch_step(const StepArgs& a, int threads, cudaStream_t stream, Cha
 cudaError_t launch_reset(const ResetArgs& a, cudaStream_t stream);
 cudaError_t launch_pack_state(int kind, int B, int N, int H, int W, int Ws, int env_bytes, const uint8_t* grid_in, const int16_t* pos_in,
                               const uint8_t* ori_in, uint8_t* grid, uint32_t* agents, cudaStream_t stream);
+// Harvest: orchard bitmaps of every env recomputed from the grid (after ssd_set_state); one warp per env
+cudaError_t launch_build_orch(int kind, int B, int n_apple, int nW, int orch_stride, int harvest_nz, int env_bytes, const uint16_t* apple_cell,
+                              const uint8_t* grid, uint32_t* orch, cudaStream_t stream);
 // counts the agents whose (row, col) lies outside the map into *bad (device int, zeroed by the caller)
 cudaError_t launch_check_positions(int B, int N, int H, int W, const int16_t* pos_in, int* bad, cudaStream_t stream);
 cudaError_t launch_unpack_state(int B, int N, int H, int W, int Ws, int env_bytes, const uint8_t* grid, const uint32_t* agents,

@@ -52,6 +52,50 @@ __device__ __forceinline__ void recount_events(uint32_t events, int my_off, uint
     }
 }
 
+// ---- orchard bitmaps (StepArgs::orch): the specialised Harvest kernel keeps, per env, one bit per apple point for "holds no
+// apple" (emp) and "holds none and SPAWN_PROB[neighbour count] != 0" (need), so that spawn_apples only looks at candidates.
+struct OrchTables {
+    const uint32_t* pt_mask;  // shared memory: bit c % 32 of word c / 32 -- tile cell c is an apple point
+    const uint16_t* pt_pre;   //                apple points in the words before
+    int nW, stride, nz;       // words per bitmap, words per env, harvest_nz
+};
+// apple-point index of tile cell `cell`, or -1
+__device__ __forceinline__ int cell_point(const OrchTables& T, int cell) {
+    const uint32_t m = T.pt_mask[cell >> 5], b = cell & 31;
+    return (m >> b) & 1u ? static_cast<int>(T.pt_pre[cell >> 5]) + __popc(m & ((1u << b) - 1u)) : -1;
+}
+// recount() for a cell of env `bm` (its bitmaps), plus the `need` bit when the cell is an empty apple point
+__device__ __forceinline__ void recount_bm(uint8_t* q, int Ws, int cell, uint32_t* bm, const OrchTables& T) {
+    const uint8_t c = *q, code = c & kCodeMask;
+    if (code == CB(C_EMPTY) || code == CB(C_APPLE)) {
+        int n = is_apple(q[-Ws - 1]) + is_apple(q[-Ws]) + is_apple(q[-Ws + 1]) + is_apple(q[-1]) + is_apple(q[1]) +
+                is_apple(q[Ws - 1]) + is_apple(q[Ws]) + is_apple(q[Ws + 1]);
+        n = n < 3 ? n : 3;
+        *q = static_cast<uint8_t>((c & 0xFC) | n);
+        if (code == CB(C_EMPTY)) {
+            const int p = cell_point(T, cell);
+            if (p >= 0) {
+                const uint32_t bit = 1u << (p & 31);
+                if ((T.nz >> n) & 1) atomicOr(&bm[T.nW + (p >> 5)], bit); else atomicAnd(&bm[T.nW + (p >> 5)], ~bit);
+            }
+        }
+    }
+}
+// recount_events() with bitmaps: my_slot / my_cell = env slot and in-tile cell of this lane's event
+__device__ __forceinline__ void recount_events_bm(uint32_t events, int my_slot, int my_cell, uint8_t* tiles0 /* cell 0 of slot 0 */, int tile_pitch,
+                                                  int Ws, uint32_t* orch, const OrchTables& T) {
+    const int lane = threadIdx.x & 31;
+    const int t = lane & 7;
+    const int nb = (t < 3 ? -Ws - 1 + t : (t == 3 ? -1 : (t == 4 ? 1 : Ws - 6 + t)));  // -Ws-1,-Ws,-Ws+1,-1,+1,Ws-1,Ws,Ws+1
+    while (events) {
+        const int src = __ffs(events) - 1;
+        events &= events - 1;
+        const int slot = __shfl_sync(0xffffffffu, my_slot, src), cell = __shfl_sync(0xffffffffu, my_cell, src);
+        if (lane < 8) recount_bm(tiles0 + slot * tile_pitch + cell + nb, Ws, cell + nb, orch + slot * T.stride, T);
+        __syncwarp();
+    }
+}
+
 struct Counters {  // per-lane event counts, reduced per warp at the end of the kernel
     int steps, eaten, fires, hits, cleaned, apples, waste;
 };
@@ -236,9 +280,11 @@ __device__ __forceinline__ void moves_group(const StepArgs& a, ES& S, MoveScratc
 // its group.  The map is wall-enclosed (checked by ssd_create), so the reference's bounds test
 // (:615) can never fire before the wall test (:616).  Agent cells carry kFlag, so the position
 // table is only searched when a ray actually runs into somebody.  Returns the painted cell count.
-template <class ES, bool ATOMIC = false>
-__device__ __forceinline__ int ray_walk(const StepArgs& a, ES& S, uint8_t* g, uint32_t key, int ori, int s,
-                                        bool clean, int& upd, int& hits) {
+// ray_probe has no side effects: it returns the number of painted cells, the cell a CLEAN beam turns into river (`upd`, -1: none)
+// and the agent an 'F' beam hits (`hit`, -1: none; a ray stops at the first agent, so there is at most one).
+template <class ES>
+__device__ __forceinline__ int ray_probe(const StepArgs& a, const ES& S, const uint8_t* g, uint32_t key, int ori, int s,
+                                         bool clean, int& upd, int& hit) {
     const int d0 = (ori == 1) - (ori == 3), d1 = (ori == 2) - (ori == 0);  // ORIENTATIONS map_env.py:19-22
     int r = static_cast<int>(key >> 8) + d0, c = static_cast<int>(key & 255) + d1;  // :608-613
     if (s == 1) { r += -d1 - d0; c += d0 - d1; }  // start + rotate_right(d) - d   (:607-609)
@@ -251,11 +297,7 @@ __device__ __forceinline__ int ray_walk(const StepArgs& a, ES& S, uint8_t* g, ui
         if (cell == CB(C_WALL)) break;                          // :616
         const bool isH = clean && cell == CB(C_WASTE);
         if (raw & kFlag) {                                      // :621-629 agents absorb beams
-            if (!clean) {  // agent.py:166-168, 212-214
-                const int v = by_pos(S.pos, a.N, static_cast<uint32_t>(r << 8 | c));
-                if constexpr (ATOMIC) atomicAdd(&S.rew[v], -50); else S.rew[v] -= 50;
-                ++hits;
-            }
+            if (!clean) hit = by_pos(S.pos, a.N, static_cast<uint32_t>(r << 8 | c));  // agent.py:166-168, 212-214
             ++n;                                                // :624
             if (isH) upd = p;                                   // :625-628
             break;
@@ -264,6 +306,17 @@ __device__ __forceinline__ int ray_walk(const StepArgs& a, ES& S, uint8_t* g, ui
         ++n;                                                    // :636
         if (isH) break;                                         // blocking_cells :639
         r += d0; c += d1; p += dp;
+    }
+    return n;
+}
+template <class ES, bool ATOMIC = false>
+__device__ __forceinline__ int ray_walk(const StepArgs& a, ES& S, uint8_t* g, uint32_t key, int ori, int s,
+                                        bool clean, int& upd, int& hits) {
+    int hit = -1;
+    const int n = ray_probe(a, S, g, key, ori, s, clean, upd, hit);
+    if (hit >= 0) {
+        if constexpr (ATOMIC) atomicAdd(&S.rew[hit], -50); else S.rew[hit] -= 50;
+        ++hits;
     }
     return n;
 }
@@ -394,11 +447,92 @@ __device__ __forceinline__ void harvest_spawn_warp(const StepArgs& a, uint8_t* t
     harvest_drain<TAPE>(a, tiles, tile_pitch, list, n_list, we, pk, lane, cnt);
 }
 
-template <bool TAPE>
-__device__ __forceinline__ void cleanup_spawn(const StepArgs& a, uint8_t* g, const uint16_t* s_apple, uint32_t* keys,
-                                              int local_env, const PhiloxKey& pk, int lane, Counters& cnt) {
-    const int n_apple = a.n_apple, n_waste = a.n_waste;
-    // compute_permitted_area / compute_probabilities, cleanup.py:156-179: count 'H' over the whole grid
+// spawn_apples (harvest.py:75-104) for all envs of a warp from the orchard bitmaps.  Lane L < EPW * nW owns word g = L % nW
+// of env slot q = L / nW: e = points that hold no apple and no agent (the agents' bits are masked out by the caller) -- the
+// eligible points, whose count before a point is the index of its np.random.rand draw -- and c = the candidates among them
+// (SPAWN_PROB != 0).  Only candidates are looked at: one list entry each (point | n << 12 | slot << 14 | draw index << 16),
+// then the same drain as above with the bitmaps kept current.  All reads of an env happen before its first write.
+template <bool TAPE, int EPW>
+__device__ __forceinline__ void harvest_spawn_bm(const StepArgs& a, uint8_t* tiles, int tile_pitch, const uint16_t* __restrict__ s_apple,
+                                                 uint32_t* orch, const OrchTables& T, uint32_t* __restrict__ list, int cap, int we,
+                                                 PhiloxKey pk, int lane, Counters& cnt) {
+    constexpr uint8_t A = CB(C_APPLE);
+    const int nW = T.nW;
+    const uint32_t lt = lanemask_lt();
+    const int q = lane / nW, g = lane - q * nW;
+    const bool mine = q < EPW;
+    uint8_t* const tiles0 = tiles + a.pad_bytes;
+    uint32_t e = 0, c = 0;
+    if (mine) { const uint32_t* bm = orch + q * T.stride; e = bm[g]; c = bm[nW + g] & e; }
+    const int cnt_e = __popc(e);
+    int base = cnt_e;  // draws before this word's points: exclusive scan over the nW lanes of the env
+    for (int d = 1; d < nW; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, base, d);
+        if (g >= d) base += v;
+    }
+    if (TAPE && a.n_draws_out != nullptr && mine && g == nW - 1) a.n_draws_out[we + q] = base;
+    base -= cnt_e;
+    // all candidates of the warp in one list when they fit; env by env otherwise (one env's candidates always fit)
+    const int total = __reduce_add_sync(0xffffffffu, __popc(c));
+    const int n_batch = total <= cap ? 1 : EPW;
+#pragma unroll 1
+    for (int b = 0; b < n_batch; ++b) {
+        uint32_t cc = (n_batch == 1 || q == b) ? c : 0u;
+        int n_list = 0;
+#pragma unroll 1
+        while (true) {
+            const uint32_t m = __ballot_sync(0xffffffffu, cc != 0);
+            if (m == 0) break;
+            if (cc != 0) {
+                const int bit = __ffs(cc) - 1;
+                cc &= cc - 1;
+                const int p = 32 * g + bit;
+                const uint32_t n = tiles0[q * tile_pitch + s_apple[p]] & 3u;  // cached count of apples in the 3x3 window (harvest.py:92-100)
+                const uint32_t k = static_cast<uint32_t>(base + __popc(e & ((1u << bit) - 1u)));
+                list[n_list + __popc(m & lt)] = static_cast<uint32_t>(p) | n << 12 | static_cast<uint32_t>(q) << 14 | k << 16;
+            }
+            n_list += __popc(m);
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int j0 = 0; j0 < n_list; j0 += 32) {
+            const int j = j0 + lane;
+            bool spawn = false;
+            int slot = 0, cell = 0;
+            if (j < n_list) {
+                const uint32_t en = list[j];
+                const int p = en & 0xfffu, n = (en >> 12) & 3;
+                const uint32_t k = en >> 16;
+                slot = (en >> 14) & 3;
+                cell = s_apple[p];
+                if (TAPE) {
+                    spawn = a.tape_u[static_cast<size_t>(we + slot) * a.u_stride + k] < a.harvest_p[n];
+                } else {
+                    pk.env = static_cast<uint32_t>(a.env_id0 + static_cast<uint64_t>(we + slot));
+                    spawn = philox_u53(pk, a.spawn_stream, k) < a.harvest_thr[n];  // u < p  <=>  u53 < ceil(p * 2^53)
+                }
+                if (spawn) {
+                    uint8_t* t = tiles0 + slot * tile_pitch + cell;
+                    *t = static_cast<uint8_t>(A | (*t & 3));  // keep the CURRENT cached count: an earlier batch may have refreshed it
+                    uint32_t* bm = orch + slot * T.stride;
+                    const uint32_t bit = 1u << (p & 31);
+                    atomicAnd(&bm[p >> 5], ~bit);
+                    atomicAnd(&bm[nW + (p >> 5)], ~bit);
+                    ++cnt.apples;
+                }
+            }
+            const uint32_t ms = __ballot_sync(0xffffffffu, spawn);
+            if (ms) {  // refresh the cached counts (and `need` bits) around the new apples
+                __syncwarp();
+                recount_events_bm(ms, slot, cell, tiles0, tile_pitch, a.Ws, orch, T);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// Number of 'H' cells of one env tile (all lanes get the sum).
+__device__ __forceinline__ int count_waste(const StepArgs& a, const uint8_t* g, int lane) {
     int nh = 0;
     for (int i = lane * 16; i < a.env_bytes; i += 512) {
         const uint4 v = *reinterpret_cast<const uint4*>(g + i);
@@ -410,7 +544,17 @@ __device__ __forceinline__ void cleanup_spawn(const StepArgs& a, uint8_t* g, con
             nh += 4 - __popc(nz);
         }
     }
-    int h = __reduce_add_sync(0xffffffffu, nh);
+    return __reduce_add_sync(0xffffffffu, nh);
+}
+
+// hcount: the env's running number of 'H' cells (specialised kernel: kept in HBM next to the grid, StepArgs::orch word 0, and
+// adjusted by every clean / waste spawn), or nullptr to count them here.
+template <bool TAPE>
+__device__ __forceinline__ void cleanup_spawn(const StepArgs& a, uint8_t* g, const uint16_t* s_apple, uint32_t* keys,
+                                              int local_env, const PhiloxKey& pk, int lane, Counters& cnt, int* hcount = nullptr) {
+    const int n_apple = a.n_apple, n_waste = a.n_waste;
+    // compute_permitted_area / compute_probabilities, cleanup.py:156-179: the number of 'H' cells of the whole grid
+    int h = hcount != nullptr ? *hcount : count_waste(a, g, lane);
     h = h < a.area ? h : a.area;
     const double apple_p = a.apple_p[h], waste_p = a.waste_p[h];
     const uint64_t apple_thr = a.apple_thr[h], waste_thr = a.waste_thr[h];
@@ -486,7 +630,7 @@ __device__ __forceinline__ void cleanup_spawn(const StepArgs& a, uint8_t* g, con
                 if (el) ok = a.tape_u[static_cast<size_t>(local_env) * a.u_stride + base + __popc(m & lanemask_lt())] < waste_p;
                 const uint32_t s = __ballot_sync(0xffffffffu, ok);
                 if (s) {  // first success spawns and breaks (:151-153); waste may appear under an agent
-                    if (lane == __ffs(s) - 1) { g[idx] = CB(C_WASTE) | (g[idx] & kFlag); ++cnt.waste; }
+                    if (lane == __ffs(s) - 1) { g[idx] = CB(C_WASTE) | (g[idx] & kFlag); ++cnt.waste; if (hcount != nullptr) ++*hcount; }
                     base += __popc(m & ((2u << (__ffs(s) - 1)) - 1u));  // draws up to and including the winner
                     break;
                 }
@@ -548,6 +692,7 @@ __device__ __forceinline__ void cleanup_spawn(const StepArgs& a, uint8_t* g, con
                     const int idx = a.waste_cell[static_cast<uint32_t>(prev)];
                     g[idx] = CB(C_WASTE) | (g[idx] & kFlag);
                     ++cnt.waste;
+                    if (hcount != nullptr) ++*hcount;
                 }
             }
         }

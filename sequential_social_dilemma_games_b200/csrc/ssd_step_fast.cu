@@ -105,8 +105,9 @@ __device__ __forceinline__ void render_rows_tma(const uint2* s_view, const uint8
     bulk_wait_read();  // shared memory must outlive the last bulk read
 }
 
-template <int KIND, bool TAPE, int VT, int G>
+template <int KIND, bool TAPE, int VT, int G, bool ORCH>
 __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid_constant__ StepArgs a) {
+    static_assert(!ORCH || KIND == SSD_KIND_HARVEST, "orchard bitmaps are a Harvest structure");
     constexpr int EPW = 32 / G;                                       // envs per warp: 4 (N <= 8) or 2 (N <= 16)
     constexpr uint32_t kSlotLsb = G == 8 ? 0x01010101u : 0x00010001u;  // bit 0 of every env's lane group
     using FastScratch = FastScratchT<G>;
@@ -125,12 +126,22 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
     if (KIND != SSD_KIND_PLAIN)
 #pragma unroll 1
         for (int i = tid; i < ((a.n_apple + 63) & ~63); i += nthr) s_apple[i] = i < a.n_apple ? a.apple_cell[i] : static_cast<uint16_t>(a.Ws + 1);
+    OrchTables T;
+    T.pt_mask = reinterpret_cast<const uint32_t*>(smem + a.Lf.pt_mask); T.pt_pre = reinterpret_cast<const uint16_t*>(smem + a.Lf.pt_pre);
+    T.nW = a.nW; T.stride = a.orch_stride; T.nz = a.harvest_nz;
+    if (ORCH)
+#pragma unroll 1
+        for (int i = tid; i < (a.env_bytes + 31) / 32; i += nthr) {
+            reinterpret_cast<uint32_t*>(smem + a.Lf.pt_mask)[i] = a.pt_mask[i];
+            reinterpret_cast<uint16_t*>(smem + a.Lf.pt_pre)[i] = a.pt_pre[i];
+        }
     __syncthreads();
 
     uint8_t* wbase = smem + a.Lf.warp0 + warp * a.Lf.warp_stride;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(wbase + a.Lf.w_mbar);
     uint8_t* tiles = wbase + a.Lf.w_tiles;
     FastScratch* envs = reinterpret_cast<FastScratch*>(wbase + a.Lf.w_env);
+    uint32_t* const orch_s = reinterpret_cast<uint32_t*>(wbase + a.Lf.w_union + a.Lf.u_orch);  // [EPW][orch_stride], phases A and B
     const int tile_pitch = a.env_bytes + a.pad_bytes;
     const int we = a.env_begin + (blockIdx.x * nwarps + warp) * EPW;  // the launcher only sends whole warps
     Counters cnt = {0, 0, 0, 0, 0, 0, 0};
@@ -144,7 +155,7 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
         // ---- load: one TMA bulk copy per env tile; zero the frames while they are in flight
         if (lane == 0) {
             mbar_init(mbar, 1);
-            mbar_expect_tx(mbar, static_cast<uint32_t>(EPW) * a.env_bytes);
+            mbar_expect_tx(mbar, static_cast<uint32_t>(EPW) * (a.env_bytes + (ORCH ? 4u * a.orch_stride : 0u)));
             if (a.dep_wait) {  // chained step: the previous step's kernel may still be running; wait for OUR four envs only
                 while (ld_acquire_u32(a.done + we / EPW) != a.epoch - 1) __nanosleep(64);
             }
@@ -155,6 +166,7 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
 #pragma unroll
             for (int q = 0; q < EPW; ++q)
                 bulk_g2s(tiles + a.pad_bytes + q * tile_pitch, a.grid + static_cast<size_t>(we + q) * a.env_bytes, a.env_bytes, mbar);
+            if (ORCH) bulk_g2s(orch_s, a.orch + static_cast<size_t>(we) * a.orch_stride, static_cast<uint32_t>(EPW) * 4u * a.orch_stride, mbar);
         }
         {
             const uint4 z = make_uint4(0, 0, 0, 0);
@@ -191,14 +203,28 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
         cnt.steps += (al == 0);
         if (valid) S.pos[al] = static_cast<uint16_t>(me.key);
         const int my_idx = tile_idx(a, me.key);
+        uint32_t* const my_bm = orch_s + j * a.orch_stride;          // ORCH: the bitmaps of this lane's env ...
+        const int my_pt = (ORCH && valid) ? cell_point(T, my_idx) : -1;  // ... and the apple point this agent stands on, if any
         {   // consume, map_env.py:178-181: of agents sharing a cell (appendix A.2 quirk) the first in agent order eats
             const uint8_t under = g[my_idx];
             const bool on_apple = valid && is_apple(under);
             const uint32_t same = __match_any_sync(0xffffffffu, on_apple ? (me.key | static_cast<uint32_t>(gbase) << 16) : (0x80000000u | lane));
             const bool ate = on_apple && (__ffs(same) - 1) == lane;
-            if (ate) { g[my_idx] = CB(C_EMPTY) | (under & 3); me.rew += 1; ++cnt.eaten; }
+            if (ate) {
+                g[my_idx] = CB(C_EMPTY) | (under & 3); me.rew += 1; ++cnt.eaten;
+                if (ORCH) {  // the point holds no apple now; it is a spawn candidate if its cached count says so
+                    atomicOr(&my_bm[my_pt >> 5], 1u << (my_pt & 31));
+                    if ((a.harvest_nz >> (under & 3)) & 1) atomicOr(&my_bm[a.nW + (my_pt >> 5)], 1u << (my_pt & 31));
+                }
+            }
             __syncwarp();
-            if (KIND == SSD_KIND_HARVEST) recount_events(__ballot_sync(0xffffffffu, ate), static_cast<int>(g - tiles) + my_idx, tiles, a.Ws);
+            if (KIND == SSD_KIND_HARVEST) {
+                if (ORCH) recount_events_bm(__ballot_sync(0xffffffffu, ate), j, my_idx, tiles + a.pad_bytes, tile_pitch, a.Ws, orch_s, T);
+                else recount_events(__ballot_sync(0xffffffffu, ate), static_cast<int>(g - tiles) + my_idx, tiles, a.Ws);
+            }
+            // "[row, col] not in self.agent_pos" (harvest.py:90): a point under an agent is not eligible.  After consume it never
+            // holds an apple, so its `emp` bit is set: clear it for the spawn pass, set it again afterwards.
+            if (ORCH && my_pt >= 0) atomicAnd(&my_bm[my_pt >> 5], ~(1u << (my_pt & 31)));
         }
         __syncwarp();
         if (KIND != SSD_KIND_PLAIN && valid) g[my_idx] |= kFlag;  // "an agent stands here"
@@ -261,7 +287,12 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
         if (KIND != SSD_KIND_PLAIN && !SSD_SKIP(a.debug, 4)) {
             void* scratch = wbase + a.Lf.w_union;
             if (KIND == SSD_KIND_HARVEST) {
-                harvest_spawn_warp<TAPE, EPW>(a, tiles, tile_pitch, s_apple, static_cast<uint32_t*>(scratch), a.Lf.u_words, we, pk, lane, cnt);
+                if (ORCH) {
+                    harvest_spawn_bm<TAPE, EPW>(a, tiles, tile_pitch, s_apple, orch_s, T, static_cast<uint32_t*>(scratch), a.Lf.u_words, we, pk, lane, cnt);
+                    if (my_pt >= 0) atomicOr(&my_bm[my_pt >> 5], 1u << (my_pt & 31));  // the points under agents are empty points again
+                } else {
+                    harvest_spawn_warp<TAPE, EPW>(a, tiles, tile_pitch, s_apple, static_cast<uint32_t*>(scratch), a.Lf.u_words, we, pk, lane, cnt);
+                }
             } else {
 #pragma unroll 1
                 for (int q = 0; q < EPW; ++q) {
@@ -283,6 +314,7 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
 #pragma unroll
                 for (int q = 0; q < EPW; ++q)
                     bulk_s2g(a.grid + static_cast<size_t>(we + q) * a.env_bytes, tiles + a.pad_bytes + q * tile_pitch, a.env_bytes);
+                if (ORCH) bulk_s2g(a.orch + static_cast<size_t>(we) * a.orch_stride, orch_s, static_cast<uint32_t>(EPW) * 4u * a.orch_stride);
                 bulk_commit();
             }
             bulk_wait_read();
@@ -391,14 +423,14 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
 }
 
 // ====================================================================== launchers
-template <int KIND, bool TAPE, int G>
+template <int KIND, bool TAPE, int G, bool ORCH = false>
 static cudaError_t launch_fast(const StepArgs& a, int threads, cudaStream_t stream) {
     const int envs_per_cta = (threads / 32) * (32 / G);
     const int ctas = (a.env_end - a.env_begin + envs_per_cta - 1) / envs_per_cta;
     if (ctas <= 0) return cudaSuccess;
 #define SSD_LAUNCH_FAST(VT_)                                                                                    \
     do {                                                                                                        \
-        auto kern = ssd_step_fast_kernel<KIND, TAPE, VT_, G>;                                                      \
+        auto kern = ssd_step_fast_kernel<KIND, TAPE, VT_, G, ORCH>;                                                      \
         static uint32_t smem_set[kMaxDevices] = {};  /* the attribute is per device */                          \
         int dev_ = 0;                                                                                           \
         cudaGetDevice(&dev_);                                                                                   \
@@ -472,7 +504,14 @@ cudaError_t launch_step(const StepArgs& a, int threads, cudaStream_t stream, Cha
     e = a.G == 8 ? (tape ? launch_fast<KIND_, true, 8>(f, threads, stream) : launch_fast<KIND_, false, 8>(f, threads, stream)) \
                  : (tape ? launch_fast<KIND_, true, 16>(f, threads, stream) : launch_fast<KIND_, false, 16>(f, threads, stream))
     switch (a.kind) {
-        case SSD_KIND_HARVEST: SSD_FAST(SSD_KIND_HARVEST); break;
+        case SSD_KIND_HARVEST:
+            if (a.use_orch) {
+                e = a.G == 8 ? (tape ? launch_fast<SSD_KIND_HARVEST, true, 8, true>(f, threads, stream) : launch_fast<SSD_KIND_HARVEST, false, 8, true>(f, threads, stream))
+                             : (tape ? launch_fast<SSD_KIND_HARVEST, true, 16, true>(f, threads, stream) : launch_fast<SSD_KIND_HARVEST, false, 16, true>(f, threads, stream));
+            } else {
+                SSD_FAST(SSD_KIND_HARVEST);
+            }
+            break;
         case SSD_KIND_CLEANUP: SSD_FAST(SSD_KIND_CLEANUP); break;
         default: SSD_FAST(SSD_KIND_PLAIN); break;
     }

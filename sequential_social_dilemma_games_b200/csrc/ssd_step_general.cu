@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_kernel(const __grid_cons
     for (int i = tid; i < kLutEntries; i += nthr) s_color[i] = a.color[i];
     if (tid < SSD_NUM_STATS) s_cta_stats[tid] = 0;
     if (tid == 0) s_done = 0;
-    if (phases & SSD_PHASE_SPAWN)
+    if (phases & (SSD_PHASE_SPAWN | SSD_PHASE_CONSUME))
         for (int i = tid; i < ((a.n_apple + 63) & ~63); i += nthr) s_apple[i] = i < a.n_apple ? a.apple_cell[i] : static_cast<uint16_t>(a.Ws + 1);
     __syncthreads();
 
@@ -167,6 +167,30 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_kernel(const __grid_cons
                 else
                     cleanup_spawn<TAPE>(a, tiles + a.pad_bytes + q * tile_pitch, s_apple, static_cast<uint32_t*>(scratch), we + q, pk, lane, cnt);
                 __syncwarp();
+            }
+        }
+
+        // ---- Harvest: the orchard bitmaps of the specialised kernel (StepArgs::orch), rebuilt from the tiles this call changed
+        if (KIND == SSD_KIND_HARVEST && a.nW > 0 && (phases & (SSD_PHASE_CONSUME | SSD_PHASE_SPAWN))) {
+            for (int q = 0; q < EPW; ++q) {
+                if (!envs[q].active) continue;
+                const uint8_t* tq = tiles + a.pad_bytes + q * tile_pitch;
+                uint32_t* bm = a.orch + static_cast<size_t>(we + q) * a.orch_stride;
+                for (int w = 0; w < a.nW; ++w) {
+                    const int i = 32 * w + lane;
+                    const uint8_t c = i < a.n_apple ? tq[s_apple[i]] : 0;
+                    const bool emp = i < a.n_apple && (c & kCodeMask) == CB(C_EMPTY);
+                    const uint32_t m_e = __ballot_sync(0xffffffffu, emp), m_n = __ballot_sync(0xffffffffu, emp && ((a.harvest_nz >> (c & 3)) & 1));
+                    if (lane == 0) { bm[w] = m_e; bm[a.nW + w] = m_n; }
+                }
+            }
+        }
+
+        if (KIND == SSD_KIND_CLEANUP && (phases & (SSD_PHASE_BEAMS | SSD_PHASE_SPAWN))) {  // the running 'H' count of the specialised kernel
+            for (int q = 0; q < EPW; ++q) {
+                if (!envs[q].active) continue;
+                const int nh = count_waste(a, tiles + a.pad_bytes + q * tile_pitch, lane);
+                if (lane == 0) a.orch[static_cast<size_t>(we + q) * a.orch_stride] = static_cast<uint32_t>(nh);
             }
         }
 

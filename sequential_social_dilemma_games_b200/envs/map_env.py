@@ -54,7 +54,7 @@ class MapEnv(MultiAgentEnv):
                  device="cuda:0"):
         self.num_agents = num_agents
         self.base_map = self.ascii_to_numpy(ascii_map)
-        self._ascii_map = [str(r) for r in ascii_map]
+        self._ascii_map = [''.join(str(ch) for ch in row) for row in ascii_map]  # list of strings or a 2-D character array (tests/test_envs.py:36-44)
         self.return_agent_actions = return_agent_actions
         if self.return_agent_actions:
             self.prev_actions = defaultdict(lambda: [0] * self.num_agents)
