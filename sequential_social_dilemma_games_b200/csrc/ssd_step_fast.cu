@@ -231,40 +231,83 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
         __syncwarp();
         uint32_t fmask = 0;  // bit (8 * env slot + agent): that agent fires
         uint32_t* const fire_list = reinterpret_cast<uint32_t*>(wbase + a.Lf.w_union);
-        const int ray_f = lane / 3, ray_s = lane - 3 * ray_f;  // Harvest: ray lane -> (firing agent of the round, ray)
+        const int ray_f = lane / 3, ray_s = lane - 3 * ray_f;  // ray lane -> (firing agent of the round, ray)
         uint32_t fire_ent = 0;
-        if (KIND == SSD_KIND_HARVEST && !SSD_SKIP(a.debug, 8)) {
-            // update_custom_moves map_env.py:545-552.  Harvest has only 'F' beams: they change no cell, so the
-            // firing order is irrelevant and the rays of ALL firing agents of the warp walk at once, 3 lanes each.
-            const bool fire_me = me.act == 7;
+        // Cleanup with an explicit action-dict order takes the literal loop further down; everything else walks the rays of ALL
+        // firing agents of the warp at once, three lanes per agent, ten agents per round.
+        const bool literal_beams = KIND == SSD_KIND_CLEANUP && a.order != nullptr;
+        if (KIND == SSD_KIND_CLEANUP && al == 0) S.hcount = static_cast<int32_t>(__ldcg(a.orch + static_cast<size_t>(e) * a.orch_stride));
+        if (KIND != SSD_KIND_PLAIN && !literal_beams && !SSD_SKIP(a.debug, 8)) {
+            // update_custom_moves map_env.py:545-552.  'F' beams change no cell, so their order is irrelevant (Harvest has no
+            // others).  A CLEAN beam turns the 'H' cell that stops it into 'R' BEFORE the next agent fires (:551-558), so a later
+            // beam depends on an earlier one exactly when both stop at the same 'H' cell: the rays of a round are probed without
+            // side effects, and only if two of them would clean the same cell is that round replayed agent by agent.  Rounds
+            // follow the firing order (env slot, agent), and a round is committed before the next one is probed.
+            const bool clean_me = KIND == SSD_KIND_CLEANUP && me.act == 8;
+            const bool fire_me = me.act == 7 || clean_me;
             fmask = __ballot_sync(0xffffffffu, fire_me);
             if (fmask) {
-                fire_ent = me.key | static_cast<uint32_t>(me.ori) << 16 | static_cast<uint32_t>(j) << 18 | static_cast<uint32_t>(al) << 21;
-                if (fire_me) { fire_list[__popc(fmask & lanemask_lt())] = fire_ent; me.rew -= 1; ++cnt.fires; }  // fire_beam agent.py:170-172
-                __syncwarp();
-                const int nf = __popc(fmask);
-#pragma unroll 1
-                for (int f0 = 0; f0 < nf; f0 += 10) {
-                    if (lane < 30 && f0 + ray_f < nf) {
-                        const uint32_t en = fire_list[f0 + ray_f];
-                        const int slot = (en >> 18) & 3, ag = en >> 21;
-                        int upd = -1, hits = 0;
-                        const int n = ray_walk<FastScratch, true>(a, envs[slot], tiles + a.pad_bytes + slot * tile_pitch, en & 0xffffu,
-                                                                  (en >> 16) & 3, ray_s, false, upd, hits);
-                        envs[slot].raylen[ag * 3 + ray_s] = static_cast<uint8_t>(n);
-                        cnt.hits += hits;
-                    }
+                fire_ent = me.key | static_cast<uint32_t>(me.ori) << 16 | static_cast<uint32_t>(j) << 18 | static_cast<uint32_t>(al) << 21 |
+                           static_cast<uint32_t>(clean_me) << 25;
+                if (fire_me) {
+                    fire_list[__popc(fmask & lanemask_lt())] = fire_ent;
+                    if (!clean_me) { me.rew -= 1; ++cnt.fires; }  // fire_beam agent.py:170-172 (a CLEAN beam is free, :205-207)
                 }
                 __syncwarp();
+                const int nf = __popc(fmask);
+                auto commit = [&](uint32_t en, int ray, int n, int upd, int hit) {
+                    const int slot = (en >> 18) & 3, ag = (en >> 21) & 15;
+                    envs[slot].raylen[ag * 3 + ray] = static_cast<uint8_t>(n);
+                    if (hit >= 0) { atomicAdd(&envs[slot].rew[hit], -50); ++cnt.hits; }  // agent.hit('F') agent.py:166-168
+                    if (KIND == SSD_KIND_CLEANUP && upd >= 0) {                          // update_map :551-558
+                        uint8_t* t = tiles + a.pad_bytes + slot * tile_pitch + upd;
+                        *t = CB(C_RIVER) | (*t & kFlag);
+                        atomicSub(&envs[slot].hcount, 1);
+                        ++cnt.cleaned;
+                    }
+                };
+#pragma unroll 1
+                for (int f0 = 0; f0 < nf; f0 += 10) {
+                    const bool act_lane = lane < 30 && f0 + ray_f < nf;
+                    uint32_t en = 0;
+                    int n = 0, upd = -1, hit = -1;
+                    if (act_lane) {
+                        en = fire_list[f0 + ray_f];
+                        const int slot = (en >> 18) & 3;
+                        n = ray_probe(a, envs[slot], tiles + a.pad_bytes + slot * tile_pitch, en & 0xffffu, (en >> 16) & 3, ray_s, (en >> 25) & 1, upd, hit);
+                    }
+                    bool replay = false;
+                    if (KIND == SSD_KIND_CLEANUP) {
+                        const uint32_t same = __match_any_sync(0xffffffffu, upd >= 0 ? (static_cast<uint32_t>(upd) | ((en >> 18) & 3) << 16) : (0x80000000u | lane));
+                        replay = __any_sync(0xffffffffu, upd >= 0 && (same & (same - 1)) != 0);
+                    }
+                    if (!replay) {
+                        if (act_lane) commit(en, ray_s, n, upd, hit);
+                    } else {
+                        const int f1 = min(f0 + 10, nf);
+#pragma unroll 1
+                        for (int f = f0; f < f1; ++f) {  // one agent at a time: its three rays see what the agents before it cleaned
+                            n = 0; upd = -1; hit = -1;
+                            if (lane < 3) {
+                                en = fire_list[f];
+                                const int slot = (en >> 18) & 3;
+                                n = ray_probe(a, envs[slot], tiles + a.pad_bytes + slot * tile_pitch, en & 0xffffu, (en >> 16) & 3, lane, (en >> 25) & 1, upd, hit);
+                            }
+                            __syncwarp();  // all three rays are walked before the agent's updates are applied (:551-552)
+                            if (lane < 3) commit(en, lane, n, upd, hit);
+                            __syncwarp();
+                        }
+                    }
+                    __syncwarp();
+                }
             }
         }
-        if (KIND == SSD_KIND_CLEANUP && !SSD_SKIP(a.debug, 8)) {  // firing order matters: a CLEAN beam turns 'H' into 'R' for the next one
+        if (literal_beams && !SSD_SKIP(a.debug, 8)) {  // explicit action order: the k-th entry of the action dict is agent S.order[k]
             fmask = __ballot_sync(0xffffffffu, me.act == 7 || me.act == 8);
-            const bool in_order = a.order != nullptr;  // the k-th entry of the action dict is agent S.order[k]
             for (int k = 0; k < N; ++k) {
-                const int ag = in_order ? S.order[k] : k;
+                const int ag = S.order[k];
                 const bool fire = (fmask >> (gbase + ag)) & 1u;
-                if (in_order ? !__any_sync(0xffffffffu, fire) : !((fmask >> k) & kSlotLsb)) continue;  // nobody in this warp fires in slot k
+                if (!__any_sync(0xffffffffu, fire)) continue;  // nobody in this warp fires in slot k
                 const int act_k = __shfl_sync(0xffffffffu, me.act, ag, G);
                 const uint32_t key_k = __shfl_sync(0xffffffffu, me.key, ag, G);
                 const int ori_k = __shfl_sync(0xffffffffu, me.ori, ag, G);
@@ -275,7 +318,7 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
                 __syncwarp();
                 if (fire && al < 3) {
                     S.raylen[k * 3 + al] = static_cast<uint8_t>(n);
-                    if (upd >= 0) { g[upd] = CB(C_RIVER) | (g[upd] & kFlag); ++cnt.cleaned; }  // update_map :551-558, before the next agent fires
+                    if (upd >= 0) { g[upd] = CB(C_RIVER) | (g[upd] & kFlag); atomicSub(&S.hcount, 1); ++cnt.cleaned; }  // update_map :551-558, before the next agent fires
                     cnt.hits += hits;
                 }
                 __syncwarp();
@@ -297,7 +340,7 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
 #pragma unroll 1
                 for (int q = 0; q < EPW; ++q) {
                     pk.env = static_cast<uint32_t>(a.env_id0 + static_cast<uint64_t>(we + q));
-                    cleanup_spawn<TAPE>(a, tiles + a.pad_bytes + q * tile_pitch, s_apple, static_cast<uint32_t*>(scratch), we + q, pk, lane, cnt);
+                    cleanup_spawn<TAPE>(a, tiles + a.pad_bytes + q * tile_pitch, s_apple, static_cast<uint32_t*>(scratch), we + q, pk, lane, cnt, &envs[q].hcount);
                     __syncwarp();
                 }
             }
@@ -326,33 +369,54 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
             const uint32_t same = __match_any_sync(0xffffffffu, valid ? (me.key | static_cast<uint32_t>(gbase) << 16) : (0x80000000u | lane));
             if (valid && (31 - __clz(same)) == lane && me.act != -2) g[my_idx] = agent_cell(al);  // the last agent on a cell wins
             __syncwarp();
-            if (KIND == SSD_KIND_HARVEST && fmask) {  // all beams are 'F': the painting order is irrelevant
+            if (KIND != SSD_KIND_PLAIN && !literal_beams && fmask) {
+                // Beams are painted in firing order and a later one overwrites an earlier one (map_env.py:298-301).  All rays paint
+                // at once; that is the same picture unless an 'F' and a 'C' beam cross, which the lanes find out by reading their
+                // cells back -- then everything is painted again, agent by agent.
                 if ((fmask >> lane) & 1u) fire_list[__popc(fmask & lanemask_lt())] = fire_ent;  // the union was reused by the spawn pass
                 __syncwarp();
                 const int nf = __popc(fmask);
+                auto paint = [&](uint32_t en, int ray, bool check) -> bool {
+                    const int slot = (en >> 18) & 3, ag = (en >> 21) & 15, ori = (en >> 16) & 3;
+                    const int d0 = (ori == 1) - (ori == 3), d1 = (ori == 2) - (ori == 0);
+                    int r = static_cast<int>((en >> 8) & 255) + d0, c = static_cast<int>(en & 255) + d1;
+                    if (ray == 1) { r += -d1 - d0; c += d0 - d1; }
+                    if (ray == 2) { r -= -d1 + d0; c -= d0 + d1; }
+                    const int n = envs[slot].raylen[ag * 3 + ray], dp = d0 * a.Ws + d1;
+                    const uint8_t ch = (KIND == SSD_KIND_CLEANUP && ((en >> 25) & 1)) ? CB(C_CLEAN) : CB(C_FIRE);
+                    uint8_t* p = tiles + a.pad_bytes + slot * tile_pitch + r * a.Ws + c;
+                    bool lost = false;
 #pragma unroll 1
-                for (int f0 = 0; f0 < nf; f0 += 10) {
-                    if (lane < 30 && f0 + ray_f < nf) {
-                        const uint32_t en = fire_list[f0 + ray_f];
-                        const int slot = (en >> 18) & 3, ag = en >> 21, ori = (en >> 16) & 3;
-                        const int d0 = (ori == 1) - (ori == 3), d1 = (ori == 2) - (ori == 0);
-                        int r = static_cast<int>((en >> 8) & 255) + d0, c = static_cast<int>(en & 255) + d1;
-                        if (ray_s == 1) { r += -d1 - d0; c += d0 - d1; }
-                        if (ray_s == 2) { r -= -d1 + d0; c -= d0 + d1; }
-                        const int n = envs[slot].raylen[ag * 3 + ray_s], dp = d0 * a.Ws + d1;
-                        uint8_t* p = tiles + a.pad_bytes + slot * tile_pitch + r * a.Ws + c;
+                    for (int i = 0; i < n; ++i) {
+                        if (check) lost |= (*p != ch); else *p = ch;
+                        p += dp;
+                    }
+                    return lost;
+                };
 #pragma unroll 1
-                        for (int i = 0; i < n; ++i) { *p = CB(C_FIRE); p += dp; }
+                for (int f0 = 0; f0 < nf; f0 += 10)
+                    if (lane < 30 && f0 + ray_f < nf) paint(fire_list[f0 + ray_f], ray_s, false);
+                __syncwarp();
+                if (KIND == SSD_KIND_CLEANUP) {
+                    bool lost = false;
+#pragma unroll 1
+                    for (int f0 = 0; f0 < nf; f0 += 10)
+                        if (lane < 30 && f0 + ray_f < nf) lost |= paint(fire_list[f0 + ray_f], ray_s, true);
+                    if (__any_sync(0xffffffffu, lost)) {
+#pragma unroll 1
+                        for (int f = 0; f < nf; ++f) {
+                            if (lane < 3) paint(fire_list[f], lane, false);
+                            __syncwarp();
+                        }
                     }
                 }
                 __syncwarp();
             }
-            if (KIND == SSD_KIND_CLEANUP) {  // beams in firing order: a later beam overwrites an earlier one
-                const bool in_order = a.order != nullptr;
+            if (literal_beams) {  // beams in firing order: a later beam overwrites an earlier one
                 for (int k = 0; k < N; ++k) {
-                    const int ag = in_order ? S.order[k] : k;
+                    const int ag = S.order[k];
                     const bool fired = (fmask >> (gbase + ag)) & 1u;
-                    if (in_order ? !__any_sync(0xffffffffu, fired) : !((fmask >> k) & kSlotLsb)) continue;
+                    if (!__any_sync(0xffffffffu, fired)) continue;
                     const uint32_t key_k = __shfl_sync(0xffffffffu, me.key, ag, G);
                     const int ori_k = __shfl_sync(0xffffffffu, me.ori, ag, G);
                     const int act_k = __shfl_sync(0xffffffffu, me.act, ag, G);
@@ -391,6 +455,7 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
             if (me.act != -2) a.agents[gi] = (me.key >> 8) | (me.key & 255) << 8 | static_cast<uint32_t>(me.ori) << 16;
             a.rew[gi] = me.rew;
         }
+        if (KIND == SSD_KIND_CLEANUP && al == 0) a.orch[static_cast<size_t>(e) * a.orch_stride] = static_cast<uint32_t>(S.hcount);
         if (a.publish) {  // everything this task wrote (grid, agent words, rewards, observation rows) is visible before the word is
             bulk_wait_all();  // all lanes: only the lane that committed the bulk stores actually waits
             __syncwarp();
