@@ -67,6 +67,7 @@ struct SsdEnv {
     uint32_t init_waste = 0;  // 'H' cells of the reset grid (Cleanup)
     unsigned long long* d_stats = nullptr;
     int* d_bad = nullptr;  // ssd_set_state: number of agent positions outside the map
+    unsigned long long* d_prof = nullptr;  // profiling builds only (SSD_PROF)
     int32_t* d_rows = nullptr; int rows_cap = 0;  // ssd_reset_rows: device copy of a host row list
     // ssd_step_host plumbing
     bool host_ready = false;
@@ -154,6 +155,7 @@ void fill_args(SsdEnv* h, ssd::StepArgs& a) {
     a.apple_thr = h->d_athr; a.apple_p = h->d_ap; a.waste_thr = h->d_wthr; a.waste_p = h->d_wp;
     a.grid = h->d_grid; a.agents = h->d_agents; a.beam_buf = h->d_beam_buf;
     a.stats = h->d_stats;
+    a.prof = h->d_prof;
 }
 
 int check_handle(ssd_handle h) { return h ? 0 : fail(SSD_ERR_INVALID, "null handle"); }
@@ -311,6 +313,10 @@ int ssd_create(const SsdConfig* cfg, ssd_handle* out) {
     h->E = E;
     h->B_pad = (h->B + E - 1) / E * E;
 
+    // the specialised kernel fetches the tables with bulk copies of whole 16-byte units: pad them (ssd_step_fast.cu)
+    while (apple.size() % 64) apple.push_back(static_cast<uint16_t>(h->Ws + 1));  // a harmless interior cell
+    while (pt_mask.size() % 4) pt_mask.push_back(0);
+    while (pt_pre.size() % 8) pt_pre.push_back(0);
     int bad = 0;
     bad |= h->upload(&h->d_apple, apple);
     bad |= h->upload(&h->d_waste, waste); bad |= h->upload(&h->d_spawn, spawn); bad |= h->upload(&h->d_color, color);
@@ -325,6 +331,7 @@ int ssd_create(const SsdConfig* cfg, ssd_handle* out) {
     bad |= h->alloc(&h->d_stats, static_cast<size_t>(SSD_NUM_STATS));
     bad |= h->alloc(&h->chain.done, static_cast<size_t>(h->B_pad / 2 + 1));  // one word per task (4 or 2 envs)
     bad |= h->alloc(&h->d_bad, 1);
+    if (ssd::knob("SSD_PROF")) { bad |= h->alloc(&h->d_prof, 32); if (!bad) cudaMemset(h->d_prof, 0, 32 * sizeof(unsigned long long)); }
     h->chain.cta_slots = prop.multiProcessorCount * 8;  // resident CTAs at the specialised kernel's shape (8 per SM)
     if (bad) { const char* m = cudaGetErrorString(cudaGetLastError()); ssd_destroy(h); return fail(SSD_ERR_CUDA, "device allocation failed: %s", m); }
     // initial state: post-reset_map grid, agents parked on the first spawn point (or cell 1,1)
@@ -357,6 +364,14 @@ int ssd_create(const SsdConfig* cfg, ssd_handle* out) {
 int ssd_destroy(ssd_handle h) {
     if (!h) return SSD_OK;
     cudaSetDevice(h->cfg.device);
+    if (h->d_prof) {  // profiling builds: per-phase cycles of the specialised kernel, per warp task
+        unsigned long long p[32];
+        if (cudaMemcpy(p, h->d_prof, sizeof p, cudaMemcpyDeviceToHost) == cudaSuccess) {
+            fprintf(stderr, "SSD_PROF B=%d:", h->B);
+            for (int i = 0; i < 16; ++i) if (p[16 + i]) fprintf(stderr, " t%d=%.0f", i, static_cast<double>(p[i]) / static_cast<double>(p[16 + i]));
+            fprintf(stderr, "\n");
+        }
+    }
     for (int i = 0; i < 2; ++i) if (h->hs[i]) cudaStreamDestroy(h->hs[i]);
     if (h->host_ev) cudaEventDestroy(h->host_ev);
     for (void* p : h->allocs) cudaFree(p);

@@ -63,6 +63,32 @@ inline const char* knob(const char* name) { return getenv(name); }
 inline const char* knob(const char*) { return nullptr; }
 #endif
 
+// Per-phase clock accounting of the specialised kernel (profiles/phase_clocks.py): SSD_TICK(i) adds the cycles since the
+// previous tick of this warp to prof[i] and counts the tick in prof[16 + i].  Compiled out of production builds.
+#ifdef SSD_PROFILING_KNOBS
+#define SSD_TICK(i)                                                                                              \
+    do {                                                                                                         \
+        if (a.prof != nullptr && (threadIdx.x & 31) == 0) {                                                      \
+            const long long now_ = clock64();                                                                    \
+            atomicAdd(s_prof + (i), static_cast<unsigned long long>(now_ - tick_));                              \
+            atomicAdd(s_prof + 16 + (i), 1ull);                                                                  \
+            tick_ = clock64();                                                                                   \
+        }                                                                                                        \
+    } while (0)
+#define SSD_TICK_DECL __shared__ unsigned long long s_prof[32]; if (threadIdx.x < 32) s_prof[threadIdx.x] = 0
+#define SSD_TICK_INIT long long tick_ = clock64()
+#define SSD_TICK_FLUSH                                                                                            \
+    do {                                                                                                         \
+        __syncthreads();                                                                                         \
+        if (a.prof != nullptr && threadIdx.x < 32 && s_prof[threadIdx.x]) atomicAdd(a.prof + threadIdx.x, s_prof[threadIdx.x]); \
+    } while (0)
+#else
+#define SSD_TICK(i) do { } while (0)
+#define SSD_TICK_DECL do { } while (0)
+#define SSD_TICK_INIT do { } while (0)
+#define SSD_TICK_FLUSH do { } while (0)
+#endif
+
 constexpr uint8_t kFlag = 0x80;
 constexpr uint8_t kCodeMask = 0x7C;  // cell code without the neighbour count and the agent flag
 
@@ -175,6 +201,7 @@ struct StepArgs {
     int dep_wait;         // wait for done[task] == epoch - 1 instead of relying on stream order
     int publish;          // write done[task] = epoch when the task's results are visible
     int pdl_wait;         // launched early behind the previous kernel of the stream: griddepcontrol.wait after the prologue
+    unsigned long long* prof;  // SSD_PROFILING_KNOBS builds with SSD_PROF set: [32] per-phase cycle sums and tick counts
 };
 
 // Host-side bookkeeping of the step chain (one per handle).

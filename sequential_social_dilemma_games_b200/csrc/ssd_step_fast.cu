@@ -26,7 +26,7 @@ __host__ __device__ constexpr int row_words_min(int RB) {
     return m;
 }
 
-template <int VT>
+template <int VT, bool SHFL_LUT = false>
 __device__ __forceinline__ void render_rows_tma(const uint2* s_view, const uint8_t* tiles, const uint32_t* s_color,
                                                 uint32_t* stage, uint8_t* dst, int total_rows, int debug) {
     constexpr int RB = 3 * VT;            // bytes per view row
@@ -56,6 +56,7 @@ __device__ __forceinline__ void render_rows_tma(const uint2* s_view, const uint8
     uint8_t* gp = img0 + lo0;           // destination, source and size of the next bulk store
     uint32_t sp = stage32 + lo0, nb = CH - lo0;
     uint32_t c0 = 0, c1 = 0, c2 = 0;
+    const uint32_t lane_color = s_color[(4 * lane) % kLutEntries];  // SHFL_LUT: lane L holds the colour of cell code L
 #pragma unroll 1
     for (int c = 0; c < n_chunks; ++c) {
         const int R = min(c * 32 + lane, total_rows - 1);  // lanes past the end redo the last row; their words are never copied out
@@ -65,8 +66,13 @@ __device__ __forceinline__ void render_rows_tma(const uint2* s_view, const uint8
             const uint2 vp = s_view[ga];
             const int si = static_cast<int16_t>(vp.y & 0xffffu), sj = static_cast<int32_t>(vp.y) >> 16;
             const uint8_t* g = tiles + static_cast<int32_t>(vp.x) + i * si;
+            if (SHFL_LUT) {
 #pragma unroll
-            for (int j = 0; j < VT; ++j) X[j] = cell_color(s_color, g[j * sj]);
+                for (int j = 0; j < VT; ++j) X[j] = __shfl_sync(0xffffffffu, lane_color, g[j * sj] >> 2);
+            } else {
+#pragma unroll
+                for (int j = 0; j < VT; ++j) X[j] = cell_color(s_color, g[j * sj]);
+            }
         }
         X[VT] = __shfl_down_sync(0xffffffffu, X[0], 1);
         X[VT + 1] = 0;
@@ -112,30 +118,38 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
     constexpr uint32_t kSlotLsb = G == 8 ? 0x01010101u : 0x00010001u;  // bit 0 of every env's lane group
     using FastScratch = FastScratchT<G>;
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ uint32_t s_color[kLutEntries];
+    __shared__ __align__(16) uint32_t s_color[kLutEntries];
+    __shared__ __align__(8) uint64_t s_tab_bar;
     __shared__ int s_cta_stats[SSD_NUM_STATS];
     __shared__ int s_done;
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
     const int N = a.N;
     uint16_t* s_apple = reinterpret_cast<uint16_t*>(smem + a.Lf.apple);
     pdl_launch_dependents();  // a chained next step may start launching (it waits per task, see below)
+    SSD_TICK_DECL;
 
-    for (int i = tid; i < kLutEntries; i += nthr) s_color[i] = a.color[i];
+    // CTA-shared tables (colours, apple points, cell -> point): static data, fetched by four bulk copies that travel while the
+    // warps set up and issue their tile loads; nobody waits for them before the tiles have been asked for.
+    static_assert(kLutEntries * 4 % 16 == 0, "the colour table is one bulk copy");
+    if (tid == 0) {
+        const uint32_t b_apple = KIND != SSD_KIND_PLAIN ? static_cast<uint32_t>((a.n_apple + 63) & ~63) * 2u : 0u;
+        const uint32_t ncw = static_cast<uint32_t>(a.env_bytes + 31) / 32u;
+        const uint32_t b_mask = ORCH ? ((ncw * 4u + 15u) & ~15u) : 0u, b_pre = ORCH ? ((ncw * 2u + 15u) & ~15u) : 0u;
+        mbar_init(&s_tab_bar, 1);
+        mbar_expect_tx(&s_tab_bar, kLutEntries * 4u + b_apple + b_mask + b_pre);
+        bulk_g2s(s_color, a.color, kLutEntries * 4u, &s_tab_bar);
+        if (b_apple) bulk_g2s(s_apple, a.apple_cell, b_apple, &s_tab_bar);
+        if (ORCH) {
+            bulk_g2s(smem + a.Lf.pt_mask, a.pt_mask, b_mask, &s_tab_bar);
+            bulk_g2s(smem + a.Lf.pt_pre, a.pt_pre, b_pre, &s_tab_bar);
+        }
+    }
     if (tid < SSD_NUM_STATS) s_cta_stats[tid] = 0;
     if (tid == 0) s_done = 0;
-    if (KIND != SSD_KIND_PLAIN)
-#pragma unroll 1
-        for (int i = tid; i < ((a.n_apple + 63) & ~63); i += nthr) s_apple[i] = i < a.n_apple ? a.apple_cell[i] : static_cast<uint16_t>(a.Ws + 1);
     OrchTables T;
     T.pt_mask = reinterpret_cast<const uint32_t*>(smem + a.Lf.pt_mask); T.pt_pre = reinterpret_cast<const uint16_t*>(smem + a.Lf.pt_pre);
     T.nW = a.nW; T.stride = a.orch_stride; T.nz = a.harvest_nz;
-    if (ORCH)
-#pragma unroll 1
-        for (int i = tid; i < (a.env_bytes + 31) / 32; i += nthr) {
-            reinterpret_cast<uint32_t*>(smem + a.Lf.pt_mask)[i] = a.pt_mask[i];
-            reinterpret_cast<uint16_t*>(smem + a.Lf.pt_pre)[i] = a.pt_pre[i];
-        }
-    __syncthreads();
+    __syncthreads();  // the table barrier is initialised
 
     uint8_t* wbase = smem + a.Lf.warp0 + warp * a.Lf.warp_stride;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(wbase + a.Lf.w_mbar);
@@ -149,9 +163,23 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
     // Every fast launch carries the programmatic-serialization attribute: the CTAs become resident while the previous
     // kernel of the stream drains and do everything above (tables, barrier) early.  Unless this step is chained to it
     // task by task (dep_wait), nothing that kernel wrote is touched before it has completed.
+    SSD_TICK_INIT;
     if (a.pdl_wait) pdl_wait();
+    SSD_TICK(0);  // waiting for the previous kernel
 
     if (we < a.env_end) {
+        // agent words and actions first: their latency hides behind the set-up of the tile loads.  (A chained step may read
+        // the agent words only after it has seen its predecessor's completion word; its actions exist by contract.)
+        const int al = lane & (G - 1), gbase = lane & ~(G - 1), j = lane / G;
+        const int e = we + j;
+        const bool valid = al < N;
+        const size_t gi = static_cast<size_t>(e) * N + (valid ? al : 0);
+        uint32_t w_agent = 0;
+        int act_in = -1;
+        if (valid) {
+            act_in = a.actions[gi];
+            if (!a.dep_wait) w_agent = __ldcg(a.agents + gi);
+        }
         // ---- load: one TMA bulk copy per env tile; zero the frames while they are in flight
         if (lane == 0) {
             mbar_init(mbar, 1);
@@ -175,32 +203,31 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
 #pragma unroll 1
                 for (int i = lane * 16; i < a.pad_bytes; i += 512) *reinterpret_cast<uint4*>(tiles + q * tile_pitch + i) = z;
         }
-        // agent words and actions travel while the tiles do
-        const int al = lane & (G - 1), gbase = lane & ~(G - 1), j = lane / G;
         FastScratch& S = envs[j];
         uint8_t* g = tiles + a.pad_bytes + j * tile_pitch;
-        const int e = we + j;
-        const bool valid = al < N;
-        const size_t gi = static_cast<size_t>(e) * N + (valid ? al : 0);
         PhiloxKey pk;
         pk.k0 = a.key0; pk.k1 = a.key1; pk.t = a.t;
         pk.env = static_cast<uint32_t>(a.env_id0 + static_cast<uint64_t>(e));
         AgentLane me;
         me.key = 0x0101; me.ori = 0; me.act = -1; me.rew = 0;
         if (valid) {
-            const uint32_t w = __ldcg(a.agents + gi);  // L2: a chained predecessor may just have written it
-            me.act = (w >> 24) & 1u ? -2 : a.actions[gi];  // -2: parked on a wall cell by ssd_set_state, never acts
+            const uint32_t w = a.dep_wait ? __ldcg(a.agents + gi) : w_agent;  // L2: a chained predecessor may just have written it
+            me.act = (w >> 24) & 1u ? -2 : act_in;  // -2: parked on a wall cell by ssd_set_state, never acts
             me.key = (w & 255) << 8 | ((w >> 8) & 255);
             me.ori = (w >> 16) & 3;
             S.order[al] = a.order != nullptr ? a.order[gi] : static_cast<uint8_t>(al);  // action-dict order (NULL: agent order)
             S.rew[al] = 0;
         }
+        SSD_TICK(1);  // issue loads, zero frames
+        mbar_wait(&s_tab_bar, 0);  // tables landed (long ago, except in the first tasks of a wave)
         mbar_wait(mbar, 0);  // tiles landed
         __syncwarp();
+        SSD_TICK(2);  // TMA wait
 
         // ---- phase A: one lane per agent
         moves_group<TAPE>(a, S, reinterpret_cast<MoveScratch*>(wbase + a.Lf.w_union)[j], g, me, valid, al, G, e, pk);
         cnt.steps += (al == 0);
+        SSD_TICK(3);  // moves
         if (valid) S.pos[al] = static_cast<uint16_t>(me.key);
         const int my_idx = tile_idx(a, me.key);
         uint32_t* const my_bm = orch_s + j * a.orch_stride;          // ORCH: the bitmaps of this lane's env ...
@@ -229,6 +256,7 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
         __syncwarp();
         if (KIND != SSD_KIND_PLAIN && valid) g[my_idx] |= kFlag;  // "an agent stands here"
         __syncwarp();
+        SSD_TICK(4);  // consume, flags
         uint32_t fmask = 0;  // bit (8 * env slot + agent): that agent fires
         uint32_t* const fire_list = reinterpret_cast<uint32_t*>(wbase + a.Lf.w_union);
         const int ray_f = lane / 3, ray_s = lane - 3 * ray_f;  // ray lane -> (firing agent of the round, ray)
@@ -325,6 +353,7 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
             }
         }
         if (valid) me.rew += S.rew[al];  // -50 per hit taken
+        SSD_TICK(5);  // beams
 
         // ---- phase B: the whole warp per env
         if (KIND != SSD_KIND_PLAIN && !SSD_SKIP(a.debug, 4)) {
@@ -348,6 +377,7 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
             __syncwarp();
         }
 
+        SSD_TICK(6);  // spawn
         // ---- store: grid tiles back to HBM, one TMA bulk store per tile.  The overlay below repaints the tiles, so the
         // warp waits until the copy engine has READ them (not until the writes have landed).
         if (!SSD_SKIP(a.debug, 64)) {
@@ -363,6 +393,7 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
             bulk_wait_read();
         }
         __syncwarp();  // the write-back above has read the tiles
+        SSD_TICK(7);  // grid write-back (until the copy engine has read the tiles)
 
         // ---- phase C: overlay (get_map_with_agents map_env.py:280-302), view geometry, packed rows
         {
@@ -447,10 +478,18 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
                                                 (static_cast<uint32_t>(si) & 0xffffu) | static_cast<uint32_t>(sj) << 16);
             }
             __syncwarp();
-            if (!SSD_SKIP(a.debug, 2))
+            SSD_TICK(8);  // overlay, view parameters
+            if (SSD_SKIP(a.debug, 128))  // experiment: rows leave with LDS.128 / STG.128 pairs instead of bulk stores
+                render_rows<VT>(s_view, tiles, s_color, reinterpret_cast<uint32_t*>(wbase + a.Lf.w_union + a.Lf.u_stage),
+                                a.obs + static_cast<size_t>(we) * a.obs_env, EPW * N * VT);
+            else if (SSD_SKIP(a.debug, 256))  // experiment: colour lookup by warp shuffle
+                render_rows_tma<VT, true>(s_view, tiles, s_color, reinterpret_cast<uint32_t*>(wbase + a.Lf.w_union + a.Lf.u_stage),
+                                          a.obs + static_cast<size_t>(we) * a.obs_env, EPW * N * VT, a.debug);
+            else if (!SSD_SKIP(a.debug, 2))
             render_rows_tma<VT>(s_view, tiles, s_color, reinterpret_cast<uint32_t*>(wbase + a.Lf.w_union + a.Lf.u_stage),
                                 a.obs + static_cast<size_t>(we) * a.obs_env, EPW * N * VT, a.debug);
         }
+        SSD_TICK(9);  // rows
         if (valid) {  // agent words and rewards last: no ordinary global store is in flight when the row loop fences
             if (me.act != -2) a.agents[gi] = (me.key >> 8) | (me.key & 255) << 8 | static_cast<uint32_t>(me.ori) << 16;
             a.rew[gi] = me.rew;
@@ -466,6 +505,7 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
         }
     }
 
+    SSD_TICK(10);  // agent words, rewards, publish
     // ---- stats: warp -> CTA -> one set of global atomics per CTA (issued by the last warp to finish)
     if (a.stats != nullptr && !SSD_SKIP(a.debug, 32)) {
         // per-warp totals are small (<= 32 agents): two packed reductions carry all seven counters
@@ -485,6 +525,7 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
             if (tot) atomicAdd(&a.stats[lane], static_cast<unsigned long long>(tot));
         }
     }
+    SSD_TICK_FLUSH;
 }
 
 // ====================================================================== launchers
