@@ -331,7 +331,7 @@ int ssd_create(const SsdConfig* cfg, ssd_handle* out) {
     bad |= h->alloc(&h->d_stats, static_cast<size_t>(SSD_NUM_STATS));
     bad |= h->alloc(&h->chain.done, static_cast<size_t>(h->B_pad / 2 + 1));  // one word per task (4 or 2 envs)
     bad |= h->alloc(&h->d_bad, 1);
-    if (ssd::knob("SSD_PROF")) { bad |= h->alloc(&h->d_prof, 32); if (!bad) cudaMemset(h->d_prof, 0, 32 * sizeof(unsigned long long)); }
+    if (ssd::knob("SSD_PROF")) { bad |= h->alloc(&h->d_prof, 48); if (!bad) cudaMemset(h->d_prof, 0, 48 * sizeof(unsigned long long)); }
     h->chain.cta_slots = prop.multiProcessorCount * 8;  // resident CTAs at the specialised kernel's shape (8 per SM)
     if (bad) { const char* m = cudaGetErrorString(cudaGetLastError()); ssd_destroy(h); return fail(SSD_ERR_CUDA, "device allocation failed: %s", m); }
     // initial state: post-reset_map grid, agents parked on the first spawn point (or cell 1,1)
@@ -365,10 +365,12 @@ int ssd_destroy(ssd_handle h) {
     if (!h) return SSD_OK;
     cudaSetDevice(h->cfg.device);
     if (h->d_prof) {  // profiling builds: per-phase cycles of the specialised kernel, per warp task
-        unsigned long long p[32];
+        unsigned long long p[48];
         if (cudaMemcpy(p, h->d_prof, sizeof p, cudaMemcpyDeviceToHost) == cudaSuccess) {
             fprintf(stderr, "SSD_PROF B=%d:", h->B);
             for (int i = 0; i < 16; ++i) if (p[16 + i]) fprintf(stderr, " t%d=%.0f", i, static_cast<double>(p[i]) / static_cast<double>(p[16 + i]));
+            fprintf(stderr, "\nSSD_PROF max:");
+            for (int i = 0; i < 16; ++i) if (p[16 + i]) fprintf(stderr, " t%d=%llu", i, p[32 + i]);
             fprintf(stderr, "\n");
         }
     }

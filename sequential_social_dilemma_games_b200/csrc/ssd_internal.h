@@ -72,15 +72,17 @@ inline const char* knob(const char*) { return nullptr; }
             const long long now_ = clock64();                                                                    \
             atomicAdd(s_prof + (i), static_cast<unsigned long long>(now_ - tick_));                              \
             atomicAdd(s_prof + 16 + (i), 1ull);                                                                  \
+            atomicMax(s_prof + 32 + (i), static_cast<unsigned long long>(now_ - tick_));                         \
             tick_ = clock64();                                                                                   \
         }                                                                                                        \
     } while (0)
-#define SSD_TICK_DECL __shared__ unsigned long long s_prof[32]; if (threadIdx.x < 32) s_prof[threadIdx.x] = 0
+#define SSD_TICK_DECL __shared__ unsigned long long s_prof[48]; if (threadIdx.x < 48) s_prof[threadIdx.x] = 0
 #define SSD_TICK_INIT long long tick_ = clock64()
 #define SSD_TICK_FLUSH                                                                                            \
     do {                                                                                                         \
         __syncthreads();                                                                                         \
         if (a.prof != nullptr && threadIdx.x < 32 && s_prof[threadIdx.x]) atomicAdd(a.prof + threadIdx.x, s_prof[threadIdx.x]); \
+        if (a.prof != nullptr && threadIdx.x >= 32 && threadIdx.x < 48) atomicMax(a.prof + threadIdx.x, s_prof[threadIdx.x]); \
     } while (0)
 #else
 #define SSD_TICK(i) do { } while (0)
@@ -122,12 +124,10 @@ struct FastScratchT {
 };
 static_assert(sizeof(FastScratchT<8>) == 96 && sizeof(FastScratchT<16>) == 176, "FastScratchT is 10 bytes per lane + 16");
 
-// Scratch of the literal update_moves emulation (moves_slow); lives in the per-warp phase union.
+// Scratch of the literal update_moves emulation (moves_coop); lives in the per-warp phase union.
 struct MoveScratch {
-    uint16_t tgt[kMaxAgents];   // agent_moves values (map_env.py:400)
-    uint16_t orig[kMaxAgents];  // search_list: targets frozen before the contested pass (:426)
-    uint16_t snap[kMaxAgents];  // agent_by_pos snapshot of one fix-point pass (:495)
-    uint8_t shuf[kMaxAgents];   // movers after np.random.shuffle (:422)
+    uint16_t orig[kMaxAgents];  // rank of every mover in the shuffled order
+    uint8_t shuf[kMaxAgents];   // movers after np.random.shuffle (map_env.py:422)
 };
 static_assert(sizeof(MoveScratch) % 16 == 0, "MoveScratch must stay 16-byte sized");
 
@@ -201,7 +201,7 @@ struct StepArgs {
     int dep_wait;         // wait for done[task] == epoch - 1 instead of relying on stream order
     int publish;          // write done[task] = epoch when the task's results are visible
     int pdl_wait;         // launched early behind the previous kernel of the stream: griddepcontrol.wait after the prologue
-    unsigned long long* prof;  // SSD_PROFILING_KNOBS builds with SSD_PROF set: [32] per-phase cycle sums and tick counts
+    unsigned long long* prof;  // SSD_PROFILING_KNOBS builds with SSD_PROF set: [48] per-phase cycle sums, tick counts, maxima
 };
 
 // Host-side bookkeeping of the step chain (one per handle).

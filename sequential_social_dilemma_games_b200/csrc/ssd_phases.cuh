@@ -3,8 +3,8 @@
 //
 //   A   moves (map_env.py:357-543), consume (:178-181), beams (:545-649): ONE LANE PER AGENT, a group of
 //       G = 8 or 16 lanes per env.  Conflict-free moves are resolved with shuffles; an env with any
-//       contested / occupied target falls back to the literal sequential emulation of update_moves on
-//       the group's first lane.  A firing agent's three rays walk on 3 lanes.
+//       contested / occupied target runs the literal emulation of update_moves, its group of lanes working
+//       together (moves_coop).  A firing agent's three rays walk on 3 lanes.
 //   B   custom_map_update (harvest.py:69-104, cleanup.py:113-179): the whole warp per env, ballot/popc
 //       prefix ranks give every eligible cell its sequential draw index
 //   C   get_map_with_agents + return_view + map_to_colors + rotate_view (map_env.py:189-199): one lane per
@@ -101,12 +101,6 @@ struct Counters {  // per-lane event counts, reduced per warp at the end of the 
 };
 
 // ====================================================================== phase A: moves
-__device__ __forceinline__ bool occupied(const uint16_t* p, int N, uint32_t key) {
-    bool f = false;  // `x in self.agent_pos` (map_env.py:251-253)
-#pragma unroll 1
-    for (int a = 0; a < N; ++a) f |= (p[a] == key);
-    return f;
-}
 __device__ __forceinline__ int by_pos(const uint16_t* p, int N, uint32_t key) {
     int o = -1;  // dict built in agent order: the LAST agent on a cell wins (map_env.py:397)
 #pragma unroll 1
@@ -114,107 +108,105 @@ __device__ __forceinline__ int by_pos(const uint16_t* p, int N, uint32_t key) {
     return o;
 }
 
-// Literal emulation of the conflict resolution of update_moves (map_env.py:394-543) for one env,
-// run by a single lane.  S.pos / S.tgt hold positions and wall-clipped targets of the movers.
+// Literal emulation of the conflict resolution of update_moves (map_env.py:394-543) for one env, run by ALL lanes of the env's
+// group together (lane = agent): positions, targets and the frozen targets stay in registers, `x in self.agent_pos` and
+// `agent_by_pos[x]` are one ballot each, and the control flow -- contested cells in key order, then the fix-point passes in
+// action order, exactly the reference's loops -- is uniform across the group.  (A single lane walking shared-memory arrays took
+// up to 40 000 cycles for this, and a step kernel is as slow as its slowest warp.)  `gm` is the group's lane mask; every lane of
+// the group must call this, converged.
 template <bool TAPE, class ES>
-__device__ __noinline__ void moves_slow(const StepArgs& a, ES& S, MoveScratch& M, uint32_t movers, int local_env,
-                                         const PhiloxKey& pk) {
+__device__ __noinline__ void moves_coop(const StepArgs& a, ES& S, MoveScratch& M, uint32_t movers, int local_env, const PhiloxKey& pk,
+                                        uint32_t& pos, uint32_t tgt, bool valid, int al, int G, uint32_t gm) {
     const int N = a.N;
-    // mover list in action order (agent_moves is an insertion-ordered dict, map_env.py:400-412)
-    uint8_t* shuf = M.shuf;
-    int n_mov = 0;
+    const int gshift = (threadIdx.x & 31) & ~(G - 1);
+    const bool mover = valid && ((movers >> al) & 1u);
+    // np.random.shuffle of the movers (action order), map_env.py:421-423: lane 0 of the group draws, everybody reads its rank
+    if (al == 0) {
+        uint8_t* shuf = M.shuf;
+        int n_mov = 0;
 #pragma unroll 1
-    for (int k = 0; k < N; ++k) {
-        const int ag = S.order[k];
-        if (movers >> ag & 1) shuf[n_mov++] = static_cast<uint8_t>(ag);
-    }
-    // np.random.shuffle(shuffle_list), map_env.py:421-423
-    if (TAPE) {
-        const uint8_t* mo = a.tape_move + static_cast<size_t>(local_env) * N;
-#pragma unroll 1
-        for (int i = 0; i < n_mov; ++i) shuf[i] = mo[i] < N ? mo[i] : static_cast<uint8_t>(N - 1);  // malformed tapes must not fault
-    } else {
-        uint4 blk = make_uint4(0, 0, 0, 0);
-        uint32_t w = 0;
-#pragma unroll 1
-        for (int i = n_mov - 1; i >= 1; --i, ++w) {
-            if ((w & 3) == 0) blk = philox4x32_10(pk.env, pk.t, STREAM_MOVE, w >> 2, pk.k0, pk.k1);
-            const uint32_t j = __umulhi(pick_word(blk, w), static_cast<uint32_t>(i + 1));
-            const uint8_t tmp = shuf[i]; shuf[i] = shuf[j]; shuf[j] = tmp;
+        for (int k = 0; k < N; ++k) {
+            const int ag = S.order[k];
+            if (movers >> ag & 1) shuf[n_mov++] = static_cast<uint8_t>(ag);
         }
-    }
+        if (TAPE) {
+            const uint8_t* mo = a.tape_move + static_cast<size_t>(local_env) * N;
 #pragma unroll 1
-    for (int ag = 0; ag < N; ++ag) M.orig[ag] = (movers >> ag & 1) ? M.tgt[ag] : 0xFFFFu;
+            for (int i = 0; i < n_mov; ++i) shuf[i] = mo[i] < N ? mo[i] : static_cast<uint8_t>(N - 1);  // malformed tapes must not fault
+        } else {
+            uint4 blk = make_uint4(0, 0, 0, 0);
+            uint32_t w = 0;
+#pragma unroll 1
+            for (int i = n_mov - 1; i >= 1; --i, ++w) {
+                if ((w & 3) == 0) blk = philox4x32_10(pk.env, pk.t, STREAM_MOVE, w >> 2, pk.k0, pk.k1);
+                const uint32_t j = __umulhi(pick_word(blk, w), static_cast<uint32_t>(i + 1));
+                const uint8_t tmp = shuf[i]; shuf[i] = shuf[j]; shuf[j] = tmp;
+            }
+        }
+#pragma unroll 1
+        for (int i = 0; i < n_mov; ++i) M.orig[shuf[i]] = static_cast<uint16_t>(i);  // rank of every mover in the shuffled order
+    }
+    __syncwarp(gm);
+    const uint32_t rank = mover ? M.orig[al] : 0xFFu;
+    const uint32_t orig = mover ? tgt : 0xFFFFFFFFu;  // search_list: targets frozen before the contested pass (:426)
+    auto occupied_now = [&](uint32_t cell) { return __ballot_sync(gm, valid && pos == cell) != 0u; };          // x in self.agent_pos
+    auto by_pos_of = [&](uint32_t key, uint32_t cell) {                                                        // the LAST agent on a cell wins (:397)
+        const uint32_t m = (__ballot_sync(gm, valid && key == cell) & gm) >> gshift;
+        return m ? 31 - __clz(m) : -1;
+    };
 
     // contested cells in lexicographic (row, col) order == ascending key (np.unique axis=0, :424)
     int prev = -1;
     while (true) {
-        int cell = 0x10000, cnt = 0;
-#pragma unroll 1
-        for (int ag = 0; ag < N; ++ag) {
-            const int o = M.orig[ag];
-            if (o != 0xFFFF && o > prev) {
-                if (o < cell) { cell = o; cnt = 1; } else if (o == cell) ++cnt;
-            }
+        const uint32_t cand = (mover && static_cast<int>(orig) > prev) ? orig : 0x10000u;
+        const uint32_t cell = __reduce_min_sync(gm, cand);
+        if (cell == 0x10000u) break;
+        prev = static_cast<int>(cell);
+        const bool in_cell = mover && orig == cell;
+        const uint32_t same = __ballot_sync(gm, in_cell);
+        if (__popc(same) < 2) continue;
+        bool bad = false;  // conditions (1)-(3) of :449-478 for this agent; nothing they read changes inside the reference's loop
+        if (occupied_now(cell)) {
+            const int o = by_pos_of(pos, cell);
+            const uint32_t o_tgt = __shfl_sync(gm, tgt, o, G);
+            const bool o_moves = (movers >> o) & 1u;
+            // cpos == cell: o stands on the cell
+            bad = in_cell && (al == o || !o_moves || o_tgt == cell || o_tgt == pos);
         }
-        if (cell == 0x10000) break;
-        prev = cell;
-        if (cnt < 2) continue;
-        bool cell_free = true;
-        int winner = -1;
-#pragma unroll 1
-        for (int i = 0; i < n_mov; ++i) {  // conflicting agents in shuffled order (:441-442)
-            const int ag = shuf[i];
-            if (M.orig[ag] != cell) continue;
-            if (winner < 0) winner = ag;  // agent_to_slot[index]: first occurrence (:481)
-            if (occupied(S.pos, N, cell)) {                       // :449
-                const int o = by_pos(S.pos, N, cell);             // :452 (rebuilt after every update)
-                const uint32_t cpos = S.pos[o];
-                const bool o_moves = movers >> o & 1;
-                const uint32_t cmove = o_moves ? M.tgt[o] : cpos; // :456
-                if (ag == o) cell_free = false;                                   // (1) :460
-                else if (!o_moves || cpos == cmove) cell_free = false;            // (2) :466
-                else if (M.tgt[o] == S.pos[ag] && cell == (int)S.pos[o]) cell_free = false;  // (3) :472
-            }
-        }
-        if (cell_free) S.pos[winner] = static_cast<uint16_t>(cell);  // :480-483
-#pragma unroll 1
-        for (int i = 0; i < n_mov; ++i) {                            // :486-491
-            const int ag = shuf[i];
-            if (M.orig[ag] == cell) M.tgt[ag] = S.pos[ag];
-        }
+        const bool cell_free = __ballot_sync(gm, bad) == 0u;
+        const int winner = static_cast<int>(__reduce_min_sync(gm, in_cell ? (rank << 8 | static_cast<uint32_t>(al)) : 0xFFFFu) & 255u);  // first in shuffled order (:481)
+        if (cell_free && al == winner) pos = cell;  // :480-483
+        if (in_cell) tgt = pos;                      // :486-491 (the winner included: everybody is a "stay" now)
     }
 
     // remaining moves: fix-point loop, map_env.py:494-543
     uint32_t alive = movers;
     while (alive) {
-#pragma unroll 1
-        for (int ag = 0; ag < N; ++ag) M.snap[ag] = S.pos[ag];  // agent_by_pos snapshot (:495)
-        const uint32_t in_copy = alive;                         // moves_copy (:498)
+        const uint32_t snap = pos;       // agent_by_pos snapshot (:495)
+        const uint32_t in_copy = alive;  // moves_copy (:498)
         uint32_t deleted = 0;
 #pragma unroll 1
         for (int k = 0; k < N; ++k) {
             const int ag = S.order[k];
             if (!(in_copy >> ag & 1) || (deleted >> ag & 1)) continue;
-            const uint32_t mv = M.tgt[ag];
-            if (occupied(S.pos, N, mv)) {                   // :503 live positions
-                const int o = by_pos(M.snap, N, mv);        // :506 snapshot
-                if (o < 0) continue;                        // reference would KeyError; unreachable
-                const uint32_t cpos = S.pos[o];
-                const uint32_t cmove = (alive >> o & 1) ? M.tgt[o] : cpos;  // :509 live agent_moves
-                if (ag == o) { alive &= ~(1u << ag); deleted |= 1u << ag; }                                  // (1)
+            const uint32_t mv = __shfl_sync(gm, tgt, ag, G), ag_pos = __shfl_sync(gm, pos, ag, G);
+            if (occupied_now(mv)) {                     // :503 live positions
+                const int o = by_pos_of(snap, mv);      // :506 snapshot
+                if (o < 0) continue;                    // reference would KeyError; unreachable
+                const uint32_t cpos = __shfl_sync(gm, pos, o, G), o_tgt = __shfl_sync(gm, tgt, o, G);
+                const uint32_t cmove = (alive >> o & 1) ? o_tgt : cpos;  // :509 live agent_moves
+                if (ag == o) { alive &= ~(1u << ag); deleted |= 1u << ag; }                                    // (1)
                 else if (!(in_copy >> o & 1) || cpos == cmove) { alive &= ~(1u << ag); deleted |= 1u << ag; }  // (2)
-                else if (M.tgt[o] == S.pos[ag] && mv == S.pos[o]) {                                           // (3)
+                else if (o_tgt == ag_pos && mv == cpos) {                                                      // (3)
                     alive &= ~((1u << ag) | (1u << o)); deleted |= (1u << ag) | (1u << o);
                 }
             } else {
-                S.pos[ag] = static_cast<uint16_t>(mv);      // :532-535
+                if (al == ag) pos = mv;                 // :532-535
                 alive &= ~(1u << ag); deleted |= 1u << ag;
             }
         }
         if (alive == in_copy) {  // nobody could move freely: move them all (:540-543)
-#pragma unroll 1
-            for (int ag = 0; ag < N; ++ag) if (alive >> ag & 1) S.pos[ag] = M.tgt[ag];
+            if (valid && (alive >> al & 1)) pos = tgt;
             break;
         }
     }
@@ -267,13 +259,9 @@ __device__ __forceinline__ void moves_group(const StepArgs& a, ES& S, MoveScratc
     const uint32_t conf = conf_all & gmask;
     const uint32_t movers = (__ballot_sync(0xffffffffu, mover) & gmask) >> gshift;
     if (conf == 0 && mover) me.key = tgt;
-    if (conf_all != 0) {  // warp-uniform branch: groups without a conflict just keep the barriers company
-        if (conf != 0 && valid) { S.pos[al] = static_cast<uint16_t>(me.key); M.tgt[al] = static_cast<uint16_t>(tgt); }
-        __syncwarp();
-        if (conf != 0 && al == 0 && !SSD_SKIP(a.debug, 16)) moves_slow<TAPE, ES>(a, S, M, movers, local_env, pk);
-        __syncwarp();
-        if (conf != 0 && valid) me.key = S.pos[al];
-    }
+    if (conf != 0 && !SSD_SKIP(a.debug, 16))  // all lanes of a group with a conflict: the literal emulation, run by the group together
+        moves_coop<TAPE, ES>(a, S, M, movers, local_env, pk, me.key, tgt, valid, al, G, gmask);
+    __syncwarp();
 }
 
 // One ray of a beam (map_env.py:566-649); the three rays of a firing agent walk on lanes 0..2 of

@@ -26,7 +26,7 @@ __host__ __device__ constexpr int row_words_min(int RB) {
     return m;
 }
 
-template <int VT, bool SHFL_LUT = false>
+template <int VT>
 __device__ __forceinline__ void render_rows_tma(const uint2* s_view, const uint8_t* tiles, const uint32_t* s_color,
                                                 uint32_t* stage, uint8_t* dst, int total_rows, int debug) {
     constexpr int RB = 3 * VT;            // bytes per view row
@@ -56,7 +56,6 @@ __device__ __forceinline__ void render_rows_tma(const uint2* s_view, const uint8
     uint8_t* gp = img0 + lo0;           // destination, source and size of the next bulk store
     uint32_t sp = stage32 + lo0, nb = CH - lo0;
     uint32_t c0 = 0, c1 = 0, c2 = 0;
-    const uint32_t lane_color = s_color[(4 * lane) % kLutEntries];  // SHFL_LUT: lane L holds the colour of cell code L
 #pragma unroll 1
     for (int c = 0; c < n_chunks; ++c) {
         const int R = min(c * 32 + lane, total_rows - 1);  // lanes past the end redo the last row; their words are never copied out
@@ -66,13 +65,8 @@ __device__ __forceinline__ void render_rows_tma(const uint2* s_view, const uint8
             const uint2 vp = s_view[ga];
             const int si = static_cast<int16_t>(vp.y & 0xffffu), sj = static_cast<int32_t>(vp.y) >> 16;
             const uint8_t* g = tiles + static_cast<int32_t>(vp.x) + i * si;
-            if (SHFL_LUT) {
 #pragma unroll
-                for (int j = 0; j < VT; ++j) X[j] = __shfl_sync(0xffffffffu, lane_color, g[j * sj] >> 2);
-            } else {
-#pragma unroll
-                for (int j = 0; j < VT; ++j) X[j] = cell_color(s_color, g[j * sj]);
-            }
+            for (int j = 0; j < VT; ++j) X[j] = cell_color(s_color, g[j * sj]);
         }
         X[VT] = __shfl_down_sync(0xffffffffu, X[0], 1);
         X[VT + 1] = 0;
@@ -479,13 +473,7 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
             }
             __syncwarp();
             SSD_TICK(8);  // overlay, view parameters
-            if (SSD_SKIP(a.debug, 128))  // experiment: rows leave with LDS.128 / STG.128 pairs instead of bulk stores
-                render_rows<VT>(s_view, tiles, s_color, reinterpret_cast<uint32_t*>(wbase + a.Lf.w_union + a.Lf.u_stage),
-                                a.obs + static_cast<size_t>(we) * a.obs_env, EPW * N * VT);
-            else if (SSD_SKIP(a.debug, 256))  // experiment: colour lookup by warp shuffle
-                render_rows_tma<VT, true>(s_view, tiles, s_color, reinterpret_cast<uint32_t*>(wbase + a.Lf.w_union + a.Lf.u_stage),
-                                          a.obs + static_cast<size_t>(we) * a.obs_env, EPW * N * VT, a.debug);
-            else if (!SSD_SKIP(a.debug, 2))
+            if (!SSD_SKIP(a.debug, 2))
             render_rows_tma<VT>(s_view, tiles, s_color, reinterpret_cast<uint32_t*>(wbase + a.Lf.w_union + a.Lf.u_stage),
                                 a.obs + static_cast<size_t>(we) * a.obs_env, EPW * N * VT, a.debug);
         }
