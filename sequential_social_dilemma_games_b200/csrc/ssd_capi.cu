@@ -147,6 +147,7 @@ void fill_args(SsdEnv* h, ssd::StepArgs& a) {
     a.obs_env = h->obs_env;
     a.G = h->cfg.num_agents <= 8 ? 8 : 16; a.env_begin = 0; a.env_end = h->B;
     a.phases = SSD_PHASE_ALL; a.rotate = 1; a.spawn_stream = ssd::STREAM_SPAWN;
+    a.n_steps = 1; a.ring_slots = 1;
     a.key0 = static_cast<uint32_t>(h->seed); a.key1 = static_cast<uint32_t>(h->seed >> 32); a.t = h->t;
     a.env_id0 = c.env_id_offset;
     a.L = h->L; a.Lf = h->Lf;
@@ -547,10 +548,27 @@ int ssd_rollout(ssd_handle h, int num_steps, const int8_t* actions, uint8_t* obs
     if (check_handle(h)) return SSD_ERR_INVALID;
     if (num_steps < 0 || ring_slots < 1) return fail(SSD_ERR_INVALID, "num_steps must be >= 0 and ring_slots >= 1");
     if (!actions || !obs_ring || !reward_out) return fail(SSD_ERR_INVALID, "actions, obs_ring and reward_out are required");
-    // every step's inputs exist before the first launch: exactly the precondition of chained steps
+    const size_t bn = static_cast<size_t>(h->B) * h->cfg.num_agents, obs_bytes = static_cast<size_t>(h->B) * h->obs_env;
+    if (num_steps == 0) return SSD_OK;
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    {   // A batch of less than half a wave of CTAs, all of it for the specialised kernel: ONE launch in which every warp runs all
+        // the steps of its own envs.  Larger batches gain nothing over chained launches (they are throughput-bound).
+        ssd::StepArgs a;
+        fill_args(h, a);
+        a.actions = actions; a.obs = obs_ring; a.rew = reward_out;
+        a.n_steps = num_steps; a.ring_slots = ring_slots; a.step_stride = bn; a.obs_slot_stride = obs_bytes;
+        if (num_steps > 1 && ssd::specialised_for_all(a, &h->chain, h->threads)) {
+            h->chain.valid = false;
+            CUDA_TRY(ssd::launch_step(a, h->threads, static_cast<cudaStream_t>(stream), &h->chain));
+            h->chain.valid = false;
+            h->launches++;
+            h->t += static_cast<uint32_t>(num_steps);
+            return SSD_OK;
+        }
+    }
+    // otherwise one launch per step; every step's inputs exist before the first launch: exactly the precondition of chained steps
     const bool was_enabled = h->chain.enabled;
     h->chain.enabled = true;
-    const size_t bn = static_cast<size_t>(h->B) * h->cfg.num_agents, obs_bytes = static_cast<size_t>(h->B) * h->obs_env;
     int rc = SSD_OK;
     for (int s = 0; s < num_steps && rc == SSD_OK; ++s)
         rc = ssd_step_phases(h, SSD_PHASE_ALL, actions + s * bn, nullptr, nullptr, obs_ring + (s % ring_slots) * obs_bytes,

@@ -201,6 +201,10 @@ struct StepArgs {
     int dep_wait;         // wait for done[task] == epoch - 1 instead of relying on stream order
     int publish;          // write done[task] = epoch when the task's results are visible
     int pdl_wait;         // launched early behind the previous kernel of the stream: griddepcontrol.wait after the prologue
+    // ---- scripted rollouts (ssd_rollout): n_steps > 1 steps in ONE launch of the specialised kernel; step s reads actions + s *
+    // step_stride, writes rewards + s * step_stride and observations into slot s % ring_slots (obs + slot * obs_slot_stride)
+    int n_steps, ring_slots;
+    size_t step_stride, obs_slot_stride;
     unsigned long long* prof;  // SSD_PROFILING_KNOBS builds with SSD_PROF set: [48] per-phase cycle sums, tick counts, maxima
 };
 
@@ -233,6 +237,8 @@ struct ResetArgs {
 constexpr int kMaxDevices = 64;
 cudaError_t launch_general(const StepArgs& a, int threads, cudaStream_t stream, bool fast_rows);
 cudaError_t launch_step(const StepArgs& a, int threads, cudaStream_t stream, ChainState* chain = nullptr);
+// true when launch_step would send ALL envs of `a` through the wide variant of the specialised kernel (so a.n_steps > 1 is allowed)
+bool specialised_for_all(const StepArgs& a, const ChainState* chain, int threads);
 cudaError_t launch_reset(const ResetArgs& a, cudaStream_t stream);
 cudaError_t launch_pack_state(int kind, int B, int N, int H, int W, int Ws, int env_bytes, const uint8_t* grid_in, const int16_t* pos_in,
                               const uint8_t* ori_in, uint8_t* grid, uint32_t* agents, cudaStream_t stream);

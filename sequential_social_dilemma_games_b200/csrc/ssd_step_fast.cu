@@ -105,8 +105,11 @@ __device__ __forceinline__ void render_rows_tma(const uint2* s_view, const uint8
     bulk_wait_read();  // shared memory must outlive the last bulk read
 }
 
-template <int KIND, bool TAPE, int VT, int G, bool ORCH>
-__global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid_constant__ StepArgs a) {
+// WIDE = false: at most 64 registers, eight CTAs of 128 threads per SM -- the shape for batches that fill the GPU, where the
+// kernel lives on latency hiding.  WIDE = true: 128 registers, four CTAs per SM: without the register squeeze a warp gets
+// through its task about a third faster, which is what counts when the whole batch is less than half a wave of CTAs.
+template <int KIND, bool TAPE, int VT, int G, bool ORCH, bool WIDE>
+__global__ void __launch_bounds__(kMaxThreads, WIDE ? 2 : 4) ssd_step_fast_kernel(const __grid_constant__ StepArgs a) {
     static_assert(!ORCH || KIND == SSD_KIND_HARVEST, "orchard bitmaps are a Harvest structure");
     constexpr int EPW = 32 / G;                                       // envs per warp: 4 (N <= 8) or 2 (N <= 16)
     constexpr uint32_t kSlotLsb = G == 8 ? 0x01010101u : 0x00010001u;  // bit 0 of every env's lane group
@@ -174,9 +177,28 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
             act_in = a.actions[gi];
             if (!a.dep_wait) w_agent = __ldcg(a.agents + gi);
         }
+        FastScratch& S = envs[j];
+        uint8_t* g = tiles + a.pad_bytes + j * tile_pitch;
+        PhiloxKey pk;
+        pk.k0 = a.key0; pk.k1 = a.key1; pk.t = a.t;
+        pk.env = static_cast<uint32_t>(a.env_id0 + static_cast<uint64_t>(e));
+        AgentLane me;
+        me.key = 0x0101; me.ori = 0; me.act = -1; me.rew = 0;
+        // A scripted rollout (ssd_rollout: every step's actions exist up front) runs all its steps in this one launch: the warp
+        // keeps stepping ITS envs -- they never interact with anybody else's -- so there is no launch, no grid-wide drain and no
+        // convoy of warps in the same phase between steps.  The tiles still make the round trip through HBM every step (phase C
+        // paints the overlay into them), ordered by the warp's own bulk-copy groups.
+        const int n_steps = WIDE ? a.n_steps : 1;  // only the wide kernel carries the step loop (launch_fast)
+#pragma unroll 1
+      for (int s = 0; s < n_steps; ++s) {
+        const size_t so = static_cast<size_t>(s) * a.step_stride;  // [B][N] elements per step of actions / rewards
+        if (s > 0) {
+            pk.t = a.t + static_cast<uint32_t>(s);
+            if (valid) act_in = a.actions[so + gi];
+        }
         // ---- load: one TMA bulk copy per env tile; zero the frames while they are in flight
         if (lane == 0) {
-            mbar_init(mbar, 1);
+            if (s == 0) mbar_init(mbar, 1);
             mbar_expect_tx(mbar, static_cast<uint32_t>(EPW) * (a.env_bytes + (ORCH ? 4u * a.orch_stride : 0u)));
             if (a.dep_wait) {  // chained step: the previous step's kernel may still be running; wait for OUR four envs only
                 while (ld_acquire_u32(a.done + we / EPW) != a.epoch - 1) __nanosleep(64);
@@ -185,36 +207,33 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
         __syncwarp();
         if (elect_one()) {  // one lane issues all tile loads: uniform operands, no per-lane replay
             if (a.dep_wait) fence_async_all();  // the predecessor's ordinary stores (acquired above) -> our TMA loads
+            if (s > 0) bulk_wait_all();         // the previous step's write-back of these tiles has landed
 #pragma unroll
             for (int q = 0; q < EPW; ++q)
                 bulk_g2s(tiles + a.pad_bytes + q * tile_pitch, a.grid + static_cast<size_t>(we + q) * a.env_bytes, a.env_bytes, mbar);
             if (ORCH) bulk_g2s(orch_s, a.orch + static_cast<size_t>(we) * a.orch_stride, static_cast<uint32_t>(EPW) * 4u * a.orch_stride, mbar);
         }
-        {
+        if (s == 0) {  // the frames are never written again: rays stop at the walls, windows only read
             const uint4 z = make_uint4(0, 0, 0, 0);
 #pragma unroll
             for (int q = 0; q <= EPW; ++q)
 #pragma unroll 1
                 for (int i = lane * 16; i < a.pad_bytes; i += 512) *reinterpret_cast<uint4*>(tiles + q * tile_pitch + i) = z;
         }
-        FastScratch& S = envs[j];
-        uint8_t* g = tiles + a.pad_bytes + j * tile_pitch;
-        PhiloxKey pk;
-        pk.k0 = a.key0; pk.k1 = a.key1; pk.t = a.t;
-        pk.env = static_cast<uint32_t>(a.env_id0 + static_cast<uint64_t>(e));
-        AgentLane me;
-        me.key = 0x0101; me.ori = 0; me.act = -1; me.rew = 0;
         if (valid) {
-            const uint32_t w = a.dep_wait ? __ldcg(a.agents + gi) : w_agent;  // L2: a chained predecessor may just have written it
-            me.act = (w >> 24) & 1u ? -2 : act_in;  // -2: parked on a wall cell by ssd_set_state, never acts
-            me.key = (w & 255) << 8 | ((w >> 8) & 255);
-            me.ori = (w >> 16) & 3;
+            if (s == 0) {
+                if (a.dep_wait) w_agent = __ldcg(a.agents + gi);  // L2: a chained predecessor may just have written it
+                me.key = (w_agent & 255) << 8 | ((w_agent >> 8) & 255);
+                me.ori = (w_agent >> 16) & 3;
+            }
+            me.act = (w_agent >> 24) & 1u ? -2 : act_in;  // -2: parked on a wall cell by ssd_set_state, never acts
+            me.rew = 0;
             S.order[al] = a.order != nullptr ? a.order[gi] : static_cast<uint8_t>(al);  // action-dict order (NULL: agent order)
             S.rew[al] = 0;
         }
         SSD_TICK(1);  // issue loads, zero frames
         mbar_wait(&s_tab_bar, 0);  // tables landed (long ago, except in the first tasks of a wave)
-        mbar_wait(mbar, 0);  // tiles landed
+        mbar_wait(mbar, static_cast<uint32_t>(s) & 1u);  // tiles landed
         __syncwarp();
         SSD_TICK(2);  // TMA wait
 
@@ -258,7 +277,7 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
         // Cleanup with an explicit action-dict order takes the literal loop further down; everything else walks the rays of ALL
         // firing agents of the warp at once, three lanes per agent, ten agents per round.
         const bool literal_beams = KIND == SSD_KIND_CLEANUP && a.order != nullptr;
-        if (KIND == SSD_KIND_CLEANUP && al == 0) S.hcount = static_cast<int32_t>(__ldcg(a.orch + static_cast<size_t>(e) * a.orch_stride));
+        if (KIND == SSD_KIND_CLEANUP && al == 0 && s == 0) S.hcount = static_cast<int32_t>(__ldcg(a.orch + static_cast<size_t>(e) * a.orch_stride));
         if (KIND != SSD_KIND_PLAIN && !literal_beams && !SSD_SKIP(a.debug, 8)) {
             // update_custom_moves map_env.py:545-552.  'F' beams change no cell, so their order is irrelevant (Harvest has no
             // others).  A CLEAN beam turns the 'H' cell that stops it into 'R' BEFORE the next agent fires (:551-558), so a later
@@ -360,10 +379,11 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
                     harvest_spawn_warp<TAPE, EPW>(a, tiles, tile_pitch, s_apple, static_cast<uint32_t*>(scratch), a.Lf.u_words, we, pk, lane, cnt);
                 }
             } else {
+                PhiloxKey pq = pk;
 #pragma unroll 1
                 for (int q = 0; q < EPW; ++q) {
-                    pk.env = static_cast<uint32_t>(a.env_id0 + static_cast<uint64_t>(we + q));
-                    cleanup_spawn<TAPE>(a, tiles + a.pad_bytes + q * tile_pitch, s_apple, static_cast<uint32_t*>(scratch), we + q, pk, lane, cnt, &envs[q].hcount);
+                    pq.env = static_cast<uint32_t>(a.env_id0 + static_cast<uint64_t>(we + q));
+                    cleanup_spawn<TAPE>(a, tiles + a.pad_bytes + q * tile_pitch, s_apple, static_cast<uint32_t*>(scratch), we + q, pq, lane, cnt, &envs[q].hcount);
                     __syncwarp();
                 }
             }
@@ -475,14 +495,26 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
             SSD_TICK(8);  // overlay, view parameters
             if (!SSD_SKIP(a.debug, 2))
             render_rows_tma<VT>(s_view, tiles, s_color, reinterpret_cast<uint32_t*>(wbase + a.Lf.w_union + a.Lf.u_stage),
-                                a.obs + static_cast<size_t>(we) * a.obs_env, EPW * N * VT, a.debug);
+                                a.obs + static_cast<size_t>(s % a.ring_slots) * a.obs_slot_stride + static_cast<size_t>(we) * a.obs_env, EPW * N * VT, a.debug);
         }
         SSD_TICK(9);  // rows
         if (valid) {  // agent words and rewards last: no ordinary global store is in flight when the row loop fences
-            if (me.act != -2) a.agents[gi] = (me.key >> 8) | (me.key & 255) << 8 | static_cast<uint32_t>(me.ori) << 16;
-            a.rew[gi] = me.rew;
+            if (me.act != -2 && s == n_steps - 1) a.agents[gi] = (me.key >> 8) | (me.key & 255) << 8 | static_cast<uint32_t>(me.ori) << 16;
+            a.rew[so + gi] = me.rew;
         }
-        if (KIND == SSD_KIND_CLEANUP && al == 0) a.orch[static_cast<size_t>(e) * a.orch_stride] = static_cast<uint32_t>(S.hcount);
+        if (KIND == SSD_KIND_CLEANUP && al == 0 && s == n_steps - 1) a.orch[static_cast<size_t>(e) * a.orch_stride] = static_cast<uint32_t>(S.hcount);
+        if (a.stats != nullptr && !SSD_SKIP(a.debug, 32)) {
+            // per-warp totals of ONE step are small (<= 32 agents): two packed reductions carry all seven counters
+            //   r0: steps | eaten << 8 | fires << 16 | hits << 24 (hits <= 3 per shooter)     r1: cleaned | waste << 8 | apples << 12
+            const uint32_t r0 = __reduce_add_sync(0xffffffffu, static_cast<uint32_t>(cnt.steps | cnt.eaten << 8 | cnt.fires << 16 | cnt.hits << 24));
+            const uint32_t r1 = __reduce_add_sync(0xffffffffu, static_cast<uint32_t>(cnt.cleaned | cnt.waste << 8 | cnt.apples << 12));
+            if (lane < 7) {
+                const uint32_t v = lane < 4 ? (r0 >> (8 * lane)) & 255u : (lane == 4 ? r1 & 255u : (lane == 5 ? r1 >> 12 : (r1 >> 8) & 15u));
+                if (v) atomicAdd(&s_cta_stats[lane == 0 ? 0 : lane + 1], static_cast<int>(v));
+            }
+            cnt = Counters{0, 0, 0, 0, 0, 0, 0};
+        }
+      }  // steps of a scripted rollout
         if (a.publish) {  // everything this task wrote (grid, agent words, rewards, observation rows) is visible before the word is
             bulk_wait_all();  // all lanes: only the lane that committed the bulk stores actually waits
             __syncwarp();
@@ -494,16 +526,8 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
     }
 
     SSD_TICK(10);  // agent words, rewards, publish
-    // ---- stats: warp -> CTA -> one set of global atomics per CTA (issued by the last warp to finish)
+    // ---- stats: warp -> CTA (once per step, above) -> one set of global atomics per CTA (issued by the last warp to finish)
     if (a.stats != nullptr && !SSD_SKIP(a.debug, 32)) {
-        // per-warp totals are small (<= 32 agents): two packed reductions carry all seven counters
-        //   r0: steps | eaten << 8 | fires << 16 | hits << 24 (hits <= 3 per shooter)     r1: cleaned | waste << 8 | apples << 12
-        const uint32_t r0 = __reduce_add_sync(0xffffffffu, static_cast<uint32_t>(cnt.steps | cnt.eaten << 8 | cnt.fires << 16 | cnt.hits << 24));
-        const uint32_t r1 = __reduce_add_sync(0xffffffffu, static_cast<uint32_t>(cnt.cleaned | cnt.waste << 8 | cnt.apples << 12));
-        if (lane < 7) {
-            const uint32_t v = lane < 4 ? (r0 >> (8 * lane)) & 255u : (lane == 4 ? r1 & 255u : (lane == 5 ? r1 >> 12 : (r1 >> 8) & 15u));
-            if (v) atomicAdd(&s_cta_stats[lane == 0 ? 0 : lane + 1], static_cast<int>(v));
-        }
         __syncwarp();
         int last = 0;
         if (lane == 0) { __threadfence_block(); last = (atomicAdd(&s_done, 1) == nwarps - 1); }
@@ -517,14 +541,14 @@ __global__ void __launch_bounds__(kMaxThreads) ssd_step_fast_kernel(const __grid
 }
 
 // ====================================================================== launchers
-template <int KIND, bool TAPE, int G, bool ORCH = false>
-static cudaError_t launch_fast(const StepArgs& a, int threads, cudaStream_t stream) {
+template <int KIND, bool TAPE, int G, bool ORCH, bool WIDE>
+static cudaError_t launch_fast_w(const StepArgs& a, int threads, cudaStream_t stream) {
     const int envs_per_cta = (threads / 32) * (32 / G);
     const int ctas = (a.env_end - a.env_begin + envs_per_cta - 1) / envs_per_cta;
     if (ctas <= 0) return cudaSuccess;
 #define SSD_LAUNCH_FAST(VT_)                                                                                    \
     do {                                                                                                        \
-        auto kern = ssd_step_fast_kernel<KIND, TAPE, VT_, G, ORCH>;                                                      \
+        auto kern = ssd_step_fast_kernel<KIND, TAPE, VT_, G, ORCH, WIDE>;                                                      \
         static uint32_t smem_set[kMaxDevices] = {};  /* the attribute is per device */                          \
         int dev_ = 0;                                                                                           \
         cudaGetDevice(&dev_);                                                                                   \
@@ -551,15 +575,45 @@ static cudaError_t launch_fast(const StepArgs& a, int threads, cudaStream_t stre
 }
 
 
-cudaError_t launch_step(const StepArgs& a, int threads, cudaStream_t stream, ChainState* chain) {
-    // the packed row renderers need every warp's slab of 32/G envs to start 4-byte aligned
-    const bool fast_rows = (((32 / a.G) * a.obs_env) % 4 == 0) && (reinterpret_cast<uintptr_t>(a.obs) % 4 == 0);
-    const bool tape = a.tape_u != nullptr || a.tape_move != nullptr;
-    // a production step: everything the specialised kernel assumes (see ssd_step_fast_kernel)
+// the packed row renderers need every warp's slab of 32/G envs to start 4-byte aligned
+static bool packed_rows_ok(const StepArgs& a) {
+    return (((32 / a.G) * a.obs_env) % 4 == 0) && (reinterpret_cast<uintptr_t>(a.obs) % 4 == 0) && (a.obs_slot_stride % 4 == 0);
+}
+// a production step: everything the specialised kernel assumes (see ssd_step_fast_kernel)
+static bool production_step(const StepArgs& a, const ChainState* chain) {
     static const bool no_fast = knob("SSD_NO_FAST") != nullptr;
-    const bool full = !no_fast && !(chain && chain->general_only) && a.phases == SSD_PHASE_ALL && a.mask == nullptr && a.rows == nullptr && !a.use_beam_buf &&
-                      !a.rew_accumulate && a.obs != nullptr && a.rew != nullptr && a.actions != nullptr && fast_rows &&
-                      (a.V == 11 || a.V == 15 || a.V == 21) && a.env_begin % (32 / a.G) == 0;
+    return !no_fast && !(chain && chain->general_only) && a.phases == SSD_PHASE_ALL && a.mask == nullptr && a.rows == nullptr && !a.use_beam_buf &&
+           !a.rew_accumulate && a.obs != nullptr && a.rew != nullptr && a.actions != nullptr && packed_rows_ok(a) &&
+           (a.V == 11 || a.V == 15 || a.V == 21) && a.env_begin % (32 / a.G) == 0;
+}
+// ... and through its wide variant, the one with the step loop: the whole grid resident at four CTAs per SM (launch_fast)
+bool specialised_for_all(const StepArgs& a, const ChainState* chain, int threads) {
+    const int envs_per_cta = (threads / 32) * (32 / a.G);
+    const int ctas = (a.env_end - a.env_begin + envs_per_cta - 1) / envs_per_cta;
+    const int cta_slots = chain && chain->cta_slots > 0 ? chain->cta_slots : 148 * 8;
+    static const bool no_wide = knob("SSD_NO_WIDE") != nullptr;
+    return production_step(a, chain) && (a.env_end - a.env_begin) % (32 / a.G) == 0 && a.tape_u == nullptr && a.tape_move == nullptr &&
+           threads <= 128 && 2 * ctas <= cta_slots && !no_wide;
+}
+
+// The wide-register kernel when the whole grid is resident at four CTAs per SM anyway (and never for tape replays: parity runs
+// need no second set of kernels).
+template <int KIND, bool TAPE, int G, bool ORCH = false>
+static cudaError_t launch_fast(const StepArgs& a, int threads, cudaStream_t stream, int cta_slots) {
+    const int envs_per_cta = (threads / 32) * (32 / G);
+    const int ctas = (a.env_end - a.env_begin + envs_per_cta - 1) / envs_per_cta;
+    static const bool no_wide = knob("SSD_NO_WIDE") != nullptr;
+    if constexpr (!TAPE) {
+        if (threads <= 128 && 2 * ctas <= cta_slots && !no_wide) return launch_fast_w<KIND, TAPE, G, ORCH, true>(a, threads, stream);
+    }
+    return launch_fast_w<KIND, TAPE, G, ORCH, false>(a, threads, stream);
+}
+
+cudaError_t launch_step(const StepArgs& a, int threads, cudaStream_t stream, ChainState* chain) {
+    const bool fast_rows = packed_rows_ok(a);
+    const bool tape = a.tape_u != nullptr || a.tape_move != nullptr;
+    const bool full = production_step(a, chain);
+    if (a.n_steps != 1 && !specialised_for_all(a, chain, threads)) return cudaErrorInvalidValue;  // ssd_rollout checks before it asks
     if (!full) {
         if (chain) chain->valid = false;
         return launch_general(a, threads, stream, fast_rows);
@@ -572,7 +626,7 @@ cudaError_t launch_step(const StepArgs& a, int threads, cudaStream_t stream, Cha
     // wave has no tail to hide and very long grids amortise it anyway, while the completion words cost a little
     // (profiles/r01h_sweep.md): chain between 1.5 and 12 waves.
     bool chain_here = false;
-    if (chain && chain->enabled && chain->done != nullptr) {
+    if (chain && chain->enabled && chain->done != nullptr && a.n_steps == 1) {
         const int slots = chain->cta_slots > 0 ? chain->cta_slots : 148 * 8;  // resident CTAs of this handle's GPU (8 per SM on B200)
         const int ctas = (f.env_end - f.env_begin + (threads / 32) * epw - 1) / ((threads / 32) * epw);
         chain_here = 2 * ctas >= 3 * slots && ctas <= 12 * slots;
@@ -594,14 +648,15 @@ cudaError_t launch_step(const StepArgs& a, int threads, cudaStream_t stream, Cha
     static const bool no_pdl = knob("SSD_NO_PDL") != nullptr;  // experiments
     f.pdl_wait = !f.dep_wait && !no_pdl;
     cudaError_t e = cudaSuccess;
+    const int cta_slots = chain && chain->cta_slots > 0 ? chain->cta_slots : 148 * 8;
 #define SSD_FAST(KIND_)                                                                                                     \
-    e = a.G == 8 ? (tape ? launch_fast<KIND_, true, 8>(f, threads, stream) : launch_fast<KIND_, false, 8>(f, threads, stream)) \
-                 : (tape ? launch_fast<KIND_, true, 16>(f, threads, stream) : launch_fast<KIND_, false, 16>(f, threads, stream))
+    e = a.G == 8 ? (tape ? launch_fast<KIND_, true, 8>(f, threads, stream, cta_slots) : launch_fast<KIND_, false, 8>(f, threads, stream, cta_slots)) \
+                 : (tape ? launch_fast<KIND_, true, 16>(f, threads, stream, cta_slots) : launch_fast<KIND_, false, 16>(f, threads, stream, cta_slots))
     switch (a.kind) {
         case SSD_KIND_HARVEST:
             if (a.use_orch) {
-                e = a.G == 8 ? (tape ? launch_fast<SSD_KIND_HARVEST, true, 8, true>(f, threads, stream) : launch_fast<SSD_KIND_HARVEST, false, 8, true>(f, threads, stream))
-                             : (tape ? launch_fast<SSD_KIND_HARVEST, true, 16, true>(f, threads, stream) : launch_fast<SSD_KIND_HARVEST, false, 16, true>(f, threads, stream));
+                e = a.G == 8 ? (tape ? launch_fast<SSD_KIND_HARVEST, true, 8, true>(f, threads, stream, cta_slots) : launch_fast<SSD_KIND_HARVEST, false, 8, true>(f, threads, stream, cta_slots))
+                             : (tape ? launch_fast<SSD_KIND_HARVEST, true, 16, true>(f, threads, stream, cta_slots) : launch_fast<SSD_KIND_HARVEST, false, 16, true>(f, threads, stream, cta_slots));
             } else {
                 SSD_FAST(SSD_KIND_HARVEST);
             }

@@ -317,22 +317,35 @@ def test_checkpoint_resume(game):
     assert all(torch.equal(x, y) for x, y in zip(a.get_state(), b.get_state()))
 
 
-def test_rollout_equals_steps():
-    """ssd_rollout (T chained steps in one call, observation ring) == T calls of ssd_step."""
+@pytest.mark.parametrize("game,B,N", [("harvest", 32768, 5), ("cleanup", 8192, 5), ("harvest", 516, 5), ("harvest", 1030, 5), ("cleanup", 2048, 10)])
+def test_rollout_equals_steps(game, B, N):
+    """ssd_rollout == T calls of ssd_step: rewards of every step, the observation ring, the final state, statistics and step
+    counter.  A batch of less than half a wave of CTAs that goes through the specialised kernel entirely is ONE launch in which
+    every warp runs all T steps of its envs; 32 768 envs (throughput-bound anyway) and 1030 envs (a tail for the general kernel)
+    are one chained launch per step.  Two rollouts in a row continue the same trajectories."""
     from sequential_social_dilemma_games_b200.batched import make_config
-    cfg = make_config("harvest")
-    B, T, R = 32768, 24, 3
+    from sequential_social_dilemma_games_b200.maps import CLEANUP_MAP, tile_map
+    cfg = make_config(game, num_agents=N, ascii_map=tile_map(CLEANUP_MAP) if N == 10 else None)
+    T, R = 24, 3
     g = torch.Generator(device="cuda").manual_seed(8)
-    acts = torch.randint(0, cfg.num_actions, (T, B, cfg.num_agents), generator=g, device="cuda", dtype=torch.int8)
+    acts = torch.randint(0, cfg.num_actions, (2 * T, B, cfg.num_agents), generator=g, device="cuda", dtype=torch.int8)
+    if game == "cleanup":
+        acts[torch.rand(acts.shape, generator=g, device="cuda") < 0.3] = 8   # clean below the depletion threshold: spawning runs
     a, b = _env(cfg, B, seed=12), _env(cfg, B, seed=12)
     a.reset(); b.reset()
-    ring, rews = a.rollout(acts, obs_ring=torch.empty((R,) + tuple(a.obs_shape), dtype=torch.uint8, device="cuda"))
-    for t in range(T):
-        obs, rew = b.step(acts[t])
-        assert torch.equal(rew, rews[t]), t
-        if t >= T - R:
-            assert torch.equal(obs, ring[t % R]), t
-    assert all(torch.equal(x, y) for x, y in zip(a.get_state(), b.get_state())) and a.stats() == b.stats() and a.t == b.t
+    for half in range(2):
+        n0 = a.launch_count
+        ring, rews = a.rollout(acts[half * T:(half + 1) * T], obs_ring=torch.empty((R,) + tuple(a.obs_shape), dtype=torch.uint8, device="cuda"))
+        assert a.launch_count - n0 == (1 if B in (8192, 516, 2048) else T)
+        for t in range(T):
+            obs, rew = b.step(acts[half * T + t])
+            assert torch.equal(rew, rews[t]), (half, t)
+            if t >= T - R:
+                assert torch.equal(obs, ring[t % R]), (half, t)
+        assert all(torch.equal(x, y) for x, y in zip(a.get_state(), b.get_state())) and a.stats() == b.stats() and a.t == b.t
+    obs_a, rew_a = a.step(acts[0])      # an ordinary step after a rollout
+    obs_b, rew_b = b.step(acts[0])
+    assert torch.equal(obs_a, obs_b) and torch.equal(rew_a, rew_b)
 
 
 @pytest.mark.parametrize("B", [32768, 32770])
