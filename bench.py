@@ -12,7 +12,7 @@ global env id).  Prints ONE JSON line (rank 0).
 
 `value` times K steps of BatchedSSDEnv.step with consecutive steps chained (SSD_OPT_CHAIN_STEPS: programmatic dependent
 launch; the actions are pre-generated, which is the option's precondition); `stream_ordered` is the same K steps
-without chaining (what a policy in the loop gets); `e2e` goes through ssd_step_host with pinned host buffers (H2D actions,
+without chaining (what a policy in the loop gets); `rollout` (configs only) is ssd_rollout, one C call for T scripted steps; `e2e` goes through ssd_step_host with pinned host buffers (H2D actions,
 D2H observations + rewards inside the timed region) next to a measured host-copy roof; `configs` carries the other
 BASELINE.json configurations (Cleanup, the tiled 10-agent stress map, the strong split of 65 536 envs over the GPUs);
 `cpu_baseline` / `--impl reference` time the C port of the reference's step on the host cores, and
@@ -280,23 +280,43 @@ def run_ours(args, rank, world, local_rank):
             return ms, max_ranks(ms)
 
         def measure(self, steps, warmup, chain=True):
-            """stream-ordered and chained timings of `steps` steps -> dict for the JSON line."""
-            for _ in range(warmup):
-                self.one_step()
+            """stream-ordered, chained and ssd_rollout timings -> dict for the JSON line.  Every mode starts from a fresh episode
+            (reset + `warmup` steps), so that all of them see the same stretch of it: Cleanup gets slower as waste is cleaned."""
+            def fresh():
+                self.n = 0
+                for _ in range(warmup):
+                    self.one_step()
+            fresh()
             _, ms_plain = self.timed(steps)
             out = {"stream_ordered": {"ms_per_step": ms_plain / steps}}
-            ms_own = ms_max = None
             if chain:
                 self.env.chain_steps(True)
-                for _ in range(min(warmup, 20)):
-                    self.one_step()
-                l0 = self.env.launch_count
-                ms_own, ms_max = self.timed(steps)
-                out["launches"] = self.env.launch_count - l0
+                fresh()
+                _, ms_max = self.timed(steps)
                 self.env.chain_steps(False)
                 out["chained"] = {"ms_per_step": ms_max / steps}
-            out["_own_ms"], out["_max_ms"], out["_plain_ms"] = ms_own, ms_max, ms_plain
+                fresh()
+                out["rollout"] = self.rollout_ms(min(steps, 100))
             return out
+
+        def rollout_ms(self, T):
+            """ssd_rollout: T steps whose actions all exist up front, one C call (one launch of the wide kernel for batches below
+            half a wave of CTAs, chained launches otherwise).  No episode reset inside (T <= 100)."""
+            acts = self.ring.repeat((T + 15) // 16, 1, 1)[:T].contiguous()
+            ring = self.obs.unsqueeze(0)
+            rews = torch.empty((T, self.B, self.N), dtype=torch.int32, device=dev)
+            self.env.rollout(acts[:8], ring, rews[:8])
+            l0 = self.env.launch_count
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            e0.record()
+            self.env.rollout(acts, ring, rews)
+            e1.record()
+            barrier()
+            ms = max_ranks(e0.elapsed_time(e1))
+            self.n += T + 8
+            return {"ms_per_step": ms / T, "steps": T,
+                    "launches": "one launch for all steps (wide kernel)" if self.env.launch_count - l0 == 1 else "one chained launch per step"}
 
         def close(self):
             self.env.close()
@@ -443,12 +463,14 @@ def run_ours(args, rank, world, local_rank):
                 a_bytes = r.env.algorithmic_bytes_per_env_step
                 entry = {"name": name, "game": game, "num_agents": n_ag, "envs_per_gpu": b_rank, "envs_total": b_total, "scaling": scaling,
                          "steps": args.config_steps, "algorithmic_bytes_per_env_step": a_bytes}
-                for k in ("stream_ordered", "chained"):
+                for k in ("stream_ordered", "chained", "rollout"):
                     if k in m:
                         ms_k = m[k]["ms_per_step"]
                         gbs = a_bytes * b_rank / (ms_k * 1e-3) / 1e9
                         entry[k] = {"ms_per_step": ms_k, "value": b_total * n_ag / (ms_k * 1e-3), "unit": UNIT,
                                     "roofline_frac_per_gpu": gbs / peak, "achieved_gbs_per_gpu": gbs}
+                        if k == "rollout":
+                            entry[k]["launches"] = m[k]["launches"]
                 configs.append(entry)
                 r.close()
                 del r
