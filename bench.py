@@ -47,7 +47,7 @@ def parse_args():
     ap.add_argument("--view", type=int, default=7)
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--cpu-sample-envs", type=int, default=8192)
-    ap.add_argument("--config-steps", type=int, default=300, help="timed steps of every entry of the `configs` array")
+    ap.add_argument("--config-steps", type=int, default=1000, help="timed steps of every entry of the `configs` array")
     ap.add_argument("--pyref-steps", type=int, default=1000, help="steps of the Python reference per process (BASELINE.md section 4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -296,12 +296,12 @@ def run_ours(args, rank, world, local_rank):
                 self.env.chain_steps(False)
                 out["chained"] = {"ms_per_step": ms_max / steps}
                 fresh()
-                out["rollout"] = self.rollout_ms(min(steps, 100))
+                out["rollout"] = self.rollout_ms(min(steps, 400))
             return out
 
         def rollout_ms(self, T):
             """ssd_rollout: T steps whose actions all exist up front, one C call (one launch of the wide kernel for batches below
-            half a wave of CTAs, chained launches otherwise).  No episode reset inside (T <= 100)."""
+            half a wave of CTAs, chained launches otherwise).  No episode reset inside (T <= 400)."""
             acts = self.ring.repeat((T + 15) // 16, 1, 1)[:T].contiguous()
             ring = self.obs.unsqueeze(0)
             rews = torch.empty((T, self.B, self.N), dtype=torch.int32, device=dev)

@@ -214,7 +214,27 @@ int ssd_create(const SsdConfig* cfg, ssd_handle* out) {
     h->cfg = *cfg;
     h->distinct_spawn = distinct_spawn;
     h->B = cfg->num_envs; h->HW = H * W;
-    h->Ws = W + cfg->view_radius;  // r zero bytes after the W cells of every row
+    // Row stride of the grid: at least r zero bytes after the W cells of every row (the right-hand padding of return_view), and
+    // such that the 2r+1 rows of one egocentric window start in 2r+1 different shared-memory banks whatever the window's
+    // alignment -- the lanes of the row renderer read one window row each (Harvest: 38 + 7 = 45 already is; Cleanup: 25 -> 27).
+    h->Ws = W + cfg->view_radius;
+    {
+        const int V = 2 * cfg->view_radius + 1;
+        auto conflict_free = [V](int ws) {
+            if (V > 32) return true;
+            for (int a0 = 0; a0 < 4; ++a0) {
+                uint32_t seen = 0;
+                for (int i = 0; i < V; ++i) {
+                    const uint32_t bank = 1u << (((a0 + ws * i) >> 2) & 31);
+                    if (seen & bank) return false;
+                    seen |= bank;
+                }
+            }
+            return true;
+        };
+        for (int extra = 0; extra < 16 && !conflict_free(h->Ws); ++extra) ++h->Ws;
+        if (!conflict_free(h->Ws)) h->Ws = W + cfg->view_radius;
+    }
     h->env_bytes = static_cast<int>(up16(H * h->Ws));
     h->pad_bytes = static_cast<int>(up16(cfg->view_radius * h->Ws + cfg->view_radius));
     h->V = 2 * cfg->view_radius + 1; h->obs_env = N * h->V * h->V * 3;

@@ -442,7 +442,14 @@ __global__ void __launch_bounds__(kMaxThreads, WIDE ? 2 : 4) ssd_step_fast_kerne
                 for (int f0 = 0; f0 < nf; f0 += 10)
                     if (lane < 30 && f0 + ray_f < nf) paint(fire_list[f0 + ray_f], ray_s, false);
                 __syncwarp();
+                // (only where some env of the warp has both kinds of beam: bit 25 of an entry marks a CLEAN beam)
+                bool mixed = false;
                 if (KIND == SSD_KIND_CLEANUP) {
+                    const uint32_t cmask = __ballot_sync(0xffffffffu, ((fmask >> lane) & 1u) && ((fire_ent >> 25) & 1u));
+                    const uint32_t grp = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << gbase;
+                    mixed = __any_sync(0xffffffffu, (cmask & grp) != 0u && (fmask & ~cmask & grp) != 0u);
+                }
+                if (KIND == SSD_KIND_CLEANUP && mixed) {
                     bool lost = false;
 #pragma unroll 1
                     for (int f0 = 0; f0 < nf; f0 += 10)
