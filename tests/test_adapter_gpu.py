@@ -112,3 +112,21 @@ def test_vector_env_against_oracle(game):
     fresh = venv.engine.render(rotate=False).cpu().numpy()
     assert all(np.array_equal(o2['agent-%d' % i]["curr_obs"], lut[fresh[2, i]]) for i in range(N))
     venv.close()
+
+
+@pytest.mark.parametrize("env_name,render_type", [("harvest", "fast"), ("cleanup", "pretty")])
+def test_rollout_controller_writes_a_video(tmp_path, env_name, render_type):
+    """SURVEY 8f-4 tooling: the reference's rollout.Controller (rollout.py:30-110) on the batched engine -- frames from
+    ssd_render_map, video through OpenCV.  The frames are the full map with the agents painted: agent-0's colour is in it."""
+    cv2 = pytest.importorskip("cv2")
+    from sequential_social_dilemma_games_b200.rollout import Controller
+    c = Controller(env_name=env_name, num_envs=3, film=1, seed=4)
+    rewards, observations, full_obs = c.rollout(horizon=4)
+    assert len(rewards) == len(observations) == len(full_obs) == 4
+    assert full_obs[0].shape == (c.cfg.height, c.cfg.width, 3) and full_obs[0].dtype == np.uint8
+    assert observations[0].shape == (15, 15, 3) and observations[0].dtype == np.float64 and np.abs(observations[0]).max() <= 0.502
+    assert (full_obs[-1] == np.array([159, 67, 255], np.uint8)).all(-1).sum() == 1     # agent-0 ('1'), map_env.py:31
+    path = c.render_rollout(horizon=5, path=str(tmp_path), render_type=render_type, fps=8)
+    assert path.endswith(env_name + "_trajectory.mp4")
+    assert int(cv2.VideoCapture(path).get(cv2.CAP_PROP_FRAME_COUNT)) == 5
+    c.close()

@@ -149,3 +149,22 @@ def test_policy_ref_hand_vector():
     fc_in = want.reshape(-1)                      # keras Flatten order (row, col, filter)
     got = policy_ref.features(dict(w2, fc1_w=np.eye(1014)[:, :32] * 1.0, fc2_w=np.eye(32)), ob)
     assert np.allclose(got[0], fc_in[:32], rtol=0, atol=1e-15)
+
+
+def test_video_helpers(tmp_path):
+    """The frame -> file half of the rollout tool (utility_funcs.py:8-56) needs no GPU: PNG frames and an mp4 whose frame
+    count and first pixel survive the round trip through OpenCV."""
+    cv2 = pytest.importorskip("cv2")
+    from sequential_social_dilemma_games_b200 import video
+    frames = [np.full((16, 38, 3), 40 * i, np.uint8) for i in range(6)]
+    path = video.make_video_from_rgb_imgs(frames, str(tmp_path), video_name="t", fps=8)
+    cap = cv2.VideoCapture(path)
+    assert int(cap.get(cv2.CAP_PROP_FRAME_COUNT)) == 6 and int(cap.get(cv2.CAP_PROP_FRAME_WIDTH)) == 640
+    img_dir = tmp_path / "frames"
+    img_dir.mkdir()
+    for i, f in enumerate(frames):
+        video.save_img(f, str(img_dir), "frame%06d.png" % i)
+    back = cv2.imread(str(img_dir / "frame000003.png"))
+    assert back.shape == (16 * 16, 38 * 16, 3) and int(back[0, 0, 0]) == 120
+    path2 = video.make_video_from_image_dir(str(tmp_path), str(img_dir), video_name="u", fps=5)
+    assert int(cv2.VideoCapture(path2).get(cv2.CAP_PROP_FRAME_COUNT)) == 6
