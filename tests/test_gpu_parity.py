@@ -509,3 +509,48 @@ def test_edge_cases():
         e2.step(a, reward_out=r2, render=False, phases=_lib.PHASE_BEAMS)
         o2, _ = e2.step(a, reward_out=r2, phases=_lib.PHASE_SPAWN | _lib.PHASE_RENDER)
         assert torch.equal(o1, o2) and torch.equal(r1, r2), t
+
+
+@pytest.mark.parametrize("game,N,view,B", [("harvest", 1, 7, 64), ("harvest", 3, 5, 256), ("harvest", 8, 10, 128), ("harvest", 9, 7, 130),
+                                           ("harvest", 16, 7, 64), ("cleanup", 1, 5, 64), ("cleanup", 8, 7, 256), ("cleanup", 16, 10, 62),
+                                           ("plain", 4, 7, 64)])
+def test_specialised_equals_general_kernel(game, N, view, B):
+    """The two step kernels share their device functions but not their data structures: the specialised one scans orchard
+    bitmaps, keeps a running 'H' count, probes all beams at once and (for these batch sizes) runs in its wide-register
+    shape; the general one scans apple points byte by byte, recounts, and fires agent by agent.  Same seeds, same actions:
+    identical states, rewards, observations and statistics, for agent counts on both sides of the 8 / 16 lanes-per-env
+    split, all three packed view sizes and a map without a game (MapEnv alone).  A scripted rollout in the middle runs as
+    one launch where the batch is whole warps."""
+    from sequential_social_dilemma_games_b200.config import EnvConfig, KIND_PLAIN, make_config
+    from sequential_social_dilemma_games_b200.maps import CLEANUP_MAP, HARVEST_MAP, tile_map
+    if game == "plain":
+        cfg = EnvConfig(KIND_PLAIN, HARVEST_MAP, N, view_size=view)
+    else:
+        amap = tile_map(CLEANUP_MAP) if (game == "cleanup" and N > 8) else None   # the default Cleanup map has 10 spawn points
+        cfg = make_config(game, num_agents=N, view_size=view, ascii_map=amap)
+    a, b = _env(cfg, B, seed=21, env_id_offset=9), _env(cfg, B, seed=21, env_id_offset=9).general_kernel_only(True)
+    oa, ob = a.reset(), b.reset()
+    assert torch.equal(oa, ob)
+    rng = np.random.RandomState(N * 100 + view)
+    T = 40
+    acts = rng.randint(cfg.num_actions, size=(T, B, N)).astype(np.int8)
+    if game == "cleanup":
+        acts[rng.rand(T, B, N) < 0.35] = 8
+    acts[rng.rand(T, B, N) < 0.05] = -1          # absent agents
+    for t in range(T):
+        if t == 20:
+            dev = torch.from_numpy(acts[20:28]).cuda()
+            ring, rews = a.rollout(dev)
+            for k in range(8):
+                ob, rb = b.step(acts[20 + k])
+                assert torch.equal(rews[k], rb), (t, k)
+            assert torch.equal(ring[0], ob)
+            continue
+        if 20 < t < 28:
+            continue
+        oa, ra = a.step(acts[t])
+        ob, rb = b.step(acts[t])
+        assert torch.equal(ra, rb), t
+        assert torch.equal(oa, ob), t
+    assert all(torch.equal(x, y) for x, y in zip(a.get_state(), b.get_state()))
+    assert a.stats() == b.stats() and a.t == b.t
