@@ -52,6 +52,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-configs", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the batch-size x view-radius sweep (BASELINE.json configs[4])")
+    ap.add_argument("--sweep-steps", type=int, default=60)
     ap.add_argument("--no-chain", action="store_true", help="stream-ordered steps only (no programmatic dependent launch)")
     return ap.parse_args()
 
@@ -477,6 +479,28 @@ def run_ours(args, rank, world, local_rank):
             except Exception as exc:  # noqa: BLE001
                 configs.append({"name": name, "unavailable": repr(exc)[:200]})
 
+    # ------------------------------------------------------------------ BASELINE.json configs[4]: batch size x view radius (informational)
+    sweep = []
+    if not args.no_sweep:
+        for r_view in (5, 7, 10):
+            for b_rank in (1024, 16384, 262144, 1048576):
+                try:
+                    c = make_config("harvest", num_agents=5, view_size=r_view)
+                    r = Run(c, b_rank, rank * b_rank)
+                    for _ in range(20):
+                        r.one_step()
+                    _, ms_sw = r.timed(args.sweep_steps)
+                    ms_sw /= args.sweep_steps
+                    a_bytes = r.env.algorithmic_bytes_per_env_step
+                    sweep.append({"envs_per_gpu": b_rank, "view_radius": r_view, "ms_per_step": ms_sw,
+                                  "value": world * b_rank * 5 / (ms_sw * 1e-3),
+                                  "roofline_frac_per_gpu": a_bytes * b_rank / (ms_sw * 1e-3) / 1e9 / peak})
+                    r.close()
+                    del r
+                    torch.cuda.empty_cache()
+                except Exception as exc:  # noqa: BLE001
+                    sweep.append({"envs_per_gpu": b_rank, "view_radius": r_view, "unavailable": repr(exc)[:160]})
+
     if rank == 0:
         kernel_ms = ms / args.steps  # this rank's average step-kernel launch (one launch per step)
         achieved = alg * B / (kernel_ms * 1e-3) / 1e9
@@ -506,6 +530,10 @@ def run_ours(args, rank, world, local_rank):
                 "totals": {"env_steps": int(tot[0]), "reward_sum": int(tot[1]), "apples_eaten": int(tot[2]), "hits": int(tot[3])}}
         if configs:
             line["configs"] = configs
+        if sweep:
+            line["sweep"] = {"what": "BASELINE.json configs[4]: HarvestEnv 5 agents, stream-ordered steps, envs per GPU x view radius, "
+                                     "%d timed steps each; value = all GPUs together (weak scaling)" % args.sweep_steps,
+                             "unit": UNIT, "rows": sweep}
         if on_device is not None:
             line["on_device_loop"] = on_device
         if world == 1 and not args.no_cpu_baseline:
