@@ -33,6 +33,9 @@ if ROOT not in sys.path:
 METRIC = "harvest_agent_steps_per_sec_obs_incl"
 UNIT = "agent-steps/s"
 HORIZON = 1000  # RLlib "horizon" of the reference's training configs (train_baseline.py:131)
+BURN_IN = 100   # untimed steps between a reset and the first timed step: right after reset() the agents still stand crowded
+                # around the spawn points (move conflicts in most envs) and the orchard is full, which is not what the other
+                # 900 steps of an episode look like; a short timed region would otherwise sample only that stretch
 
 
 def parse_args():
@@ -66,6 +69,7 @@ def workload(args):
             "game": args.game, "num_agents": args.agents, "envs_per_gpu": args.envs_per_gpu,
             "view_radius": args.view, "rng": "philox4x32-10 (production mode)",
             "actions": "pre-generated on device, ring of 16 x [B,N] int8",
+            "episode": "reset every %d steps; timed regions start at least %d untimed steps after a reset (W warm-up steps included)" % (HORIZON, BURN_IN),
             "l2": "per-step working set (state r/w + obs write) is %.0f MB > 126 MB L2; no explicit flush"
                   % ((2 * 608 + 3 * args.agents * (2 * args.view + 1) ** 2) * args.envs_per_gpu / 1e6),
             "parallelism": "env-sharded x%d" % args.gpus}
@@ -328,7 +332,7 @@ def run_ours(args, rank, world, local_rank):
     B, N = args.envs_per_gpu, cfg.num_agents
     run = Run(cfg, B, rank * B)
     env = run.env
-    for _ in range(args.warmup):
+    for _ in range(max(args.warmup, BURN_IN)):
         run.one_step()
     with ClockSampler(local_rank) as clk:  # clocks and throttle reasons over both timed regions
         # stream-ordered steps first (every kernel waits for the previous one to drain) ...

@@ -112,7 +112,6 @@ template <int KIND, bool TAPE, int VT, int G, bool ORCH, bool WIDE>
 __global__ void __launch_bounds__(kMaxThreads, WIDE ? 2 : 4) ssd_step_fast_kernel(const __grid_constant__ StepArgs a) {
     static_assert(!ORCH || KIND == SSD_KIND_HARVEST, "orchard bitmaps are a Harvest structure");
     constexpr int EPW = 32 / G;                                       // envs per warp: 4 (N <= 8) or 2 (N <= 16)
-    constexpr uint32_t kSlotLsb = G == 8 ? 0x01010101u : 0x00010001u;  // bit 0 of every env's lane group
     using FastScratch = FastScratchT<G>;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(16) uint32_t s_color[kLutEntries];
@@ -195,6 +194,7 @@ __global__ void __launch_bounds__(kMaxThreads, WIDE ? 2 : 4) ssd_step_fast_kerne
         if (s > 0) {
             pk.t = a.t + static_cast<uint32_t>(s);
             if (valid) act_in = a.actions[so + gi];
+            fence_async_smem();  // the overlay this warp painted into the tiles (generic proxy) before the copy engine overwrites them
         }
         // ---- load: one TMA bulk copy per env tile; zero the frames while they are in flight
         if (lane == 0) {
