@@ -48,10 +48,8 @@ __device__ __forceinline__ void render_rows_tma(const uint2* s_view, const uint8
     const int hi_last = min(CH, end_last & ~15);
     uint8_t* const img0 = dst - mis;  // 16-byte aligned image of chunk 0
     const uint32_t stage32 = smem_u32(stage);
-    // where lane 31 parks the words that spill over a chunk: the head of the next image, or a dummy slot
-    uint32_t* const k1 = stage + (mis4 >= 1 ? mis4 - 1 : CH / 4 + 5);
-    uint32_t* const k2 = stage + (mis4 >= 2 ? mis4 - 2 : CH / 4 + 6);
-    uint32_t* const k3 = stage + (mis4 >= 3 ? mis4 - 3 : CH / 4 + 7);
+    // lane 31 parks the mis4 words that spill over a chunk at the head of the next image (mis4 is warp-uniform: a slab that
+    // starts 16-byte aligned spills nothing and stores nothing)
     const int lo0 = mis != 0 ? 16 : 0;  // the first 16 - mis bytes of the slab leave with plain stores
     uint8_t* gp = img0 + lo0;           // destination, source and size of the next bulk store
     uint32_t sp = stage32 + lo0, nb = CH - lo0;
@@ -85,7 +83,11 @@ __device__ __forceinline__ void render_rows_tma(const uint2* s_view, const uint8
 #pragma unroll
         for (int m = 0; m < MMIN; ++m) st[m] = Q[m];
         if (extra) st[MMIN] = Q[MMIN];
-        if (lane == 31) { *k1 = c2; *k2 = c1; *k3 = c0; }  // head of this image = spill of the previous chunk (unused for c == 0)
+        if (lane == 31) {  // head of this image = spill of the previous chunk (unused for c == 0)
+            if (mis4 >= 1) stage[mis4 - 1] = c2;
+            if (mis4 >= 2) stage[mis4 - 2] = c1;
+            if (mis4 >= 3) stage[mis4 - 3] = c0;
+        }
         c0 = Q[M31 - 3]; c1 = Q[M31 - 2]; c2 = Q[M31 - 1];
         fence_async_smem();
         __syncwarp();
