@@ -168,3 +168,34 @@ def test_video_helpers(tmp_path):
     assert back.shape == (16 * 16, 38 * 16, 3) and int(back[0, 0, 0]) == 120
     path2 = video.make_video_from_image_dir(str(tmp_path), str(img_dir), video_name="u", fps=5)
     assert int(cv2.VideoCapture(path2).get(cv2.CAP_PROP_FRAME_COUNT)) == 6
+
+
+def test_bench_reference_arm_line():
+    """`bench.py --impl reference` (the arm the driver launches beside ours) on a tiny sample: one JSON line with the contract's
+    keys, the same `config` our arm prints, the C port as its value and -- where a reference tree is reachable -- the
+    reference's own Python step timed one process per core; and it never maps the product library."""
+    import json
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
+                          "--cpu-sample-envs", "256", "--pyref-steps", "20"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["gpu_launches"] == 0
+    sys.path.insert(0, root)
+    import bench
+    ns = type("A", (), dict(game="harvest", agents=5, envs_per_gpu=65536, view=7, gpus=1))()
+    assert line["config"] == bench.workload(ns)
+    py = line["cpu_baseline"]["python_reference"]
+    assert ("aggregate_agent_steps_per_s" in py and py["cores"] >= 1) or "unavailable" in py
+    # the reference arm is CPU only: nothing it imports loads libssd_b200.so
+    probe = subprocess.run([sys.executable, "-c",
+                            "import sys; sys.path.insert(0, %r); import bench, oracle.oracle; "
+                            "from sequential_social_dilemma_games_b200.config import make_config; "
+                            "print(any('libssd_b200' in l for l in open('/proc/self/maps')))" % root],
+                           capture_output=True, text=True, timeout=300, cwd=root)
+    assert probe.stdout.strip() == "False", probe.stdout + probe.stderr[-500:]
