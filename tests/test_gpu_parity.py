@@ -554,3 +554,43 @@ def test_specialised_equals_general_kernel(game, N, view, B):
         assert torch.equal(oa, ob), t
     assert all(torch.equal(x, y) for x, y in zip(a.get_state(), b.get_state()))
     assert a.stats() == b.stats() and a.t == b.t
+
+
+@pytest.mark.parametrize("game", ["harvest", "cleanup"])
+def test_long_run_with_resets_specialised_equals_general(game):
+    """600 steps of 4096 envs with everything that touches the incrementally maintained state in between -- masked resets,
+    row-list resets, a state download / upload, a short one-launch rollout -- stepped by the specialised kernel (orchard
+    bitmaps, running 'H' count) and by the general kernel (which rebuilds them): a bitmap or count that drifted would change
+    which cells draw, and the trajectories would part."""
+    from sequential_social_dilemma_games_b200.config import make_config
+    cfg = make_config(game)
+    B, T = 4096, 600
+    a, b = _env(cfg, B, seed=77, env_id_offset=3), _env(cfg, B, seed=77, env_id_offset=3).general_kernel_only(True)
+    a.reset(); b.reset()
+    g = torch.Generator(device="cuda").manual_seed(31)
+    ring = torch.randint(0, cfg.num_actions, (32, B, cfg.num_agents), generator=g, device="cuda", dtype=torch.int8)
+    if game == "cleanup":
+        ring[torch.rand(ring.shape, generator=g, device="cuda") < 0.3] = 8
+    mask = (torch.arange(B, device="cuda") % 7 == 0).to(torch.uint8)
+    rows = [5, 6, 7, 8, 1000, 4095]
+    for t in range(T):
+        if t % 150 == 149:
+            a.reset(mask=mask); b.reset(mask=mask)
+        if t % 100 == 50:
+            a.reset_rows(rows); b.reset_rows(rows)
+        if t == 300:
+            st = a.get_state()
+            a.set_state(*st)
+        if t == 400:
+            _, rews = a.rollout(ring[:8].contiguous())
+            for k in range(8):
+                _, rb = b.step(ring[k])
+                assert torch.equal(rews[k], rb), (t, k)
+            continue
+        oa, ra = a.step(ring[t % 32])
+        ob, rb = b.step(ring[t % 32])
+        if t % 25 == 0 or t == T - 1:
+            assert torch.equal(ra, rb) and torch.equal(oa, ob), t
+    assert all(torch.equal(x, y) for x, y in zip(a.get_state(), b.get_state()))
+    sa, sb = a.stats(), b.stats()
+    assert sa == sb and sa["apples_spawned"] > 0 and (game == "harvest" or sa["waste_spawned"] > 0)
