@@ -199,6 +199,9 @@ def main():
     record("cleanup_tape64", KIND_CLEANUP, CLEANUP_MAP, 5, 64, 200, p_clean=0.35, p_fire=0.05, seed0=100, seeded=True, obs_every=5)
     # BASELINE.json configs[3] / SURVEY 8d config 4: 64 reference envs on the 2x2-tiled map, 10 agents, P(FIRE) = P(CLEAN) = 0.25
     record("cleanup10_tiled_tape64", KIND_CLEANUP, tiled, 10, 64, 80, p_clean=0.25, p_fire=0.25, seed0=200, seeded=True, obs_every=8)
+    # BASELINE.json configs[2] (the headline workload) under the PRODUCTION random streams: 64 reference envs x 200 steps driven by
+    # the Philox streams the kernels draw from, reset() included, one mid-episode reset
+    record("harvest_philox64", KIND_HARVEST, HARVEST_MAP, 5, 64, 200, mode="philox", p_fire=0.05, seed0=300, reset_at=(120,), obs_every=10)
     record("harvest_philox", KIND_HARVEST, HARVEST_MAP, 5, 4, 100, mode="philox", p_fire=0.1, reset_at=(50,))
     record("cleanup_philox", KIND_CLEANUP, CLEANUP_MAP, 5, 4, 160, mode="philox", p_clean=0.5, reset_at=(130,))
     record("cleanup10_tiled_philox", KIND_CLEANUP, tiled, 10, 2, 90, mode="philox", p_clean=0.65, p_fire=0.1, seed0=3)

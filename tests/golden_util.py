@@ -44,6 +44,7 @@ def regenerate_tape(d):
 TAPE_FIXTURES = ["harvest_tape", "cleanup_tape", "cleanup10_tiled_tape", "harvest_dense_tape",
                  "harvest_r5_tape", "harvest_r10_tape", "cleanup_order_tape"]
 SEEDED_TAPE_FIXTURES = ["cleanup_tape64", "cleanup10_tiled_tape64"]  # 64 reference envs each, tape regenerated from MT19937 states
+PHILOX64_FIXTURES = ["harvest_philox64"]  # the headline workload: 64 reference envs driven by the production Philox streams
 PHILOX_FIXTURES = ["harvest_philox", "cleanup_philox", "cleanup10_tiled_philox"]
 
 
